@@ -1,0 +1,266 @@
+/* include/sclgpu.h -- C ABI of libsclgpu.so, the B200 (sm_100a) implementation of
+ * SCL's data-parallel hot path: batched scl::math::Fp<61>/Fp<127> arithmetic,
+ * util::PRG (AES-128-CTR) expansion, Shamir share / Lagrange reconstruct.
+ *
+ * SCL (anderspkd/secure-computation-library 0.1.0) has no FFI of its own; its
+ * batch seam is the value-semantic template API.  Every
+ * entry point below names the reference interface it replaces (paths relative
+ * to the reference root).  Conventions:
+ *
+ *  - Elements are SCL's FF::write bytes (ff.h:295-297): little-endian canonical
+ *    residues in [0,p); 8 bytes per Fp<61> element (mersenne61.cc:92-95),
+ *    16 bytes per Fp<127> element, low word first (mersenne127.cc:120-123).
+ *    Fp<127> buffers are passed as `const void*` / `void*` and must be 16-byte
+ *    aligned.  Inputs are expected canonical, as SCL's own containers hold them.
+ *  - `seed` is the 16-byte AES key exactly as PRG::create leaves it: the user
+ *    seed zero-padded / truncated to 16 bytes (prg.cc:88-101).
+ *  - `first_block` makes the PRG seekable: keystream block i is
+ *    AES_seed(LE64(i) || LE64(PRG_NONCE)) (prg.cc:82-84, prg.h:34-43) and a call
+ *    that SCL would make on a PRG whose counter is c passes first_block = c.
+ *    Each function documents how many blocks the equivalent SCL calls consume
+ *    so the caller can advance its own counter.
+ *  - Host entry points take HOST pointers; the library stages through pinned
+ *    memory and does all device work itself.  `_dev` entry points take DEVICE
+ *    pointers valid on the context's device, enqueue on the context's stream
+ *    (sclgpu_set_stream) and do not synchronise unless they return a status
+ *    that depends on device results (recover_d, lagrange).
+ *  - Return value: SCLGPU_OK or a negative code.  The mapping to the
+ *    reference's exceptions is given per code; the reference's exact what()
+ *    string for the last failure is available from sclgpu_last_error().
+ *  - One context per device per process; calls on one context are serialised
+ *    by the caller (SCL itself is single-threaded).
+ *  - There is no CPU fallback: every compute entry point fails with
+ *    SCLGPU_ECUDA if no sm_100 device is usable.
+ */
+#ifndef SCLGPU_H
+#define SCLGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCLGPU_OK 0
+#define SCLGPU_EINVAL (-1)  /* std::invalid_argument (vector.h:483, matrix.h:165,425,500) */
+#define SCLGPU_ELOGIC (-2)  /* std::logic_error: "not enough shares provided to detect errors"
+                               (shamir.h:122-124) or "0 not invertible modulo prime" (small_ff.h:70-72) */
+#define SCLGPU_EDETECT (-3) /* std::logic_error("error detected during recovery") (shamir.h:133-135)
+                               for at least one secret of the batch; see err[] */
+#define SCLGPU_ECUDA (-4)   /* CUDA runtime failure / no usable device */
+#define SCLGPU_ENOMEM (-5)  /* device or pinned-host allocation failed */
+
+/* Layout of a batch of N sharings of n shares each. */
+#define SCLGPU_SECRET_MAJOR 0 /* [N][n]: row j = the Vector SCL returns for secret j (shamir.h:60-67) */
+#define SCLGPU_PARTY_MAJOR 1  /* [n][N]: row i = party i's share of every secret (device-native SoA) */
+
+typedef struct sclgpu_ctx sclgpu_ctx;
+
+/* ---- context, memory, plumbing (no reference counterpart: SCL is CPU-only) */
+int sclgpu_init(int device, sclgpu_ctx** ctx);
+void sclgpu_destroy(sclgpu_ctx* ctx);
+/* cudaStream_t to enqueue on (NULL = the legacy default stream). */
+int sclgpu_set_stream(sclgpu_ctx* ctx, void* cuda_stream);
+int sclgpu_sync(sclgpu_ctx* ctx);
+const char* sclgpu_last_error(const sclgpu_ctx* ctx);
+const char* sclgpu_strerror(int code);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+uint64_t sclgpu_launch_count(const sclgpu_ctx* ctx);
+int sclgpu_device_info(const sclgpu_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                       size_t* free_bytes, size_t* total_bytes);
+int sclgpu_malloc(sclgpu_ctx* ctx, size_t bytes, void** dptr);
+int sclgpu_free(sclgpu_ctx* ctx, void* dptr);
+int sclgpu_host_alloc(sclgpu_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int sclgpu_host_free(sclgpu_ctx* ctx, void* hptr);
+int sclgpu_memcpy_h2d(sclgpu_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
+int sclgpu_memcpy_d2h(sclgpu_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
+
+/* ---- util::PRG ------------------------------------------------------------
+ * PRG::next(buf, n) (prg.cc:124-146): ceil(n/16) blocks starting at
+ * first_block; the first n bytes are written (the tail of the last block is
+ * discarded, as the reference does).  Consumes ceil(n/16) blocks. */
+int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                      uint64_t n_bytes, uint8_t* out);
+int sclgpu_prg_expand_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                          uint64_t n_bytes, uint8_t* d_out);
+
+/* ---- FF::read / Vector::random / FF::random ---------------------------------
+ * from_bytes: FF::read = load LE word then "% p" (ff.h:63-67,
+ *   mersenne61.cc:87-90, mersenne127.cc:115-118) on n packed elements.
+ * random:     Vector<Fp>::random(n, prg) (vector.h:508-519): ONE next() of
+ *   n*byteSize bytes; consumes ceil(n*byteSize/16) blocks.
+ * ff_random:  FF::random(prg) called n times (ff.h:72-76): one whole AES block
+ *   per element, bytes beyond byteSize dropped; consumes n blocks. */
+int sclgpu_fp61_from_bytes(sclgpu_ctx* ctx, const uint8_t* bytes, uint64_t n, uint64_t* out);
+int sclgpu_fp127_from_bytes(sclgpu_ctx* ctx, const uint8_t* bytes, uint64_t n, void* out);
+int sclgpu_fp61_random(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n,
+                       uint64_t* out);
+int sclgpu_fp127_random(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n,
+                        void* out);
+int sclgpu_fp61_ff_random(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                          uint64_t n, uint64_t* out);
+int sclgpu_fp127_ff_random(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                           uint64_t n, void* out);
+int sclgpu_fp61_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* d_bytes, uint64_t n, uint64_t* d_out);
+int sclgpu_fp127_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* d_bytes, uint64_t n, void* d_out);
+int sclgpu_fp61_random_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                           uint64_t n, uint64_t* d_out);
+int sclgpu_fp127_random_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                            uint64_t n, void* d_out);
+int sclgpu_fp61_ff_random_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                              uint64_t n, uint64_t* d_out);
+int sclgpu_fp127_ff_random_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                               uint64_t n, void* d_out);
+
+/* ---- ss::shamirSecretShare (shamir.h:52-68), called N times on one PRG ------
+ * Secret j gets the coefficients SCL would draw when its PRG counter is
+ * first_block + j*B, B = ceil((t+1)*byteSize/16) blocks per call: coefficient
+ * k (1 <= k <= t) = read(keystream bytes [k*bs,(k+1)*bs)), slot 0 is consumed
+ * and replaced by the secret (shamir.h:56-57).  shares[j][i] = f_j(i+1)
+ * (poly.h:56-64).  Consumes N*B blocks.  t >= 0, n >= 0; n < 2^31.
+ * Host version: `shares` is SCLGPU_SECRET_MAJOR (what SCL returns). */
+int sclgpu_fp61_shamir_share(sclgpu_ctx* ctx, const uint64_t* secrets, uint64_t N, uint32_t t,
+                             uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                             uint64_t* shares);
+int sclgpu_fp127_shamir_share(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t t,
+                              uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                              void* shares);
+int sclgpu_fp61_shamir_share_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N,
+                                 uint32_t t, uint32_t n, const uint8_t seed[16],
+                                 uint64_t first_block, uint64_t* d_shares, int layout);
+int sclgpu_fp127_shamir_share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_t t,
+                                  uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                  void* d_shares, int layout);
+/* Sharing from caller-supplied coefficients (Polynomial::create + evaluate,
+ * poly.h:56-64,179-198): d_coeffs is [t+1][N] (coefficient k of secret j at
+ * k*N + j), coefficient 0 being the secret.  Used to separate the PRG from the
+ * evaluation in tests and in the C4 staged pipeline. */
+int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const uint64_t* d_coeffs, uint64_t N,
+                                        uint32_t t, uint32_t n, uint64_t* d_shares, int layout);
+int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N,
+                                         uint32_t t, uint32_t n, void* d_shares, int layout);
+
+/* ---- math::computeLagrangeBasis (lagrange.h:55-71) --------------------------
+ * out[i] = prod_{j != i} (x - nodes[j]) / (nodes[i] - nodes[j]).  nodes == NULL
+ * means Vector::range(1, n+1) (vector.h:491-505).  Computed on the device.
+ * SCLGPU_ELOGIC ("0 not invertible modulo prime") if two nodes coincide. */
+int sclgpu_fp61_lagrange_basis(sclgpu_ctx* ctx, const uint64_t* nodes, uint32_t n,
+                               const uint64_t* x, uint64_t* out);
+int sclgpu_fp127_lagrange_basis(sclgpu_ctx* ctx, const void* nodes, uint32_t n, const void* x,
+                                void* out);
+
+/* ---- ss::shamirRecoverP (shamir.h:82-87, 100-104) on N sharings -------------
+ * out[j] = <shares_j, basis(alphas, x)> over ALL n shares.  alphas == NULL is
+ * the one-argument overload: alphas = 1..n, x = 0 (x is then ignored). */
+int sclgpu_fp61_recover_p(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t n,
+                          const uint64_t* alphas, const uint64_t* x, uint64_t* out);
+int sclgpu_fp127_recover_p(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n,
+                           const void* alphas, const void* x, void* out);
+/* d_shares / d_out are device pointers; alphas / x stay HOST pointers (n values). */
+int sclgpu_fp61_recover_p_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N, uint32_t n,
+                              int layout, const uint64_t* alphas, const uint64_t* x,
+                              uint64_t* d_out);
+int sclgpu_fp127_recover_p_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n,
+                               int layout, const void* alphas, const void* x, void* d_out);
+
+/* ---- ss::shamirRecoverD (shamir.h:117-140, 152-155) on N sharings -----------
+ * alphas == NULL is the (shares, t) overload: alphas = 1..2t+1, d = t, x = 0
+ * (n_alphas, d, x ignored).  Otherwise the five-argument form.
+ * SCLGPU_ELOGIC if n_given < d+t or n_alphas < d+t ("not enough shares provided
+ * to detect errors").  Exactly as the reference, only share indices
+ * d+1 .. d+t-1 are checked against the interpolation through shares 0..d.
+ * err[j] = 1 where the reference would throw "error detected during recovery"
+ * (out[j] is then 0); returns SCLGPU_EDETECT if any err[j] is set (out/err are
+ * still fully written), SCLGPU_OK otherwise.  *n_detected (nullable) receives
+ * the number of flagged secrets.  n_given = shares per secret in the buffer. */
+int sclgpu_fp61_recover_d(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t n_given,
+                          uint32_t t, const uint64_t* alphas, uint32_t n_alphas, uint32_t d,
+                          const uint64_t* x, uint64_t* out, uint8_t* err, uint64_t* n_detected);
+int sclgpu_fp127_recover_d(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n_given,
+                           uint32_t t, const void* alphas, uint32_t n_alphas, uint32_t d,
+                           const void* x, void* out, uint8_t* err, uint64_t* n_detected);
+int sclgpu_fp61_recover_d_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N,
+                              uint32_t n_given, int layout, uint32_t t, const uint64_t* alphas,
+                              uint32_t n_alphas, uint32_t d, const uint64_t* x, uint64_t* d_out,
+                              uint8_t* d_err, uint64_t* n_detected);
+int sclgpu_fp127_recover_d_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N,
+                               uint32_t n_given, int layout, uint32_t t, const void* alphas,
+                               uint32_t n_alphas, uint32_t d, const void* x, void* d_out,
+                               uint8_t* d_err, uint64_t* n_detected);
+
+/* ---- math::Vector entrywise ops (vector.h:192-301, 522-556) -----------------
+ * add / sub / mul = add / subtract / multiplyEntryWise; scale = scalarMultiply
+ * (scalar points to ONE element); dot (vector.h:252-259, innerProd :45-52) and
+ * sum (:262-267) write one element.  Size mismatch is the caller's check (the
+ * host mirror raises "Vec sizes mismatch").  muladd is the Beaver-style
+ * z = e*b + d*a + c + e*d (test/scl/protocol/beaver.h:57-61, vectorised). */
+int sclgpu_fp61_vec_add(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_sub(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_mul(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_scale(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* scalar, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_muladd(sclgpu_ctx* ctx, const uint64_t* e, const uint64_t* b, const uint64_t* d,
+                           const uint64_t* a, const uint64_t* c, uint64_t n, uint64_t* z);
+int sclgpu_fp61_dot(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_sum(sclgpu_ctx* ctx, const uint64_t* a, uint64_t n, uint64_t* out);
+int sclgpu_fp127_vec_add(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_vec_sub(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_vec_mul(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_vec_scale(sclgpu_ctx* ctx, const void* a, const void* scalar, uint64_t n, void* out);
+int sclgpu_fp127_vec_muladd(sclgpu_ctx* ctx, const void* e, const void* b, const void* d,
+                            const void* a, const void* c, uint64_t n, void* z);
+int sclgpu_fp127_dot(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_sum(sclgpu_ctx* ctx, const void* a, uint64_t n, void* out);
+/* device-pointer forms; `scalar` of vec_scale_dev is a HOST pointer, dot/sum
+ * write one element to DEVICE memory */
+int sclgpu_fp61_vec_add_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_sub_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_mul_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_scale_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* scalar, uint64_t n, uint64_t* out);
+int sclgpu_fp61_vec_muladd_dev(sclgpu_ctx* ctx, const uint64_t* e, const uint64_t* b, const uint64_t* d,
+                               const uint64_t* a, const uint64_t* c, uint64_t n, uint64_t* z);
+int sclgpu_fp61_dot_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
+int sclgpu_fp61_sum_dev(sclgpu_ctx* ctx, const uint64_t* a, uint64_t n, uint64_t* out);
+int sclgpu_fp127_vec_add_dev(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_vec_sub_dev(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_vec_mul_dev(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_vec_scale_dev(sclgpu_ctx* ctx, const void* a, const void* scalar, uint64_t n, void* out);
+int sclgpu_fp127_vec_muladd_dev(sclgpu_ctx* ctx, const void* e, const void* b, const void* d,
+                                const void* a, const void* c, uint64_t n, void* z);
+int sclgpu_fp127_dot_dev(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
+int sclgpu_fp127_sum_dev(sclgpu_ctx* ctx, const void* a, uint64_t n, void* out);
+
+/* ---- math::Matrix (matrix.h) ------------------------------------------------
+ * matvec: Matrix::multiply(Vector) (matrix.h:498-513), A row-major rows x cols
+ *   (matrix.h:199-201); SCLGPU_EINVAL when rows or cols is 0 (matrix.h:165).
+ * vandermonde: Matrix::vandermonde(n, m) with xs = 1..n (matrix.h:102-104,
+ *   445-460): out[i][j] = (i+1)^j, row-major n x m. */
+int sclgpu_fp61_matvec(sclgpu_ctx* ctx, const uint64_t* A, uint32_t rows, uint32_t cols,
+                       const uint64_t* x, uint64_t* y);
+int sclgpu_fp127_matvec(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t cols,
+                        const void* x, void* y);
+int sclgpu_fp61_matvec_dev(sclgpu_ctx* ctx, const uint64_t* d_A, uint32_t rows, uint32_t cols,
+                           const uint64_t* d_x, uint64_t* d_y);
+int sclgpu_fp127_matvec_dev(sclgpu_ctx* ctx, const void* d_A, uint32_t rows, uint32_t cols,
+                            const void* d_x, void* d_y);
+int sclgpu_fp61_vandermonde(sclgpu_ctx* ctx, uint32_t n, uint32_t m, uint64_t* out);
+int sclgpu_fp127_vandermonde(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out);
+
+/* ---- layout helpers (device) -------------------------------------------------
+ * [rows][cols] -> [cols][rows] of 8-byte (fp61) / 16-byte (fp127) elements. */
+int sclgpu_fp61_transpose_dev(sclgpu_ctx* ctx, const uint64_t* d_in, uint64_t rows, uint64_t cols,
+                              uint64_t* d_out);
+int sclgpu_fp127_transpose_dev(sclgpu_ctx* ctx, const void* d_in, uint64_t rows, uint64_t cols,
+                               void* d_out);
+
+/* ---- measurement helper -------------------------------------------------------
+ * Integer-pipe microbenchmark used for the "int-mul roofline" denominator:
+ * runs `iters` dependent-chain-free IMAD (kind 0), IMAD.WIDE.U32 (kind 1),
+ * LOP3 (kind 2), IADD3 (kind 3) or LDS.32 (kind 4) warp instructions per warp on every SM and
+ * returns the achieved thread-level operations per second in *ops_per_s. */
+int sclgpu_pipe_microbench(sclgpu_ctx* ctx, int kind, uint32_t iters, double* ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCLGPU_H */

@@ -1,0 +1,334 @@
+"""Host-side handle on libsclgpu.so: one `Context` per GPU per process.
+
+Two families of methods, both thin wrappers over the C ABI (include/sclgpu.h):
+
+* host methods take / return numpy arrays in SCL's FF::write layout (Fp<61> ->
+  uint64[...]; Fp<127> -> uint64[..., 2] = low word, high word) and go through the
+  library's own pinned / chunked H2D-compute-D2H pipelines;
+* ``*_dev`` methods take torch CUDA tensors (int64 storage, same bit layout) and
+  enqueue on torch's current stream -- torch is only the allocator / stream owner.
+
+Errors mirror the reference: SCLGPU_EINVAL -> InvalidArgument (std::invalid_argument),
+SCLGPU_ELOGIC / EDETECT -> LogicError (std::logic_error) carrying the reference's
+what() string.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import binding as B
+
+P61 = (1 << 61) - 1
+P127 = (1 << 127) - 1
+PRIME = {61: P61, 127: P127}
+_SUF = {61: "fp61", 127: "fp127"}
+
+
+class InvalidArgument(ValueError):
+    """std::invalid_argument"""
+
+
+class LogicError(RuntimeError):
+    """std::logic_error"""
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def seed16(seed) -> bytes:
+    """PRG::create(seed): zero-pad / truncate to 16 bytes (prg.cc:88-101)."""
+    if isinstance(seed, str):
+        seed = seed.encode()
+    seed = bytes(seed)[:16]
+    return seed + b"\0" * (16 - len(seed))
+
+
+def elem_shape(field: int):
+    return () if field == 61 else (2,)
+
+
+def empty(field: int, *shape) -> np.ndarray:
+    return np.zeros(tuple(shape) + elem_shape(field), dtype=np.uint64)
+
+
+def from_ints(vals, field: int) -> np.ndarray:
+    vals = np.asarray(vals, dtype=object)
+    flat = [int(v) for v in vals.reshape(-1)]
+    if field == 61:
+        return np.array(flat, dtype=np.uint64).reshape(vals.shape)
+    out = np.array([[v & 0xFFFFFFFFFFFFFFFF, v >> 64] for v in flat], dtype=np.uint64)
+    return out.reshape(vals.shape + (2,))
+
+
+def to_ints(arr, field: int):
+    arr = np.asarray(arr, dtype=np.uint64)
+    if field == 61:
+        return np.array([int(v) for v in arr.reshape(-1)], dtype=object).reshape(arr.shape)
+    flat = arr.reshape(-1, 2)
+    return np.array([int(lo) | (int(hi) << 64) for lo, hi in flat], dtype=object).reshape(arr.shape[:-1])
+
+
+def blocks_per_share_call(field: int, t: int) -> int:
+    """Keystream blocks one shamirSecretShare call consumes: ceil((t+1)*byteSize/16)."""
+    bs = 8 if field == 61 else 16
+    return ((t + 1) * bs + 15) // 16
+
+
+def _c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _nelem(a: np.ndarray, field: int) -> int:
+    return a.size if field == 61 else a.size // 2
+
+
+def _dp(t):
+    """device pointer of a torch tensor (or None)"""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise InvalidArgument("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = B.load()
+        self._ctx = C.c_void_p()
+        rc = self.lib.sclgpu_init(int(device), C.byref(self._ctx))
+        if rc != B.OK:
+            self._ctx = None
+            raise CudaError(
+                f"sclgpu_init(device={device}) failed: {self.lib.sclgpu_strerror(rc).decode()} "
+                "(libsclgpu needs a CUDA device; there is no CPU fallback)"
+            )
+        self.device = int(device)
+
+    # ------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.sclgpu_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow=()):
+        if rc == B.OK or rc in allow:
+            return rc
+        msg = self.lib.sclgpu_last_error(self._ctx).decode(errors="replace")
+        if rc == B.EINVAL:
+            raise InvalidArgument(msg)
+        if rc in (B.ELOGIC, B.EDETECT):
+            raise LogicError(msg)
+        raise CudaError(f"{self.lib.sclgpu_strerror(rc).decode()}: {msg}")
+
+    def _f(self, field: int, name: str):
+        return getattr(self.lib, f"sclgpu_{_SUF[field]}_{name}")
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self.lib.sclgpu_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def use_torch_stream(self):
+        import torch
+
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self._check(self.lib.sclgpu_sync(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.sclgpu_launch_count(self._ctx))
+
+    def device_info(self) -> dict:
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        fr, tot = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.sclgpu_device_info(self._ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(fr), C.byref(tot)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "free": fr.value, "total": tot.value}
+
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """pinned host buffer as a uint8 numpy array (freed with host_free)"""
+        p = C.c_void_p()
+        self._check(self.lib.sclgpu_host_alloc(self._ctx, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        arr._sclgpu_ptr = p  # type: ignore[attr-defined]
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        base = arr
+        while getattr(base, "base", None) is not None and not hasattr(base, "_sclgpu_ptr"):
+            base = base.base
+        self._check(self.lib.sclgpu_host_free(self._ctx, C.c_void_p(arr.ctypes.data)))
+
+    def pipe_microbench(self, kind: int, iters: int = 4096) -> float:
+        v = C.c_double()
+        self._check(self.lib.sclgpu_pipe_microbench(self._ctx, kind, iters, C.byref(v)))
+        return v.value
+
+    # ------------------------------------------------------------ PRG
+    def prg_expand(self, seed, first_block: int, n_bytes: int) -> np.ndarray:
+        out = np.zeros(n_bytes, dtype=np.uint8)
+        self._check(self.lib.sclgpu_prg_expand(self._ctx, seed16(seed), first_block, n_bytes, _p(out)))
+        return out
+
+    def prg_expand_dev(self, seed, first_block: int, n_bytes: int, out):
+        self._check(self.lib.sclgpu_prg_expand_dev(self._ctx, seed16(seed), first_block, n_bytes, _dp(out)))
+
+    def from_bytes(self, field: int, raw) -> np.ndarray:
+        bs = 8 if field == 61 else 16
+        src = np.frombuffer(bytes(raw), dtype=np.uint8).copy() if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw, dtype=np.uint8)
+        n = src.size // bs
+        out = empty(field, n)
+        self._check(self._f(field, "from_bytes")(self._ctx, _p(src), n, _p(out)))
+        return out
+
+    def random(self, field: int, seed, first_block: int, n: int) -> np.ndarray:
+        out = empty(field, n)
+        self._check(self._f(field, "random")(self._ctx, seed16(seed), first_block, n, _p(out)))
+        return out
+
+    # oracle-compatible aliases
+    vector_random = random
+
+    def ff_random(self, field: int, seed, first_block: int, n: int) -> np.ndarray:
+        out = empty(field, n)
+        self._check(self._f(field, "ff_random")(self._ctx, seed16(seed), first_block, n, _p(out)))
+        return out
+
+    def random_dev(self, field: int, seed, first_block: int, n: int, out):
+        self._check(self._f(field, "random_dev")(self._ctx, seed16(seed), first_block, n, _dp(out)))
+
+    def ff_random_dev(self, field: int, seed, first_block: int, n: int, out):
+        self._check(self._f(field, "ff_random_dev")(self._ctx, seed16(seed), first_block, n, _dp(out)))
+
+    # ------------------------------------------------------------ Shamir
+    def shamir_share(self, field: int, secrets, t: int, n: int, seed, first_block: int = 0) -> np.ndarray:
+        secrets = _c(secrets)
+        N = _nelem(secrets, field)
+        out = empty(field, N, n)
+        self._check(self._f(field, "shamir_share")(self._ctx, _p(secrets), N, t, n, seed16(seed), first_block, _p(out)))
+        return out
+
+    def shamir_share_dev(self, field: int, secrets, N: int, t: int, n: int, seed, first_block: int, shares,
+                         layout: int = B.PARTY_MAJOR):
+        self._check(self._f(field, "shamir_share_dev")(self._ctx, _dp(secrets), N, t, n, seed16(seed), first_block, _dp(shares), layout))
+
+    def shamir_share_coeffs_dev(self, field: int, coeffs, N: int, t: int, n: int, shares, layout: int = B.PARTY_MAJOR):
+        self._check(self._f(field, "shamir_share_coeffs_dev")(self._ctx, _dp(coeffs), N, t, n, _dp(shares), layout))
+
+    def lagrange(self, field: int, nodes, x: int, n: int | None = None) -> np.ndarray:
+        nodes_a = None if nodes is None else _c(nodes)
+        n = _nelem(nodes_a, field) if nodes_a is not None else int(n)
+        X = from_ints([x], field)
+        out = empty(field, n)
+        self._check(self._f(field, "lagrange_basis")(self._ctx, _p(nodes_a), n, _p(X), _p(out)))
+        return out
+
+    def recover_p(self, field: int, shares, alphas=None, x: int | None = None) -> np.ndarray:
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        out = empty(field, N)
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], field)
+        self._check(self._f(field, "recover_p")(self._ctx, _p(shares), N, n, _p(A), _p(X), _p(out)))
+        return out
+
+    def recover_p_dev(self, field: int, shares, N: int, n: int, out, layout: int = B.PARTY_MAJOR, alphas=None,
+                      x: int | None = None):
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], field)
+        self._check(self._f(field, "recover_p_dev")(self._ctx, _dp(shares), N, n, layout, _p(A), _p(X), _dp(out)))
+
+    def recover_d(self, field: int, shares, t: int, alphas=None, d: int | None = None, x: int | None = None):
+        """-> (secrets, err uint8[N], rc) with rc = -1 for "not enough shares provided to
+        detect errors", else the number of secrets flagged (oracle-compatible)."""
+        shares = _c(shares)
+        N, n_given = shares.shape[0], shares.shape[1]
+        out = empty(field, N)
+        err = np.zeros(N, dtype=np.uint8)
+        A = None if alphas is None else _c(alphas)
+        n_alphas = 0 if A is None else _nelem(A, field)
+        X = from_ints([x or 0], field)
+        nd = C.c_uint64(0)
+        rc = self._f(field, "recover_d")(self._ctx, _p(shares), N, n_given, t, _p(A), n_alphas,
+                                          d if d is not None else t, _p(X), _p(out), _p(err), C.byref(nd))
+        if rc == B.ELOGIC:
+            return out, err, -1
+        self._check(rc, allow=(B.EDETECT,))
+        return out, err, int(nd.value)
+
+    def recover_d_dev(self, field: int, shares, N: int, n_given: int, t: int, out, err, layout: int = B.PARTY_MAJOR,
+                      alphas=None, d: int | None = None, x: int | None = None) -> int:
+        A = None if alphas is None else _c(alphas)
+        n_alphas = 0 if A is None else _nelem(A, field)
+        X = from_ints([x or 0], field)
+        nd = C.c_uint64(0)
+        rc = self._f(field, "recover_d_dev")(self._ctx, _dp(shares), N, n_given, layout, t, _p(A), n_alphas,
+                                              d if d is not None else t, _p(X), _dp(out), _dp(err), C.byref(nd))
+        self._check(rc, allow=(B.EDETECT,))
+        return int(nd.value)
+
+    # ------------------------------------------------------------ Vector / Matrix
+    _OPS = {0: "vec_add", 1: "vec_sub", 2: "vec_mul", 3: "vec_scale", 4: "dot", 5: "sum"}
+
+    def vec_op(self, field: int, op: int, a, b=None) -> np.ndarray:
+        """op: 0 add 1 subtract 2 multiplyEntryWise 3 scalarMultiply(b[0]) 4 dot 5 sum"""
+        a = _c(a)
+        n = _nelem(a, field)
+        out = empty(field, 1 if op in (4, 5) else n)
+        f = self._f(field, self._OPS[op])
+        if op == 5:
+            self._check(f(self._ctx, _p(a), n, _p(out)))
+        else:
+            b = _c(b)
+            self._check(f(self._ctx, _p(a), _p(b), n, _p(out)))
+        return out
+
+    def vec_op_dev(self, field: int, op: int, a, b, n: int, out):
+        f = self._f(field, self._OPS[op] + "_dev")
+        if op == 5:
+            self._check(f(self._ctx, _dp(a), n, _dp(out)))
+        elif op == 3:
+            self._check(f(self._ctx, _dp(a), _p(_c(b)), n, _dp(out)))
+        else:
+            self._check(f(self._ctx, _dp(a), _dp(b), n, _dp(out)))
+
+    def beaver(self, field: int, e, b, d, a, c) -> np.ndarray:
+        e, b, d, a, c = map(_c, (e, b, d, a, c))
+        n = _nelem(e, field)
+        z = empty(field, n)
+        self._check(self._f(field, "vec_muladd")(self._ctx, _p(e), _p(b), _p(d), _p(a), _p(c), n, _p(z)))
+        return z
+
+    def beaver_dev(self, field: int, e, b, d, a, c, n: int, z):
+        self._check(self._f(field, "vec_muladd_dev")(self._ctx, _dp(e), _dp(b), _dp(d), _dp(a), _dp(c), n, _dp(z)))
+
+    def matvec(self, field: int, A, x) -> np.ndarray:
+        A, x = _c(A), _c(x)
+        rows, cols = A.shape[0], A.shape[1]
+        y = empty(field, rows)
+        self._check(self._f(field, "matvec")(self._ctx, _p(A), rows, cols, _p(x), _p(y)))
+        return y
+
+    def matvec_dev(self, field: int, A, rows: int, cols: int, x, y):
+        self._check(self._f(field, "matvec_dev")(self._ctx, _dp(A), rows, cols, _dp(x), _dp(y)))
+
+    def vandermonde(self, field: int, n: int, m: int) -> np.ndarray:
+        out = empty(field, n, m)
+        self._check(self._f(field, "vandermonde")(self._ctx, n, m, _p(out)))
+        return out
+
+    def transpose_dev(self, field: int, src, rows: int, cols: int, dst):
+        self._check(self._f(field, "transpose_dev")(self._ctx, _dp(src), rows, cols, _dp(dst)))

@@ -1,0 +1,131 @@
+// aes_ctr.cuh -- AES-128-CTR keystream of scl::util::PRG on sm_100a.
+//
+// Reference behaviour (src/scl/util/prg.cc:82-84, 124-146; include/scl/util/prg.h:34-43):
+//   block i = AES128_seed( LE64(i) || LE64(PRG_NONCE) ),  PRG_NONCE = 0x0123456789ABCDEF,
+//   counter starts at PRG_INITIAL_COUNTER = 0 and advances by one per block.
+// The reference uses AES-NI; here AES-128 (FIPS-197) is done with four T-tables
+// in shared memory.  Layout (DESIGN.md "AES tables"): every table is replicated
+// once per lane so that lane l only ever touches bank l -- conflict-free for any
+// index pattern -- and the row stride is 256 bytes so that ONE byte-permute
+// (PRMT) builds a lookup address from a state byte:
+//
+//   byte address = tbase + idx*256 + (tbl&1)*128 + lane*4 + (tbl>>1)*65536
+//                  ^^^^^ 64 KiB aligned: address byte 1 is exactly idx
+//
+// State/round-key words are little-endian column words (byte 0 = row 0).
+#pragma once
+#include <cstdint>
+
+namespace sclgpu {
+
+struct AesKey {
+  uint32_t rk[44];  // 11 round keys x 4 LE column words (host-expanded, prg.cc:54-75)
+};
+
+static constexpr uint32_t kPrgNonceLo = 0x89ABCDEFu;  // PRG_NONCE, prg.h:34-36
+static constexpr uint32_t kPrgNonceHi = 0x01234567u;
+static constexpr uint32_t kAesTableBytes = 128u * 1024u;  // 4 tables x 256 rows x 32 lanes x 4 B
+static constexpr uint32_t kAesTableAlign = 64u * 1024u;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// First 64 KiB-aligned shared address at or after `dyn` (the dynamic smem base).
+__device__ __forceinline__ uint32_t aes_table_base(const void* dyn) {
+  return (smem_u32(dyn) + (kAesTableAlign - 1)) & ~(kAesTableAlign - 1);
+}
+
+// Cooperative fill of the replicated tables from T0 (256 words in global memory):
+// T0[x] = (2s, s, s, 3s) LE, T1/T2/T3 = T0 rotated left by 8/16/24 bits.
+__device__ __forceinline__ void aes_fill_tables(uint32_t tbase, const uint32_t* __restrict__ g_t0) {
+  for (uint32_t e = threadIdx.x; e < 256u * 32u; e += blockDim.x) {
+    const uint32_t idx = e >> 5, l = e & 31u;
+    const uint32_t t0 = __ldg(g_t0 + idx);
+    const uint32_t t1 = __funnelshift_l(t0, t0, 8);
+    const uint32_t t2 = __funnelshift_l(t0, t0, 16);
+    const uint32_t t3 = __funnelshift_l(t0, t0, 24);
+    const uint32_t a = tbase + idx * 256u + l * 4u;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(t0) : "memory");
+    asm volatile("st.shared.u32 [%0+128], %1;" ::"r"(a), "r"(t1) : "memory");
+    asm volatile("st.shared.u32 [%0+65536], %1;" ::"r"(a), "r"(t2) : "memory");
+    asm volatile("st.shared.u32 [%0+65664], %1;" ::"r"(a), "r"(t3) : "memory");
+  }
+}
+
+template <int OFF>
+__device__ __forceinline__ uint32_t aes_lds(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+
+// lookup address for byte K of w: (lanebase with byte 1 replaced by that byte)
+template <int K>
+__device__ __forceinline__ uint32_t aes_addr(uint32_t w, uint32_t lanebase) {
+  return __byte_perm(w, lanebase, 0x7604 | (K << 4));
+}
+
+// One AES-128 block.  lanebase = tbase + lane*4 (byte 1 zero).
+__device__ __forceinline__ void aes128_encrypt(const AesKey& key, uint32_t lanebase, uint32_t s0,
+                                               uint32_t s1, uint32_t s2, uint32_t s3,
+                                               uint32_t& o0, uint32_t& o1, uint32_t& o2,
+                                               uint32_t& o3) {
+  s0 ^= key.rk[0];
+  s1 ^= key.rk[1];
+  s2 ^= key.rk[2];
+  s3 ^= key.rk[3];
+#pragma unroll
+  for (int r = 1; r < 10; ++r) {
+    const uint32_t a00 = aes_addr<0>(s0, lanebase), a01 = aes_addr<1>(s0, lanebase),
+                   a02 = aes_addr<2>(s0, lanebase), a03 = aes_addr<3>(s0, lanebase);
+    const uint32_t a10 = aes_addr<0>(s1, lanebase), a11 = aes_addr<1>(s1, lanebase),
+                   a12 = aes_addr<2>(s1, lanebase), a13 = aes_addr<3>(s1, lanebase);
+    const uint32_t a20 = aes_addr<0>(s2, lanebase), a21 = aes_addr<1>(s2, lanebase),
+                   a22 = aes_addr<2>(s2, lanebase), a23 = aes_addr<3>(s2, lanebase);
+    const uint32_t a30 = aes_addr<0>(s3, lanebase), a31 = aes_addr<1>(s3, lanebase),
+                   a32 = aes_addr<2>(s3, lanebase), a33 = aes_addr<3>(s3, lanebase);
+    // column j = T0[b0(s_j)] ^ T1[b1(s_j+1)] ^ T2[b2(s_j+2)] ^ T3[b3(s_j+3)] ^ rk
+    const uint32_t t0 = aes_lds<0>(a00) ^ aes_lds<128>(a11) ^ aes_lds<65536>(a22) ^
+                        aes_lds<65664>(a33) ^ key.rk[4 * r + 0];
+    const uint32_t t1 = aes_lds<0>(a10) ^ aes_lds<128>(a21) ^ aes_lds<65536>(a32) ^
+                        aes_lds<65664>(a03) ^ key.rk[4 * r + 1];
+    const uint32_t t2 = aes_lds<0>(a20) ^ aes_lds<128>(a31) ^ aes_lds<65536>(a02) ^
+                        aes_lds<65664>(a13) ^ key.rk[4 * r + 2];
+    const uint32_t t3 = aes_lds<0>(a30) ^ aes_lds<128>(a01) ^ aes_lds<65536>(a12) ^
+                        aes_lds<65664>(a23) ^ key.rk[4 * r + 3];
+    s0 = t0;
+    s1 = t1;
+    s2 = t2;
+    s3 = t3;
+  }
+  // final round: SubBytes + ShiftRows + AddRoundKey.  S[x] sits in byte 0 of T2/T3,
+  // byte 1 of T0/T3, byte 2 of T0/T1, byte 3 of T1/T2.
+  {
+    const uint32_t a00 = aes_addr<0>(s0, lanebase), a01 = aes_addr<1>(s0, lanebase),
+                   a02 = aes_addr<2>(s0, lanebase), a03 = aes_addr<3>(s0, lanebase);
+    const uint32_t a10 = aes_addr<0>(s1, lanebase), a11 = aes_addr<1>(s1, lanebase),
+                   a12 = aes_addr<2>(s1, lanebase), a13 = aes_addr<3>(s1, lanebase);
+    const uint32_t a20 = aes_addr<0>(s2, lanebase), a21 = aes_addr<1>(s2, lanebase),
+                   a22 = aes_addr<2>(s2, lanebase), a23 = aes_addr<3>(s2, lanebase);
+    const uint32_t a30 = aes_addr<0>(s3, lanebase), a31 = aes_addr<1>(s3, lanebase),
+                   a32 = aes_addr<2>(s3, lanebase), a33 = aes_addr<3>(s3, lanebase);
+#define SCLGPU_AES_LAST(x0, x1, x2, x3)                                               \
+  __byte_perm(__byte_perm(aes_lds<65536>(x0), aes_lds<65664>(x1), 0x0050),            \
+              __byte_perm(aes_lds<0>(x2), aes_lds<128>(x3), 0x7200), 0x7610)
+    o0 = SCLGPU_AES_LAST(a00, a11, a22, a33) ^ key.rk[40];
+    o1 = SCLGPU_AES_LAST(a10, a21, a32, a03) ^ key.rk[41];
+    o2 = SCLGPU_AES_LAST(a20, a31, a02, a13) ^ key.rk[42];
+    o3 = SCLGPU_AES_LAST(a30, a01, a12, a23) ^ key.rk[43];
+#undef SCLGPU_AES_LAST
+  }
+}
+
+// keystream block `ctr` of the PRG (prg.cc:82-84): plaintext = LE64(ctr) || LE64(nonce)
+__device__ __forceinline__ void prg_block(const AesKey& key, uint32_t lanebase, uint64_t ctr,
+                                          uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+  aes128_encrypt(key, lanebase, (uint32_t)ctr, (uint32_t)(ctr >> 32), kPrgNonceLo, kPrgNonceHi, o0,
+                 o1, o2, o3);
+}
+
+}  // namespace sclgpu

@@ -1,0 +1,1116 @@
+// sclgpu.cu -- host side of libsclgpu.so: context, launch logic, the C ABI of
+// include/sclgpu.h.  Pure CUDA runtime; no torch types cross this boundary.
+//
+// Host-side arithmetic is limited to the AES-128 key schedule (PRG::create /
+// aes128LoadKey, src/scl/util/prg.cc:54-101); all field arithmetic, including the
+// Lagrange bases, runs on the device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/sclgpu.h"
+#include "kernels.cuh"
+
+using namespace sclgpu;
+
+// ------------------------------------------------------------------ context
+struct sclgpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;      // user stream for _dev entry points
+  cudaStream_t pipe[2] = {nullptr, nullptr};  // host-pointer pipelines
+  cudaEvent_t pipe_ev[2] = {nullptr, nullptr};
+  uint32_t* d_t0 = nullptr;           // AES T0 table (256 words)
+  int* d_flag = nullptr;              // lagrange "zero denominator" flag
+  unsigned long long* d_count = nullptr;  // recover_d error counter
+  void* d_partial = nullptr;          // dot/sum partials (kMaxPartials elements of 16 B)
+  uint64_t launches = 0;
+  std::string last_error;
+  std::set<const void*> smem_opted;   // kernels with the 192 KiB opt-in done
+  std::map<std::string, void*> basis_cache;  // (field, nodes, xs) -> device matrix
+};
+
+static constexpr int kMaxPartials = 2048;
+static constexpr uint64_t kHostChunk = 1ull << 21;  // secrets per pipeline chunk
+
+static int fail(sclgpu_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+static int cuda_fail(sclgpu_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, e == cudaErrorMemoryAllocation ? SCLGPU_ENOMEM : SCLGPU_ECUDA,
+              std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                   \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);     \
+  } while (0)
+#define CKL()                                                      \
+  do {                                                             \
+    ctx->launches++;                                               \
+    cudaError_t e__ = cudaGetLastError();                          \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, "launch");  \
+  } while (0)
+#define RET(x)                       \
+  do {                               \
+    int rc__ = (x);                  \
+    if (rc__ != SCLGPU_OK) return rc__; \
+  } while (0)
+
+// ------------------------------------------------- AES-128 host key schedule
+// FIPS-197 5.2 (== aes128LoadKey, prg.cc:54-75).  S-box from its definition.
+static uint8_t g_sbox[256];
+static uint32_t g_t0[256];
+static bool g_aes_ready = false;
+
+static void aes_host_init() {
+  if (g_aes_ready) return;
+  uint8_t p = 1, q = 1;
+  do {
+    p = (uint8_t)(p ^ (p << 1) ^ ((p & 0x80) ? 0x1b : 0));
+    q ^= (uint8_t)(q << 1);
+    q ^= (uint8_t)(q << 2);
+    q ^= (uint8_t)(q << 4);
+    if (q & 0x80) q ^= 0x09;
+    const uint8_t x = (uint8_t)(q ^ (uint8_t)(q << 1 | q >> 7) ^ (uint8_t)(q << 2 | q >> 6) ^
+                                (uint8_t)(q << 3 | q >> 5) ^ (uint8_t)(q << 4 | q >> 4));
+    g_sbox[p] = (uint8_t)(x ^ 0x63);
+  } while (p != 1);
+  g_sbox[0] = 0x63;
+  for (int i = 0; i < 256; ++i) {
+    const uint8_t s = g_sbox[i];
+    const uint8_t s2 = (uint8_t)((s << 1) ^ ((s >> 7) * 0x1b));
+    const uint8_t s3 = (uint8_t)(s2 ^ s);
+    g_t0[i] = (uint32_t)s2 | ((uint32_t)s << 8) | ((uint32_t)s << 16) | ((uint32_t)s3 << 24);
+  }
+  g_aes_ready = true;
+}
+
+static AesKey aes_expand(const uint8_t seed[16]) {
+  static const uint8_t rcon[10] = {0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36};
+  AesKey k;
+  for (int i = 0; i < 4; ++i) std::memcpy(&k.rk[i], seed + 4 * i, 4);
+  for (int i = 4; i < 44; ++i) {
+    uint32_t t = k.rk[i - 1];
+    if ((i & 3) == 0) {
+      t = (t >> 8) | (t << 24);
+      t = (uint32_t)g_sbox[t & 0xff] | ((uint32_t)g_sbox[(t >> 8) & 0xff] << 8) |
+          ((uint32_t)g_sbox[(t >> 16) & 0xff] << 16) | ((uint32_t)g_sbox[t >> 24] << 24);
+      t ^= rcon[i / 4 - 1];
+    }
+    k.rk[i] = k.rk[i - 4] ^ t;
+  }
+  return k;
+}
+
+// ------------------------------------------------------------ launch helpers
+static int grid_for(const sclgpu_ctx* ctx, uint64_t work, int threads, int ctas_per_sm) {
+  uint64_t g = (work + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)ctx->sm_count * ctas_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <class K>
+static int aes_opt_in(sclgpu_ctx* ctx, K kernel) {
+  const void* f = reinterpret_cast<const void*>(kernel);
+  if (ctx->smem_opted.count(f)) return SCLGPU_OK;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAesDynSmem));
+  ctx->smem_opted.insert(f);
+  return SCLGPU_OK;
+}
+
+// ------------------------------------------------------------ context / memory
+extern "C" int sclgpu_init(int device, sclgpu_ctx** out) {
+  if (!out) return SCLGPU_EINVAL;
+  *out = nullptr;
+  sclgpu_ctx* ctx = new sclgpu_ctx();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    delete ctx;
+    return SCLGPU_ECUDA;  // no CPU fallback
+  }
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return SCLGPU_ECUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  aes_host_init();
+  bool ok = cudaMalloc(&ctx->d_t0, sizeof(g_t0)) == cudaSuccess &&
+            cudaMemcpy(ctx->d_t0, g_t0, sizeof(g_t0), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMalloc(&ctx->d_flag, sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&ctx->d_count, sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc(&ctx->d_partial, kMaxPartials * 16) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    sclgpu_destroy(ctx);
+    return SCLGPU_ECUDA;
+  }
+  *out = ctx;
+  return SCLGPU_OK;
+}
+
+extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+    if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
+  }
+  cudaFree(ctx->d_t0);
+  cudaFree(ctx->d_flag);
+  cudaFree(ctx->d_count);
+  cudaFree(ctx->d_partial);
+  delete ctx;
+}
+
+extern "C" int sclgpu_set_stream(sclgpu_ctx* ctx, void* s) {
+  if (!ctx) return SCLGPU_EINVAL;
+  ctx->stream = (cudaStream_t)s;
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_sync(sclgpu_ctx* ctx) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCLGPU_OK;
+}
+extern "C" const char* sclgpu_last_error(const sclgpu_ctx* ctx) {
+  return ctx ? ctx->last_error.c_str() : "no context";
+}
+extern "C" const char* sclgpu_strerror(int code) {
+  switch (code) {
+    case SCLGPU_OK: return "ok";
+    case SCLGPU_EINVAL: return "invalid argument";
+    case SCLGPU_ELOGIC: return "logic error";
+    case SCLGPU_EDETECT: return "error detected during recovery";
+    case SCLGPU_ECUDA: return "CUDA failure or no usable device";
+    case SCLGPU_ENOMEM: return "out of memory";
+    default: return "unknown";
+  }
+}
+extern "C" uint64_t sclgpu_launch_count(const sclgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int sclgpu_device_info(const sclgpu_ctx* ctx_, int* sm, int* maj, int* min, size_t* fr,
+                                  size_t* tot) {
+  sclgpu_ctx* ctx = const_cast<sclgpu_ctx*>(ctx_);
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  if (sm) *sm = ctx->sm_count;
+  if (maj) *maj = ctx->cc_major;
+  if (min) *min = ctx->cc_minor;
+  if (fr) *fr = f;
+  if (tot) *tot = t;
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_malloc(sclgpu_ctx* ctx, size_t bytes, void** p) {
+  if (!ctx || !p) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(p, bytes ? bytes : 1));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_free(sclgpu_ctx* ctx, void* p) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(p));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_host_alloc(sclgpu_ctx* ctx, size_t bytes, void** p) {
+  if (!ctx || !p) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_host_free(sclgpu_ctx* ctx, void* p) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaFreeHost(p));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_memcpy_h2d(sclgpu_ctx* ctx, void* d, const void* h, size_t bytes) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_memcpy_d2h(sclgpu_ctx* ctx, void* h, const void* d, size_t bytes) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCLGPU_OK;
+}
+
+// RAII device scratch
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// ============================================================ device-level ops
+// (stream passed explicitly so the host pipelines can use their own)
+
+static int prg_bytes_on(sclgpu_ctx* ctx, cudaStream_t st, const uint8_t seed[16], uint64_t first_block,
+                        uint64_t n_bytes, uint8_t* d_out) {
+  if (n_bytes == 0) return SCLGPU_OK;
+  RET(aes_opt_in(ctx, k_prg_bytes));
+  const AesKey key = aes_expand(seed);
+  const int grid = grid_for(ctx, (n_bytes + 15) / 16, kAesThreads, 1);
+  k_prg_bytes<<<grid, kAesThreads, kAesDynSmem, st>>>(key, ctx->d_t0, first_block, n_bytes, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F, bool ONE>
+static int random_on(sclgpu_ctx* ctx, cudaStream_t st, const uint8_t seed[16], uint64_t first_block,
+                     uint64_t n, typename F::E* d_out) {
+  if (n == 0) return SCLGPU_OK;
+  RET(aes_opt_in(ctx, k_random<F, ONE>));
+  const AesKey key = aes_expand(seed);
+  const int grid = grid_for(ctx, n, kAesThreads, 1);
+  k_random<F, ONE><<<grid, kAesThreads, kAesDynSmem, st>>>(key, ctx->d_t0, first_block, n, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int from_bytes_on(sclgpu_ctx* ctx, cudaStream_t st, const uint8_t* d_bytes, uint64_t n,
+                         typename F::E* d_out) {
+  if (n == 0) return SCLGPU_OK;
+  k_from_bytes<F><<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(d_bytes, n, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F, int T>
+static int share_fused_launch(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t first_block,
+                              const typename F::E* d_secrets, uint64_t N, uint32_t n,
+                              typename F::E* d_out, uint64_t si, uint64_t sj) {
+  RET(aes_opt_in(ctx, k_share_fused<F, T>));
+  const int grid = grid_for(ctx, N, kAesThreads, 1);
+  k_share_fused<F, T><<<grid, kAesThreads, kAesDynSmem, st>>>(key, ctx->d_t0, first_block, d_secrets, N,
+                                                             n, d_out, si, sj);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static constexpr int max_fused_t() {
+  return F::BYTES == 8 ? 16 : 8;
+}
+
+template <class F>
+static int share_coeffs_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_coeffs, uint64_t N,
+                           uint32_t t, uint32_t n, typename F::E* d_out, uint64_t si, uint64_t sj) {
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  k_share_coeffs<F><<<grid_for(ctx, N, 256, 8), 256, 0, st>>>(d_coeffs, N, t, n, d_out, si, sj);
+  CKL();
+  return SCLGPU_OK;
+}
+
+// party-major / strided share of N secrets (out index = i*si + j*sj)
+template <class F>
+static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_secrets, uint64_t N,
+                            uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                            typename F::E* d_out, uint64_t si, uint64_t sj) {
+  typedef typename F::E E;
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const AesKey key = aes_expand(seed);
+#define SCLGPU_CASE(TT) \
+  case TT: return share_fused_launch<F, (TT <= max_fused_t<F>() ? TT : 0)>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
+  if ((int)t <= max_fused_t<F>()) {
+    switch (t) {
+      SCLGPU_CASE(0) SCLGPU_CASE(1) SCLGPU_CASE(2) SCLGPU_CASE(3) SCLGPU_CASE(4) SCLGPU_CASE(5)
+      SCLGPU_CASE(6) SCLGPU_CASE(7) SCLGPU_CASE(8) SCLGPU_CASE(9) SCLGPU_CASE(10) SCLGPU_CASE(11)
+      SCLGPU_CASE(12) SCLGPU_CASE(13) SCLGPU_CASE(14) SCLGPU_CASE(15) SCLGPU_CASE(16)
+      default: break;
+    }
+  }
+#undef SCLGPU_CASE
+  // any other threshold: keystream -> coefficient planes -> evaluation, in
+  // chunks that keep the planes below ~1 GiB
+  const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
+  uint64_t chunk = (1ull << 30) / ((uint64_t)(t + 1) * sizeof(E));
+  if (chunk < 1024) chunk = 1024;
+  if (chunk > N) chunk = N;
+  DevBuf planes;
+  CK(planes.alloc(chunk * (uint64_t)(t + 1) * sizeof(E)));
+  RET(aes_opt_in(ctx, k_expand_coeffs<F>));
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    k_expand_coeffs<F><<<grid_for(ctx, nc, kAesThreads, 1), kAesThreads, kAesDynSmem, st>>>(
+        key, ctx->d_t0, first_block + c0 * B, d_secrets + c0, nc, t, planes.as<E>());
+    CKL();
+    RET(share_coeffs_on<F>(ctx, st, planes.as<E>(), nc, t, n, d_out + c0 * sj, si, sj));
+  }
+  CK(cudaStreamSynchronize(st));  // planes is freed on return
+  return SCLGPU_OK;
+}
+
+template <class E>
+static int transpose_on(sclgpu_ctx* ctx, cudaStream_t st, const E* d_in, uint64_t rows, uint64_t cols,
+                        E* d_out) {
+  if (rows == 0 || cols == 0) return SCLGPU_OK;
+  const uint64_t tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16);
+  k_transpose<E><<<grid, 256, 0, st>>>(d_in, rows, cols, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+// Lagrange rows on the device, cached per (field, nodes, xs).  nodes == nullptr
+// -> 1..m.  Returns a device matrix rows x m.
+template <class F>
+static int basis_rows(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* nodes, uint32_t m,
+                      const typename F::E* xs, uint32_t rows, const typename F::E** d_mat) {
+  typedef typename F::E E;
+  std::vector<E> hn(m), hx(rows);
+  for (uint32_t i = 0; i < m; ++i) hn[i] = nodes ? nodes[i] : F::from_u32(i + 1);
+  for (uint32_t r = 0; r < rows; ++r) hx[r] = xs[r];
+  std::string key(1, (char)F::BYTES);
+  key.append(reinterpret_cast<const char*>(&m), 4);
+  key.append(reinterpret_cast<const char*>(hn.data()), (size_t)m * sizeof(E));
+  key.append(reinterpret_cast<const char*>(hx.data()), (size_t)rows * sizeof(E));
+  auto it = ctx->basis_cache.find(key);
+  if (it != ctx->basis_cache.end()) {
+    *d_mat = reinterpret_cast<const E*>(it->second);
+    return SCLGPU_OK;
+  }
+  DevBuf dn, dx;
+  void* dm = nullptr;
+  CK(dn.alloc((size_t)m * sizeof(E)));
+  CK(dx.alloc((size_t)rows * sizeof(E)));
+  CK(cudaMalloc(&dm, std::max<size_t>((size_t)rows * m * sizeof(E), 16)));
+  cudaError_t e = cudaMemcpyAsync(dn.p, hn.data(), (size_t)m * sizeof(E), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dx.p, hx.data(), (size_t)rows * sizeof(E), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st);
+  if (e != cudaSuccess) {
+    cudaFree(dm);
+    return cuda_fail(ctx, e, "basis upload");
+  }
+  if (m > 0 && rows > 0) {
+    k_lagrange_rows<F><<<rows, (int)std::min<uint32_t>(std::max<uint32_t>(m, 32), 256), 0, st>>>(
+        dn.as<E>(), m, dx.as<E>(), reinterpret_cast<E*>(dm), ctx->d_flag);
+    ctx->launches++;
+  }
+  int bad = 0;
+  e = cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(dm);
+    return cuda_fail(ctx, e, "lagrange");
+  }
+  if (bad) {
+    cudaFree(dm);
+    return fail(ctx, SCLGPU_ELOGIC, "0 not invertible modulo prime");
+  }
+  if (ctx->basis_cache.size() > 64) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
+    ctx->basis_cache.clear();
+  }
+  ctx->basis_cache[key] = dm;
+  *d_mat = reinterpret_cast<const E*>(dm);
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_shares, uint64_t N,
+                        uint32_t n, uint64_t si, uint64_t sj, const typename F::E* d_basis,
+                        typename F::E* d_out) {
+  if (N == 0) return SCLGPU_OK;
+  const size_t smem = (size_t)n * sizeof(typename F::E);
+  if (smem > 48 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_p: more than 48 KiB of basis");
+  k_recover_p<F><<<grid_for(ctx, N, 256, 8), 256, smem, st>>>(d_shares, N, n, si, sj, d_basis, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+// the (alphas, t, d, x) -> check matrix part of shamirRecoverD (shamir.h:117-131, 137-139)
+template <class F>
+static int recover_d_matrix(sclgpu_ctx* ctx, cudaStream_t st, uint32_t n_given, uint32_t& t,
+                            const typename F::E* alphas, uint32_t& n_alphas, uint32_t& d,
+                            const typename F::E* x, uint32_t& m, uint32_t& n_checks,
+                            const typename F::E** d_mat) {
+  typedef typename F::E E;
+  std::vector<E> al;
+  E xx = F::zero();
+  if (alphas == nullptr) {  // shamir.h:152-155
+    n_alphas = 2 * t + 1;
+    d = t;
+    al.resize(n_alphas);
+    for (uint32_t i = 0; i < n_alphas; ++i) al[i] = F::from_u32(i + 1);
+  } else {
+    al.assign(alphas, alphas + n_alphas);
+    if (x) xx = *x;
+  }
+  if ((uint64_t)n_given < (uint64_t)d + t || (uint64_t)n_alphas < (uint64_t)d + t)
+    return fail(ctx, SCLGPU_ELOGIC, "not enough shares provided to detect errors");
+  m = d + 1;
+  n_checks = (d + t > m) ? d + t - m : 0;
+  std::vector<E> xs(n_checks + 1);
+  for (uint32_t r = 0; r < n_checks; ++r) xs[r] = al[m + r];
+  xs[n_checks] = xx;
+  return basis_rows<F>(ctx, st, al.data(), m, xs.data(), n_checks + 1, d_mat);
+}
+
+template <class F>
+static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_shares, uint64_t N,
+                        uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
+                        const typename F::E* d_mat, typename F::E* d_out, uint8_t* d_err) {
+  if (N == 0) return SCLGPU_OK;
+  const size_t smem = (size_t)(n_checks + 1) * m * sizeof(typename F::E);
+  if (smem > 200 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_d: check matrix exceeds shared memory");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_recover_d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_recover_d<F><<<grid_for(ctx, N, 256, 8), 256, smem, st>>>(d_shares, N, si, sj, m, n_checks, d_mat,
+                                                              d_out, d_err, ctx->d_count);
+  CKL();
+  return SCLGPU_OK;
+}
+
+static void strides_for(int layout, uint64_t N, uint32_t n, uint64_t& si, uint64_t& sj) {
+  if (layout == SCLGPU_PARTY_MAJOR) {
+    si = N;
+    sj = 1;
+  } else {
+    si = 1;
+    sj = n;
+  }
+}
+
+// ================================================================ C ABI: PRG
+extern "C" int sclgpu_prg_expand_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                                     uint64_t n_bytes, uint8_t* d_out) {
+  if (!ctx || !seed || (!d_out && n_bytes)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return prg_bytes_on(ctx, ctx->stream, seed, first_block, n_bytes, d_out);
+}
+
+extern "C" int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                                 uint64_t n_bytes, uint8_t* out) {
+  if (!ctx || !seed || (!out && n_bytes)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (n_bytes == 0) return SCLGPU_OK;
+  const uint64_t chunk = 256ull << 20;  // bytes, multiple of 16
+  DevBuf buf[2];
+  CK(buf[0].alloc(std::min(chunk, n_bytes)));
+  if (n_bytes > chunk) CK(buf[1].alloc(std::min(chunk, n_bytes - chunk)));
+  int k = 0;
+  for (uint64_t off = 0; off < n_bytes; off += chunk, k ^= 1) {
+    const uint64_t nb = std::min(chunk, n_bytes - off);
+    cudaStream_t st = ctx->pipe[k];
+    RET(prg_bytes_on(ctx, st, seed, first_block + off / 16, nb, buf[k].as<uint8_t>()));
+    CK(cudaMemcpyAsync(out + off, buf[k].p, nb, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+
+// ================================== generic host wrappers (upload / run / download)
+// Small helper for the host entry points whose buffers comfortably fit on the
+// device at once: inputs are copied up on pipe[0], the op runs there, outputs
+// come back, one synchronise at the end.
+struct HostOp {
+  sclgpu_ctx* ctx;
+  cudaStream_t st;
+  std::vector<void*> bufs;
+  explicit HostOp(sclgpu_ctx* c) : ctx(c), st(c->pipe[0]) {}
+  ~HostOp() {
+    cudaStreamSynchronize(st);
+    for (void* p : bufs) cudaFree(p);
+  }
+  int up(const void* h, size_t bytes, void** d) {
+    CK(cudaMalloc(d, bytes ? bytes : 1));
+    bufs.push_back(*d);
+    if (bytes) CK(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st));
+    return SCLGPU_OK;
+  }
+  int dev(size_t bytes, void** d) {
+    CK(cudaMalloc(d, bytes ? bytes : 1));
+    bufs.push_back(*d);
+    return SCLGPU_OK;
+  }
+  int down(void* h, const void* d, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SCLGPU_OK;
+  }
+};
+
+// --------------------------------------------------------------- random etc.
+template <class F, bool ONE>
+static int random_host(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n,
+                       void* out) {
+  typedef typename F::E E;
+  if (!ctx || !seed || (!out && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return SCLGPU_OK;
+  const uint64_t chunk = 1ull << 25;  // elements; even, so Fp61 chunks start on a block boundary
+  const uint64_t per_block = (F::BYTES == 16 || ONE) ? 1 : 2;
+  DevBuf buf[2];
+  CK(buf[0].alloc(std::min(chunk, n) * sizeof(E)));
+  if (n > chunk) CK(buf[1].alloc(std::min(chunk, n - chunk) * sizeof(E)));
+  int k = 0;
+  for (uint64_t off = 0; off < n; off += chunk, k ^= 1) {
+    const uint64_t nc = std::min(chunk, n - off);
+    cudaStream_t st = ctx->pipe[k];
+    RET((random_on<F, ONE>(ctx, st, seed, first_block + off / per_block, nc, buf[k].as<E>())));
+    CK(cudaMemcpyAsync(reinterpret_cast<E*>(out) + off, buf[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+
+template <class F, bool ONE>
+static int random_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n,
+                      void* d_out) {
+  if (!ctx || !seed || (!d_out && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return random_on<F, ONE>(ctx, ctx->stream, seed, first_block, n, reinterpret_cast<typename F::E*>(d_out));
+}
+
+template <class F>
+static int from_bytes_host(sclgpu_ctx* ctx, const uint8_t* bytes, uint64_t n, void* out) {
+  typedef typename F::E E;
+  if (!ctx || ((!bytes || !out) && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return SCLGPU_OK;
+  HostOp op(ctx);
+  void *db, *dout;
+  RET(op.up(bytes, n * F::BYTES, &db));
+  RET(op.dev(n * sizeof(E), &dout));
+  RET(from_bytes_on<F>(ctx, op.st, (const uint8_t*)db, n, (E*)dout));
+  return op.down(out, dout, n * sizeof(E));
+}
+
+extern "C" int sclgpu_fp61_from_bytes(sclgpu_ctx* c, const uint8_t* b, uint64_t n, uint64_t* o) { return from_bytes_host<F61>(c, b, n, o); }
+extern "C" int sclgpu_fp127_from_bytes(sclgpu_ctx* c, const uint8_t* b, uint64_t n, void* o) { return from_bytes_host<F127>(c, b, n, o); }
+extern "C" int sclgpu_fp61_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_host<F61, false>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp127_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_host<F127, false>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp61_ff_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_host<F61, true>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp127_ff_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_host<F127, true>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp61_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_dev<F61, false>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp127_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_dev<F127, false>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp61_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_dev<F61, true>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp127_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_dev<F127, true>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp61_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, uint64_t* o) {
+  if (!ctx || ((!b || !o) && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return from_bytes_on<F61>(ctx, ctx->stream, b, n, o);
+}
+extern "C" int sclgpu_fp127_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, void* o) {
+  if (!ctx || ((!b || !o) && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return from_bytes_on<F127>(ctx, ctx->stream, b, n, (E127*)o);
+}
+
+// ------------------------------------------------------------------ share
+template <class F>
+static int share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_t t, uint32_t n,
+                     const uint8_t seed[16], uint64_t first_block, void* d_shares, int layout) {
+  typedef typename F::E E;
+  if (!ctx || !seed || ((!d_secrets || !d_shares) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n too large");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const E* sec = reinterpret_cast<const E*>(d_secrets);
+  E* out = reinterpret_cast<E*>(d_shares);
+  if (layout == SCLGPU_PARTY_MAJOR)
+    return share_strided_on<F>(ctx, ctx->stream, sec, N, t, n, seed, first_block, out, N, 1);
+  // secret-major: evaluate party-major into a chunk buffer, then transpose the
+  // chunk into place (coalesced on both sides)
+  const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
+  uint64_t chunk = std::max<uint64_t>((512ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
+  if (chunk > N) chunk = N;
+  DevBuf tmp;
+  CK(tmp.alloc(chunk * n * sizeof(E)));
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    RET(share_strided_on<F>(ctx, ctx->stream, sec + c0, nc, t, n, seed, first_block + c0 * B,
+                            tmp.as<E>(), nc, 1));
+    RET(transpose_on<E>(ctx, ctx->stream, tmp.as<E>(), n, nc, out + c0 * n));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // tmp is freed on return
+  return SCLGPU_OK;
+}
+
+// Host pipeline: two streams, chunked; H2D secrets -> share (party-major) ->
+// transpose to SCL's [N][n] -> D2H, the copies of one chunk overlapping the
+// kernels of the other.
+template <class F>
+static int share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t t, uint32_t n,
+                      const uint8_t seed[16], uint64_t first_block, void* shares) {
+  typedef typename F::E E;
+  if (!ctx || !seed || ((!secrets || !shares) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n too large");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  DevBuf dsec[2], dpm[2], dsm[2];
+  const int nbuf = N > chunk ? 2 : 1;
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsec[k].alloc(chunk * sizeof(E)));
+    CK(dpm[k].alloc(chunk * n * sizeof(E)));
+    CK(dsm[k].alloc(chunk * n * sizeof(E)));
+  }
+  const E* hs = reinterpret_cast<const E*>(secrets);
+  E* ho = reinterpret_cast<E*>(shares);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    CK(cudaMemcpyAsync(dsec[k].p, hs + c0, nc * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(share_strided_on<F>(ctx, st, dsec[k].as<E>(), nc, t, n, seed, first_block + c0 * B,
+                            dpm[k].as<E>(), nc, 1));
+    RET(transpose_on<E>(ctx, st, dpm[k].as<E>(), n, nc, dsm[k].as<E>()));
+    CK(cudaMemcpyAsync(ho + c0 * n, dsm[k].p, nc * n * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+
+extern "C" int sclgpu_fp61_shamir_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return share_host<F61>(c, s, N, t, n, seed, fb, o); }
+extern "C" int sclgpu_fp127_shamir_share(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return share_host<F127>(c, s, N, t, n, seed, fb, o); }
+extern "C" int sclgpu_fp61_shamir_share_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return share_dev<F61>(c, s, N, t, n, seed, fb, o, layout); }
+extern "C" int sclgpu_fp127_shamir_share_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return share_dev<F127>(c, s, N, t, n, seed, fb, o, layout); }
+
+template <class F>
+static int share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, uint32_t t, uint32_t n,
+                            void* d_shares, int layout) {
+  typedef typename F::E E;
+  if (!ctx || ((!d_coeffs || !d_shares) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n too large");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  uint64_t si, sj;
+  strides_for(layout, N, n, si, sj);
+  return share_coeffs_on<F>(ctx, ctx->stream, (const E*)d_coeffs, N, t, n, (E*)d_shares, si, sj);
+}
+extern "C" int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, uint32_t n, uint64_t* o, int layout) { return share_coeffs_dev<F61>(c, k, N, t, n, o, layout); }
+extern "C" int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, uint32_t n, void* o, int layout) { return share_coeffs_dev<F127>(c, k, N, t, n, o, layout); }
+
+// ------------------------------------------------------------------ lagrange
+template <class F>
+static int lagrange_host(sclgpu_ctx* ctx, const void* nodes, uint32_t n, const void* x, void* out) {
+  typedef typename F::E E;
+  if (!ctx || !x || (!out && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return SCLGPU_OK;
+  const E* d_mat = nullptr;
+  RET(basis_rows<F>(ctx, ctx->pipe[0], (const E*)nodes, n, (const E*)x, 1, &d_mat));
+  CK(cudaMemcpyAsync(out, d_mat, (size_t)n * sizeof(E), cudaMemcpyDeviceToHost, ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_lagrange_basis(sclgpu_ctx* c, const uint64_t* nodes, uint32_t n, const uint64_t* x, uint64_t* o) { return lagrange_host<F61>(c, nodes, n, x, o); }
+extern "C" int sclgpu_fp127_lagrange_basis(sclgpu_ctx* c, const void* nodes, uint32_t n, const void* x, void* o) { return lagrange_host<F127>(c, nodes, n, x, o); }
+
+// ------------------------------------------------------------------ recover P
+template <class F>
+static int recover_p_basis(sclgpu_ctx* ctx, cudaStream_t st, uint32_t n, const void* alphas, const void* x,
+                           const typename F::E** d_basis) {
+  typedef typename F::E E;
+  E xx = F::zero();
+  if (alphas != nullptr) {
+    if (!x) return fail(ctx, SCLGPU_EINVAL, "x is required with explicit alphas");
+    xx = *reinterpret_cast<const E*>(x);
+  }
+  return basis_rows<F>(ctx, st, (const E*)alphas, n, &xx, 1, d_basis);
+}
+
+template <class F>
+static int recover_p_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n, int layout,
+                         const void* alphas, const void* x, void* d_out) {
+  typedef typename F::E E;
+  if (!ctx || ((!d_shares && n) || !d_out) && N) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  const E* d_basis = nullptr;
+  RET(recover_p_basis<F>(ctx, ctx->stream, n, alphas, x, &d_basis));
+  uint64_t si, sj;
+  strides_for(layout, N, n, si, sj);
+  return recover_p_on<F>(ctx, ctx->stream, (const E*)d_shares, N, n, si, sj, d_basis, (E*)d_out);
+}
+
+template <class F>
+static int recover_p_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n, const void* alphas,
+                          const void* x, void* out) {
+  typedef typename F::E E;
+  if (!ctx || ((!shares && n) || !out) && N) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  const E* d_basis = nullptr;
+  RET(recover_p_basis<F>(ctx, ctx->pipe[0], n, alphas, x, &d_basis));
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n, 1) * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  const int nbuf = N > chunk ? 2 : 1;
+  DevBuf dsh[2], dout[2];
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsh[k].alloc(chunk * n * sizeof(E)));
+    CK(dout[k].alloc(chunk * sizeof(E)));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  const E* hs = reinterpret_cast<const E*>(shares);
+  E* ho = reinterpret_cast<E*>(out);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n, nc * n * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(recover_p_on<F>(ctx, st, dsh[k].as<E>(), nc, n, 1, n, d_basis, dout[k].as<E>()));
+    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_recover_p(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_host<F61>(c, s, N, n, a, x, o); }
+extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return recover_p_host<F127>(c, s, N, n, a, x, o); }
+extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }
+extern "C" int sclgpu_fp127_recover_p_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, const void* x, void* o) { return recover_p_dev<F127>(c, s, N, n, layout, a, x, o); }
+
+// ------------------------------------------------------------------ recover D
+static int finish_detect(sclgpu_ctx* ctx, cudaStream_t st, uint64_t* n_detected) {
+  unsigned long long bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->d_count, sizeof(bad), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_detected) *n_detected = bad;
+  if (bad) return fail(ctx, SCLGPU_EDETECT, "error detected during recovery");
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int recover_d_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n_given, int layout,
+                         uint32_t t, const void* alphas, uint32_t n_alphas, uint32_t d, const void* x,
+                         void* d_out, uint8_t* d_err, uint64_t* n_detected) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  uint32_t m = 0, n_checks = 0;
+  const E* d_mat = nullptr;
+  RET(recover_d_matrix<F>(ctx, ctx->stream, n_given, t, (const E*)alphas, n_alphas, d, (const E*)x, m,
+                          n_checks, &d_mat));
+  if (n_detected) *n_detected = 0;
+  if (N == 0) return SCLGPU_OK;
+  if (!d_shares || !d_out || !d_err) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), ctx->stream));
+  uint64_t si, sj;
+  strides_for(layout, N, n_given, si, sj);
+  RET(recover_d_on<F>(ctx, ctx->stream, (const E*)d_shares, N, si, sj, m, n_checks, d_mat, (E*)d_out, d_err));
+  return finish_detect(ctx, ctx->stream, n_detected);
+}
+
+template <class F>
+static int recover_d_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n_given, uint32_t t,
+                          const void* alphas, uint32_t n_alphas, uint32_t d, const void* x, void* out,
+                          uint8_t* err, uint64_t* n_detected) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t m = 0, n_checks = 0;
+  const E* d_mat = nullptr;
+  RET(recover_d_matrix<F>(ctx, ctx->pipe[0], n_given, t, (const E*)alphas, n_alphas, d, (const E*)x, m,
+                          n_checks, &d_mat));
+  if (n_detected) *n_detected = 0;
+  if (N == 0) return SCLGPU_OK;
+  if (!shares || !out || !err) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n_given * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  const int nbuf = N > chunk ? 2 : 1;
+  DevBuf dsh[2], dout[2], derr[2];
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsh[k].alloc(chunk * n_given * sizeof(E)));
+    CK(dout[k].alloc(chunk * sizeof(E)));
+    CK(derr[k].alloc(chunk));
+  }
+  CK(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  const E* hs = reinterpret_cast<const E*>(shares);
+  E* ho = reinterpret_cast<E*>(out);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n_given, nc * n_given * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(recover_d_on<F>(ctx, st, dsh[k].as<E>(), nc, 1, n_given, m, n_checks, d_mat, dout[k].as<E>(),
+                        derr[k].as<uint8_t>()));
+    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(err + c0, derr[k].p, nc, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return finish_detect(ctx, ctx->pipe[0], n_detected);
+}
+extern "C" int sclgpu_fp61_recover_d(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F61>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
+extern "C" int sclgpu_fp127_recover_d(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F127>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
+extern "C" int sclgpu_fp61_recover_d_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return recover_d_dev<F61>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }
+extern "C" int sclgpu_fp127_recover_d_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_dev<F127>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }
+
+// ------------------------------------------------------------------ vector ops
+template <class F, int OP>
+static int binop_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* a, const typename F::E* b,
+                    uint64_t n, typename F::E* out) {
+  if (n == 0) return SCLGPU_OK;
+  if constexpr (F::BYTES == 8) {
+    const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                      reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (al && n >= 2) {
+      const uint64_t n2 = n >> 1;
+      k_vec_binop61_v2<OP><<<grid_for(ctx, n2, 256, 8), 256, 0, st>>>(
+          reinterpret_cast<const ulonglong2*>(a), reinterpret_cast<const ulonglong2*>(b), n2,
+          reinterpret_cast<ulonglong2*>(out));
+      CKL();
+      if (n & 1) {
+        k_vec_binop<F, OP><<<1, 32, 0, st>>>(a + n - 1, b + n - 1, 1, out + n - 1);
+        CKL();
+      }
+      return SCLGPU_OK;
+    }
+  }
+  k_vec_binop<F, OP><<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(a, b, n, out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int muladd_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* e, const typename F::E* b,
+                     const typename F::E* d, const typename F::E* a, const typename F::E* c, uint64_t n,
+                     typename F::E* z) {
+  if (n == 0) return SCLGPU_OK;
+  const uint64_t work = F::BYTES == 8 ? (n + 1) / 2 : n;
+  k_vec_muladd<F><<<grid_for(ctx, work, 256, 8), 256, 0, st>>>(e, b, d, a, c, n, z);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int dot_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* a, const typename F::E* b,
+                  uint64_t n, typename F::E* d_out) {
+  typedef typename F::E E;
+  const int grid = std::min(grid_for(ctx, n, 256, 8), kMaxPartials);
+  k_dot_partial<F><<<grid, 256, 0, st>>>(a, b, n, reinterpret_cast<E*>(ctx->d_partial));
+  CKL();
+  k_sum_final<F><<<1, 256, 0, st>>>(reinterpret_cast<const E*>(ctx->d_partial), (uint32_t)grid, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+// op: 0 add 1 sub 2 mul 3 scale 4 dot 5 sum 6 muladd
+template <class F>
+static int vec_dev(sclgpu_ctx* ctx, int op, const void* a, const void* b, const void* d, const void* a2,
+                   const void* c, uint64_t n, void* out) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (n && (!a || !out)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  switch (op) {
+    case 0: return binop_on<F, 0>(ctx, st, (const E*)a, (const E*)b, n, (E*)out);
+    case 1: return binop_on<F, 1>(ctx, st, (const E*)a, (const E*)b, n, (E*)out);
+    case 2: return binop_on<F, 2>(ctx, st, (const E*)a, (const E*)b, n, (E*)out);
+    case 3: {
+      if (!b) return fail(ctx, SCLGPU_EINVAL, "null scalar");
+      if (n == 0) return SCLGPU_OK;
+      k_vec_scale<F><<<grid_for(ctx, n, 256, 8), 256, 0, st>>>((const E*)a, *(const E*)b, n, (E*)out);
+      CKL();
+      return SCLGPU_OK;
+    }
+    case 4: return dot_on<F>(ctx, st, (const E*)a, (const E*)b, n, (E*)out);
+    case 5: return dot_on<F>(ctx, st, (const E*)a, nullptr, n, (E*)out);
+    case 6: return muladd_on<F>(ctx, st, (const E*)a, (const E*)b, (const E*)d, (const E*)a2, (const E*)c, n, (E*)out);
+    default: return fail(ctx, SCLGPU_EINVAL, "bad op");
+  }
+}
+
+template <class F>
+static int vec_host(sclgpu_ctx* ctx, int op, const void* a, const void* b, const void* d, const void* a2,
+                    const void* c, uint64_t n, void* out) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (!out || (n && !a)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  HostOp hop(ctx);
+  const size_t bytes = n * sizeof(E);
+  void *da = nullptr, *db = nullptr, *dd = nullptr, *da2 = nullptr, *dc = nullptr, *dout = nullptr;
+  RET(hop.up(a, bytes, &da));
+  if (op == 0 || op == 1 || op == 2 || op == 4 || op == 6) {
+    if (n && !b) return fail(ctx, SCLGPU_EINVAL, "null argument");
+    RET(hop.up(b, bytes, &db));
+  }
+  if (op == 6) {
+    if (n && (!d || !a2 || !c)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+    RET(hop.up(d, bytes, &dd));
+    RET(hop.up(a2, bytes, &da2));
+    RET(hop.up(c, bytes, &dc));
+  }
+  const size_t out_bytes = (op == 4 || op == 5) ? sizeof(E) : bytes;
+  RET(hop.dev(out_bytes, &dout));
+  cudaStream_t saved = ctx->stream;
+  ctx->stream = hop.st;
+  const int rc = vec_dev<F>(ctx, op, da, op == 3 ? b : db, dd, da2, dc, n, dout);
+  ctx->stream = saved;
+  RET(rc);
+  return hop.down(out, dout, out_bytes);
+}
+
+#define SCLGPU_VEC_API(SUF, F, PTR, CPTR)                                                                                              \
+  extern "C" int sclgpu_##SUF##_vec_add(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 0, a, b, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_sub(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 1, a, b, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_mul(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 2, a, b, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_scale(sclgpu_ctx* c, CPTR a, CPTR s, uint64_t n, PTR o) { return vec_host<F>(c, 3, a, s, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_muladd(sclgpu_ctx* c, CPTR e, CPTR b, CPTR d, CPTR a, CPTR cc, uint64_t n, PTR z) { return vec_host<F>(c, 6, e, b, d, a, cc, n, z); } \
+  extern "C" int sclgpu_##SUF##_dot(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 4, a, b, 0, 0, 0, n, o); }     \
+  extern "C" int sclgpu_##SUF##_sum(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return vec_host<F>(c, 5, a, 0, 0, 0, 0, n, o); }             \
+  extern "C" int sclgpu_##SUF##_vec_add_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 0, a, b, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_sub_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 1, a, b, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_mul_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 2, a, b, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_scale_dev(sclgpu_ctx* c, CPTR a, CPTR s, uint64_t n, PTR o) { return vec_dev<F>(c, 3, a, s, 0, 0, 0, n, o); } \
+  extern "C" int sclgpu_##SUF##_vec_muladd_dev(sclgpu_ctx* c, CPTR e, CPTR b, CPTR d, CPTR a, CPTR cc, uint64_t n, PTR z) { return vec_dev<F>(c, 6, e, b, d, a, cc, n, z); } \
+  extern "C" int sclgpu_##SUF##_dot_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 4, a, b, 0, 0, 0, n, o); }  \
+  extern "C" int sclgpu_##SUF##_sum_dev(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return vec_dev<F>(c, 5, a, 0, 0, 0, 0, n, o); }
+
+SCLGPU_VEC_API(fp61, F61, uint64_t*, const uint64_t*)
+SCLGPU_VEC_API(fp127, F127, void*, const void*)
+
+// ------------------------------------------------------------------ matrix
+template <class F>
+static int matvec_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, uint32_t rows, uint32_t cols,
+                     const typename F::E* x, typename F::E* y) {
+  const int grid = (int)std::min<uint64_t>(rows, (uint64_t)ctx->sm_count * 8);
+  if constexpr (F::BYTES == 8) {
+    if ((cols & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+      k_matvec61_v2<<<grid, 256, 0, st>>>(A, rows, cols, x, y);
+      CKL();
+      return SCLGPU_OK;
+    }
+  }
+  k_matvec<F><<<grid, 256, 0, st>>>(A, rows, cols, x, y);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int matvec_dev(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t cols, const void* x, void* y) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (rows == 0 || cols == 0) return fail(ctx, SCLGPU_EINVAL, "n or m cannot be 0");
+  if (!A || !x || !y) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return matvec_on<F>(ctx, ctx->stream, (const E*)A, rows, cols, (const E*)x, (E*)y);
+}
+
+template <class F>
+static int matvec_host(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t cols, const void* x, void* y) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (rows == 0 || cols == 0) return fail(ctx, SCLGPU_EINVAL, "n or m cannot be 0");
+  if (!A || !x || !y) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  HostOp hop(ctx);
+  void *dA, *dx, *dy;
+  RET(hop.up(A, (size_t)rows * cols * sizeof(E), &dA));
+  RET(hop.up(x, (size_t)cols * sizeof(E), &dx));
+  RET(hop.dev((size_t)rows * sizeof(E), &dy));
+  RET(matvec_on<F>(ctx, hop.st, (const E*)dA, rows, cols, (const E*)dx, (E*)dy));
+  return hop.down(y, dy, (size_t)rows * sizeof(E));
+}
+extern "C" int sclgpu_fp61_matvec(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return matvec_host<F61>(c, A, r, k, x, y); }
+extern "C" int sclgpu_fp127_matvec(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return matvec_host<F127>(c, A, r, k, x, y); }
+extern "C" int sclgpu_fp61_matvec_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return matvec_dev<F61>(c, A, r, k, x, y); }
+extern "C" int sclgpu_fp127_matvec_dev(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return matvec_dev<F127>(c, A, r, k, x, y); }
+
+template <class F>
+static int vandermonde_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (n == 0 || m == 0) return fail(ctx, SCLGPU_EINVAL, "n or m cannot be 0");
+  if (!out) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  HostOp hop(ctx);
+  void* dv;
+  RET(hop.dev((size_t)n * m * sizeof(E), &dv));
+  k_vandermonde<F><<<(n + 127) / 128, 128, 0, hop.st>>>(n, m, (E*)dv);
+  CKL();
+  return hop.down(out, dv, (size_t)n * m * sizeof(E));
+}
+extern "C" int sclgpu_fp61_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return vandermonde_host<F61>(c, n, m, o); }
+extern "C" int sclgpu_fp127_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return vandermonde_host<F127>(c, n, m, o); }
+
+extern "C" int sclgpu_fp61_transpose_dev(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
+  if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return transpose_on<uint64_t>(ctx, ctx->stream, in, rows, cols, out);
+}
+extern "C" int sclgpu_fp127_transpose_dev(sclgpu_ctx* ctx, const void* in, uint64_t rows, uint64_t cols, void* out) {
+  if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return transpose_on<E127>(ctx, ctx->stream, (const E127*)in, rows, cols, (E127*)out);
+}
+
+// ------------------------------------------------------------------ microbench
+extern "C" int sclgpu_pipe_microbench(sclgpu_ctx* ctx, int kind, uint32_t iters, double* ops_per_s) {
+  if (!ctx || !ops_per_s || kind < 0 || kind > 4) return fail(ctx, SCLGPU_EINVAL, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  DevBuf sink;
+  CK(sink.alloc(16));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int grid = ctx->sm_count, threads = 512;
+  auto launch = [&](uint32_t it) {
+    switch (kind) {
+      case 0: k_pipe_bench<0><<<grid, threads, 0, ctx->stream>>>(it, sink.as<uint32_t>()); break;
+      case 1: k_pipe_bench<1><<<grid, threads, 0, ctx->stream>>>(it, sink.as<uint32_t>()); break;
+      case 2: k_pipe_bench<2><<<grid, threads, 0, ctx->stream>>>(it, sink.as<uint32_t>()); break;
+      case 3: k_pipe_bench<3><<<grid, threads, 0, ctx->stream>>>(it, sink.as<uint32_t>()); break;
+      default: k_pipe_bench<4><<<grid, threads, 0, ctx->stream>>>(it, sink.as<uint32_t>()); break;
+    }
+    ctx->launches++;
+  };
+  launch(iters / 8 + 1);  // warm-up
+  CK(cudaEventRecord(e0, ctx->stream));
+  launch(iters);
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaGetLastError());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double ops = (double)grid * threads * (double)iters * 64.0;  // 8 chains x 8 unroll
+  *ops_per_s = ops / ((double)ms * 1e-3);
+  return SCLGPU_OK;
+}

@@ -1,0 +1,114 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header
+declares (no compute calls without a GPU), the host-side logic (seed padding,
+block accounting, shard arithmetic), and the N>1 sharding path under gloo with
+world_size 2."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.binding.load()
+    names = pkg.binding.declared_symbols()
+    assert len(names) >= 80
+    missing = [s for s in names if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.sclgpu_strerror(pkg.binding.EDETECT) == b"error detected during recovery"
+
+
+def test_no_cpu_fallback_without_gpu(pkg):
+    """On a box without a GPU the context refuses to come up (SCLGPU_ECUDA)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.CudaError):
+        pkg.Context(0)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through oracle/ (test infrastructure)."""
+    pdir = os.path.join(REPO, "secure-computation-library_b200")
+    for root, _, files in os.walk(pdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "scl_oracle" not in src, f
+                assert "libscloracle" not in src and "libsclref" not in src, f
+    for f in os.listdir(os.path.join(REPO, "include")):
+        src = open(os.path.join(REPO, "include", f)).read()
+        assert "scl_oracle" not in src and "sclo_" not in src and "sclref_" not in src, f
+
+
+def test_seed_and_block_accounting(pkg):
+    api, sh = pkg.api, pkg.sharding
+    assert api.seed16("abc") == b"abc" + b"\0" * 13
+    assert api.seed16(b"0123456789abcdefXYZ") == b"0123456789abcdef"  # prg.cc:88-101 truncation
+    assert api.seed16(b"") == b"\0" * 16
+    # B = ceil((t+1)*byteSize/16)  
+    assert sh.blocks_per_share_call(61, 2) == 2
+    assert sh.blocks_per_share_call(61, 15) == 8
+    assert sh.blocks_per_share_call(127, 7) == 8
+    assert sh.blocks_per_share_call(61, 0) == 1
+    assert sh.blocks_for_random(61, 5) == 3 and sh.blocks_for_random(61, 5, True) == 5
+    assert sh.blocks_for_random(127, 5) == 5
+    v = api.from_ints([1, (1 << 127) - 2], 127)
+    assert v.shape == (2, 2) and list(api.to_ints(v, 127)) == [1, (1 << 127) - 2]
+
+
+def test_shard_range_properties(pkg):
+    sh = pkg.sharding
+    for N in (0, 1, 5, 1 << 20, (1 << 26) + 3):
+        for world in (1, 2, 3, 4, 8):
+            for align in (1, 2):
+                parts = [sh.shard_range(N, world, r, align) for r in range(world)]
+                assert parts[0].lo == 0 and parts[-1].hi == N
+                for a, b in zip(parts, parts[1:]):
+                    assert a.hi == b.lo
+                    assert a.hi % align == 0 or a.hi == N
+                assert max(p.count for p in parts) - min(p.count for p in parts) <= align
+    with pytest.raises(ValueError):
+        sh.shard_range(10, 2, 2)
+    s = sh.shard_range(1 << 26, 8, 3)
+    assert sh.share_first_block(61, 15, 100, s) == 100 + 3 * (1 << 23) * 8
+    assert sh.random_first_block(61, 7, sh.shard_range(100, 2, 1, 2)) == 7 + 25
+    assert sh.random_first_block(127, 7, sh.shard_range(100, 2, 1)) == 7 + 50
+
+
+def test_sharded_share_equals_unsharded_single_process(pkg, port):
+    """Rank r sharing its slice with first_block + lo*B reproduces the slice of the
+    one-PRG batch (the engine here is the oracle: this checks the HOST arithmetic)."""
+    sh = pkg.sharding
+    for field, t, n, N in [(61, 15, 32, 101), (127, 7, 16, 37), (61, 2, 5, 64)]:
+        secrets = port.vector_random(field, "secrets", 0, N)
+        full = port.shamir_share(field, secrets, t, n, "shamir bench", 11)
+        for world in (2, 3, 8):
+            parts = []
+            for r in range(world):
+                s = sh.shard_range(N, world, r)
+                parts.append(port.shamir_share(field, secrets[s.lo:s.hi], t, n, "shamir bench",
+                                               sh.share_first_block(field, t, 11, s)))
+            assert np.array_equal(np.concatenate(parts, axis=0), full)
+    for field in (61, 127):
+        full = port.vector_random(field, "prg bench", 5, 1001)
+        parts = []
+        for r in range(4):
+            s = sh.shard_range(1001, 4, r, align=2)
+            parts.append(port.vector_random(field, "prg bench", sh.random_first_block(field, 5, s), s.count))
+        assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+def test_gloo_world2_sharded_share_recover():
+    """world_size-2 gloo run of the sharded driver (tests/dist_worker.py)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611",
+           os.path.join(REPO, "tests", "dist_worker.py")]
+    r = subprocess.run(cmd, env=env, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "DIST_OK world=2" in r.stdout, r.stdout[-3000:]
