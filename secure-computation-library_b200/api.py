@@ -158,18 +158,14 @@ class Context:
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "free": fr.value, "total": tot.value}
 
     def host_alloc(self, nbytes: int) -> np.ndarray:
-        """pinned host buffer as a uint8 numpy array (freed with host_free)"""
+        """pinned host buffer as a uint8 numpy array (release with host_free)"""
         p = C.c_void_p()
         self._check(self.lib.sclgpu_host_alloc(self._ctx, nbytes, C.byref(p)))
         buf = (C.c_uint8 * nbytes).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=np.uint8)
-        arr._sclgpu_ptr = p  # type: ignore[attr-defined]
-        return arr
+        return np.frombuffer(buf, dtype=np.uint8)
 
     def host_free(self, arr: np.ndarray):
-        base = arr
-        while getattr(base, "base", None) is not None and not hasattr(base, "_sclgpu_ptr"):
-            base = base.base
+        """`arr` is the array host_alloc returned (or a view starting at its first byte)"""
         self._check(self.lib.sclgpu_host_free(self._ctx, C.c_void_p(arr.ctypes.data)))
 
     def pipe_microbench(self, kind: int, iters: int = 4096) -> float:

@@ -1,0 +1,354 @@
+"""GPU parity tests: libsclgpu.so (through its C ABI) against the oracle on the
+same seeded inputs, bit-exact (integer work: no tolerance anywhere), plus the
+committed golden vectors recorded from the unmodified reference, plus
+size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = {61: (1 << 61) - 1, 127: (1 << 127) - 1}
+
+
+def ints(o, arr, field):
+    return [int(v) for v in o.to_ints(arr, field).reshape(-1)]
+
+
+def unhex(o, hexes, field, shape=None):
+    a = o.from_ints([int(h, 16) for h in hexes], field)
+    if shape is not None:
+        a = a.reshape(tuple(shape) + (() if field == 61 else (2,)))
+    return a
+
+
+def test_device_is_b200(ctx):
+    info = ctx.device_info()
+    assert info["cc"][0] == 10, info
+    assert info["sm_count"] >= 100
+
+
+# ------------------------------------------------------------------ PRG
+def test_prg_golden(ctx, golden):
+    for c in golden["prg"]:
+        got = ctx.prg_expand(c["seed"], c["first_block"], c["n_bytes"])
+        assert bytes(got).hex() == c["hex"], c
+
+
+@pytest.mark.parametrize("nbytes", [0, 1, 15, 16, 17, 4096, 1 << 20, (1 << 22) + 5])
+def test_prg_vs_oracle(ctx, orc, nbytes):
+    first = 12345 if orc.kind == "reference" else (1 << 40) + 77
+    got = ctx.prg_expand("prg bench", first, nbytes)
+    assert np.array_equal(got, orc.prg_next("prg bench", first, nbytes))
+
+
+def test_prg_counter_high_word(ctx, port):
+    first = (1 << 32) - 3  # crosses the 32-bit boundary of the counter
+    assert np.array_equal(ctx.prg_expand("k", first, 160), port.prg_next("k", first, 160))
+    first = (1 << 63) - 4
+    assert np.array_equal(ctx.prg_expand("k", first, 64), port.prg_next("k", first, 64))
+
+
+# ------------------------------------------------------------------ random / read
+def test_random_golden(ctx, golden):
+    for c in golden["random"]:
+        f = ctx.vector_random if c["kind"] == "vector" else ctx.ff_random
+        got = f(c["field"], c["seed"], c["first_block"], c["n"])
+        assert ints(ctx_o(), got, c["field"]) == [int(h, 16) for h in c["hex"]], c
+
+
+class _O:
+    @staticmethod
+    def to_ints(arr, field):
+        arr = np.asarray(arr, dtype=np.uint64)
+        if field == 61:
+            return np.array([int(v) for v in arr.reshape(-1)], dtype=object).reshape(arr.shape)
+        flat = arr.reshape(-1, 2)
+        return np.array([int(lo) | (int(hi) << 64) for lo, hi in flat], dtype=object).reshape(arr.shape[:-1])
+
+
+def ctx_o():
+    return _O
+
+
+@pytest.mark.parametrize("field", [61, 127])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 1000, 1001, (1 << 20) + 1])
+def test_random_vs_oracle(ctx, orc, field, n):
+    assert np.array_equal(ctx.vector_random(field, "secrets", 5, n), orc.vector_random(field, "secrets", 5, n))
+    m = min(n, 5000)
+    assert np.array_equal(ctx.ff_random(field, "ff", 9, m), orc.ff_random(field, "ff", 9, m))
+
+
+def test_from_bytes_golden_and_edges(ctx, port, golden):
+    for c in golden["from_bytes"]:
+        got = ctx.from_bytes(c["field"], bytes.fromhex(c["raw"]))
+        assert ints(port, got, c["field"]) == [int(h, 16) for h in c["hex"]]
+    raw = bytes(port.prg_next("raw", 0, 16 * 1000))
+    for field in (61, 127):
+        assert np.array_equal(ctx.from_bytes(field, raw), port.from_bytes(field, raw))
+
+
+# ------------------------------------------------------------------ Shamir
+def test_shamir_golden(ctx, port, golden):
+    for c in golden["shamir"]:
+        f = c["field"]
+        secrets = unhex(port, c["secrets"], f)
+        sh = ctx.shamir_share(f, secrets, c["t"], c["n"], c["seed"], c["first_block"])
+        assert ints(port, sh, f) == [int(h, 16) for h in c["shares"]], (f, c["t"], c["n"])
+        assert ints(port, ctx.recover_p(f, sh), f) == [int(h, 16) for h in c["recover_p"]]
+
+
+def test_survey_sum_of_1023_calls(ctx, port, golden):
+    s = port.from_ints([123 + j for j in range(1024)], 61)
+    sh = ctx.shamir_share(61, s, 15, 32, "shamir bench")
+    assert sum(ints(port, sh[1:], 61)) % P[61] == int(golden["survey_sum_1023"], 16) == 0x44672D90DD13206
+
+
+@pytest.mark.parametrize("field,t,n,N", [
+    (61, 2, 5, 1 << 16), (61, 15, 32, 1 << 14), (61, 15, 32, 1000), (61, 0, 1, 7), (61, 1, 3, 33),
+    (61, 16, 33, 257), (61, 17, 40, 129), (61, 31, 64, 65), (61, 3, 70000 // 1000, 100),
+    (127, 7, 16, 1 << 13), (127, 2, 5, 1 << 14), (127, 0, 2, 5), (127, 8, 17, 300), (127, 9, 20, 123),
+    (127, 15, 32, 64),
+])
+def test_share_recover_vs_oracle(ctx, orc, field, t, n, N):
+    secrets = orc.vector_random(field, "secrets", 0, N)
+    first = 1000
+    got = ctx.shamir_share(field, secrets, t, n, "shamir bench", first)
+    want = orc.shamir_share(field, secrets, t, n, "shamir bench", first)
+    assert np.array_equal(got, want)
+    rec = ctx.recover_p(field, got)
+    assert np.array_equal(rec, orc.recover_p(field, want))
+    assert np.array_equal(rec, secrets)
+
+
+def test_share_empty_and_degenerate(ctx, port):
+    for field in (61, 127):
+        e = port.from_ints([], field).reshape((0,) + (() if field == 61 else (2,)))
+        assert ctx.shamir_share(field, e, 2, 5, "x").shape[0] == 0
+        s = port.from_ints([9, 10], field)
+        assert ctx.shamir_share(field, s, 2, 0, "x").shape[:2] == (2, 0)
+        # t = 0: every share equals the secret
+        sh = ctx.shamir_share(field, s, 0, 4, "x")
+        assert ints(port, sh, field) == [9, 9, 9, 9, 10, 10, 10, 10]
+
+
+def test_share_large_point_count(ctx, port):
+    """n above the small-point Horner limit exercises the generic evaluation path."""
+    s = port.from_ints([1, 2, 3], 61)
+    n = 70000
+    got = ctx.shamir_share(61, s, 2, n, "big n", 0)
+    want = port.shamir_share(61, s, 2, n, "big n", 0)
+    assert np.array_equal(got, want)
+
+
+def test_recover_p_custom_golden(ctx, port, golden):
+    for c in golden["recover_p_custom"]:
+        f = c["field"]
+        sh = unhex(port, c["shares"], f, (c["N"], c["n"]))
+        out = ctx.recover_p(f, sh, unhex(port, c["alphas"], f), c["x"])
+        assert ints(port, out, f) == [int(h, 16) for h in c["out"]]
+
+
+def test_recover_d_golden(ctx, port, golden):
+    for c in golden["recover_d"]:
+        f = c["field"]
+        sh = unhex(port, c["shares"], f, (c["N"], c["n"]))
+        out, err, rc = ctx.recover_d(f, sh, c["t"])
+        assert rc == c["rc"] and [int(e) for e in err] == c["err"], (f, c["t"])
+        assert ints(port, out, f) == [int(h, 16) for h in c["out"]]
+    c = golden["recover_d_not_enough"]
+    sh = port.shamir_share(61, port.from_ints([5], 61), c["t"], c["n"], "few")
+    assert ctx.recover_d(61, sh, c["t"])[2] == -1
+    c = golden["recover_d_custom"]
+    sh = unhex(port, c["shares"], 61, (2, c["n"]))
+    out, err, rc = ctx.recover_d(61, sh, c["t"], alphas=unhex(port, c["alphas"], 61), d=c["d"], x=c["x"])
+    assert rc == c["rc"] and ints(port, out, 61) == [int(h, 16) for h in c["out"]]
+
+
+@pytest.mark.parametrize("field,t,n,N", [(127, 7, 16, 4096), (61, 7, 16, 4096), (61, 15, 32, 2048), (127, 2, 5, 999)])
+def test_recover_d_tamper_vs_oracle(ctx, orc, field, t, n, N):
+    """C3's tamper set: flip one share at idx in {0, 8, 2t-1, 2t, 2t+1}; the last two
+    are never checked by the reference (shamir.h:129) and must stay undetected."""
+    secrets = orc.vector_random(field, "secrets127", 0, N)
+    sh = orc.shamir_share(field, secrets, t, n, "shamir bench", 0)
+    flat = sh.reshape(N, n, -1)
+    idxs = [0, min(8, n - 1), 2 * t - 1, 2 * t, min(2 * t + 1, n - 1)]
+    for k, j in enumerate(range(0, N, 16)):
+        flat[j, idxs[k % len(idxs)], k % flat.shape[2]] ^= np.uint64(1 << (k % 60))
+    out, err, nd = ctx.recover_d(field, sh, t)
+    w_out, w_err, w_nd = orc.recover_d(field, sh, t)
+    assert nd == w_nd and nd > 0
+    assert np.array_equal(err, w_err)
+    assert np.array_equal(out, w_out)
+
+
+def test_recover_d_raises_reference_strings(ctx, pkg, port):
+    lib = ctx.lib
+    sh = port.shamir_share(61, port.from_ints([5], 61), 3, 5, "few")
+    import ctypes as C
+    out = np.zeros(1, dtype=np.uint64)
+    err = np.zeros(1, dtype=np.uint8)
+    nd = C.c_uint64()
+    rc = lib.sclgpu_fp61_recover_d(ctx._ctx, sh.ctypes.data_as(C.c_void_p), 1, 5, 3, None, 0, 3, None,
+                                   out.ctypes.data_as(C.c_void_p), err.ctypes.data_as(C.c_void_p), C.byref(nd))
+    assert rc == pkg.binding.ELOGIC
+    assert lib.sclgpu_last_error(ctx._ctx) == b"not enough shares provided to detect errors"
+    sh = port.shamir_share(61, port.from_ints([5], 61), 3, 7, "ok")
+    sh[0, 2] = 4
+    rc = lib.sclgpu_fp61_recover_d(ctx._ctx, sh.ctypes.data_as(C.c_void_p), 1, 7, 3, None, 0, 3, None,
+                                   out.ctypes.data_as(C.c_void_p), err.ctypes.data_as(C.c_void_p), C.byref(nd))
+    assert rc == pkg.binding.EDETECT and nd.value == 1 and err[0] == 1
+    assert lib.sclgpu_last_error(ctx._ctx) == b"error detected during recovery"
+
+
+def test_lagrange_golden_and_collision(ctx, pkg, port, golden):
+    for c in golden["lagrange"]:
+        f = c["field"]
+        lb = ctx.lagrange(f, port.from_ints(c["nodes"], f), int(c["x"], 16))
+        assert ints(port, lb, f) == [int(h, 16) for h in c["hex"]]
+    with pytest.raises(pkg.LogicError, match="0 not invertible modulo prime"):
+        ctx.lagrange(61, port.from_ints([1, 2, 2], 61), 0)
+
+
+# ------------------------------------------------------------------ Vector / Matrix
+def test_vec_golden(ctx, port, golden):
+    for c in golden["vec"]:
+        f = c["field"]
+        a, b = port.vector_random(f, "a", 0, 37), port.vector_random(f, "b", 0, 37)
+        if c["op"] == "beaver":
+            e, d, cc = (port.vector_random(f, s, 0, 37) for s in ("e", "d", "c"))
+            got = ctx.beaver(f, e, b, d, a, cc)
+        else:
+            got = ctx.vec_op(f, c["op"], a, b)
+        assert ints(port, got, f) == [int(h, 16) for h in c["hex"]], c["op"]
+
+
+@pytest.mark.parametrize("field", [61, 127])
+@pytest.mark.parametrize("n", [1, 2, 31, 1000, 1001, (1 << 18) + 3])
+def test_vec_ops_vs_oracle(ctx, orc, field, n):
+    a, b = orc.vector_random(field, "va", 0, n), orc.vector_random(field, "vb", 9, n)
+    for op in range(6):
+        assert np.array_equal(ctx.vec_op(field, op, a, b), orc.vec_op(field, op, a, b)), op
+    e, d, c = (orc.vector_random(field, s, 0, n) for s in ("e", "d", "c"))
+    assert np.array_equal(ctx.beaver(field, e, b, d, a, c), orc.beaver(field, e, b, d, a, c))
+
+
+@pytest.mark.parametrize("field", [61, 127])
+def test_field_edge_values(ctx, port, field):
+    p = P[field]
+    vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, (1 << 60) + 5, p // 3, (1 << 32) - 1, 1 << 32]
+    if field == 127:
+        vals += [(1 << 64) - 1, 1 << 64, (1 << 126) + (1 << 64) - 1, (1 << 63), (1 << 127) - (1 << 64)]
+    A = port.from_ints([a for a in vals for _ in vals], field)
+    B = port.from_ints([b for _ in vals for b in vals], field)
+    for op in (0, 1, 2, 4):
+        assert np.array_equal(ctx.vec_op(field, op, A, B), port.vec_op(field, op, A, B)), op
+    assert np.array_equal(ctx.vec_op(field, 5, A), port.vec_op(field, 5, A))
+
+
+def test_matvec_golden_and_vs_oracle(ctx, orc, port, golden):
+    for c in golden["matvec"]:
+        f, rows, cols = c["field"], c["rows"], c["cols"]
+        A = port.vector_random(f, "mat A", 0, rows * cols).reshape((rows, cols) + (() if f == 61 else (2,)))
+        x = port.vector_random(f, "vec x", 0, cols)
+        assert ints(port, ctx.matvec(f, A, x), f) == [int(h, 16) for h in c["hex"]]
+    for field, rows, cols in [(61, 300, 1024), (61, 7, 4097), (61, 1, 1), (127, 64, 513), (61, 128, 8192)]:
+        A = orc.vector_random(field, "mat A", 0, rows * cols).reshape((rows, cols) + (() if field == 61 else (2,)))
+        x = orc.vector_random(field, "vec x", 0, cols)
+        assert np.array_equal(ctx.matvec(field, A, x), orc.matvec(field, A, x)), (field, rows, cols)
+
+
+def test_matvec_and_vandermonde_errors(ctx, pkg, port, golden):
+    with pytest.raises(pkg.InvalidArgument, match="n or m cannot be 0"):
+        ctx.vandermonde(61, 0, 3)
+    for c in golden["vandermonde"]:
+        assert ints(port, ctx.vandermonde(c["field"], c["n"], c["m"]), c["field"]) == [int(h, 16) for h in c["hex"]]
+
+
+# ------------------------------------------------------------------ device-pointer path
+def test_dev_path_party_major_and_secret_major(ctx, pkg, orc):
+    import torch
+
+    ctx.use_torch_stream()
+    B = pkg.binding
+    for field, t, n, N in [(61, 15, 32, 5000), (127, 7, 16, 3000), (61, 2, 5, 777)]:
+        w = 1 if field == 61 else 2
+        secrets = orc.vector_random(field, "secrets", 0, N)
+        want = orc.shamir_share(field, secrets, t, n, "shamir bench", 0)
+        d_sec = torch.from_numpy(secrets.view(np.int64)).cuda()
+        d_pm = torch.empty((n, N, w), dtype=torch.int64, device="cuda")
+        d_sm = torch.empty((N, n, w), dtype=torch.int64, device="cuda")
+        ctx.shamir_share_dev(field, d_sec, N, t, n, "shamir bench", 0, d_pm, B.PARTY_MAJOR)
+        ctx.shamir_share_dev(field, d_sec, N, t, n, "shamir bench", 0, d_sm, B.SECRET_MAJOR)
+        torch.cuda.synchronize()
+        sm = d_sm.cpu().numpy().view(np.uint64).reshape(want.shape)
+        pm = d_pm.cpu().numpy().view(np.uint64)
+        assert np.array_equal(sm, want)
+        assert np.array_equal(np.swapaxes(pm, 0, 1).reshape(want.shape), want)
+        for layout, buf in ((B.PARTY_MAJOR, d_pm), (B.SECRET_MAJOR, d_sm)):
+            d_out = torch.empty((N, w), dtype=torch.int64, device="cuda")
+            ctx.recover_p_dev(field, buf, N, n, d_out, layout)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(secrets.shape), secrets)
+            if n >= 2 * t + 1:
+                d_err = torch.empty(N, dtype=torch.uint8, device="cuda")
+                nd = ctx.recover_d_dev(field, buf, N, n, t, d_out, d_err, layout)
+                assert nd == 0 and int(d_err.sum()) == 0
+                assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(secrets.shape), secrets)
+
+
+def test_sharded_gpu_engine(ctx, pkg, orc):
+    """The N>1 driver logic with the GPU engine: slices shared with the offset counter
+    concatenate to the one-PRG batch (what tests/dist_worker.py checks under gloo)."""
+    sh = pkg.sharding
+    field, t, n, N = 61, 15, 32, 4099
+    secrets = orc.vector_random(field, "secrets", 0, N)
+    full = ctx.shamir_share(field, secrets, t, n, "shamir bench", 3)
+    assert np.array_equal(full, orc.shamir_share(field, secrets, t, n, "shamir bench", 3))
+    parts = []
+    for r in range(8):
+        s = sh.shard_range(N, 8, r)
+        parts.append(ctx.shamir_share(field, secrets[s.lo:s.hi], t, n, "shamir bench", sh.share_first_block(field, t, 3, s)))
+    assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_c2_properties(ctx, pkg, orc):
+    """BASELINE config C2 at a large size (2^24 secrets per pass here; bench.py runs 2^26):
+    (i) share -> recoverP round trip returns every secret, (ii) a prefix and strided
+    samples equal the oracle bit for bit, (iii) linearity: share(a)+share(b) over the
+    same coefficients... is checked through sum of shares == share of sums at x (party) level
+    via recoverP(shares_a + shares_b) == a + b."""
+    import torch
+
+    ctx.use_torch_stream()
+    B = pkg.binding
+    field, t, n, N = 61, 15, 32, 1 << 24
+    d_sec = torch.empty(N, dtype=torch.int64, device="cuda")
+    ctx.random_dev(61, "secrets", 0, N, d_sec)
+    d_sh = torch.empty((n, N), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_dev(61, d_sec, N, t, n, "shamir bench", 0, d_sh, B.PARTY_MAJOR)
+    d_out = torch.empty(N, dtype=torch.int64, device="cuda")
+    ctx.recover_p_dev(61, d_sh, N, n, d_out, B.PARTY_MAJOR)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, d_sec)
+    # prefix + strided samples against the oracle
+    K = 2048
+    sec_h = d_sec[:K].cpu().numpy().view(np.uint64)
+    assert np.array_equal(sec_h, orc.vector_random(61, "secrets", 0, K))
+    want = orc.shamir_share(61, sec_h, t, n, "shamir bench", 0)
+    assert np.array_equal(d_sh[:, :K].t().contiguous().cpu().numpy().view(np.uint64), want)
+    if orc.kind == "port":  # seekable oracle: check far-away slices too
+        for lo in (N // 2 - 5, N - K):
+            sec_h = d_sec[lo:lo + K].cpu().numpy().view(np.uint64)
+            want = orc.shamir_share(61, sec_h, t, n, "shamir bench", lo * 8)
+            assert np.array_equal(d_sh[:, lo:lo + K].t().contiguous().cpu().numpy().view(np.uint64), want)
+    # linearity of reconstruction: recoverP(sh_a + sh_b) = a + b
+    d_sh2 = torch.empty((n, N), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_dev(61, d_out, N, t, n, "other", 0, d_sh2, B.PARTY_MAJOR)
+    ctx.vec_op_dev(61, 0, d_sh, d_sh2, n * N, d_sh2)
+    d_sum = torch.empty(N, dtype=torch.int64, device="cuda")
+    ctx.recover_p_dev(61, d_sh2, N, n, d_sum, B.PARTY_MAJOR)
+    d_want = torch.empty(N, dtype=torch.int64, device="cuda")
+    ctx.vec_op_dev(61, 0, d_sec, d_sec, N, d_want)
+    torch.cuda.synchronize()
+    assert torch.equal(d_sum, d_want)
