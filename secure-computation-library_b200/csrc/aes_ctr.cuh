@@ -121,6 +121,86 @@ __device__ __forceinline__ void aes128_encrypt(const AesKey& key, uint32_t laneb
   }
 }
 
+// ---------------------------------------------------------------------------
+// Counter-mode caching.  The plaintext of block `ctr` is LE64(ctr) || LE64(nonce):
+// only state byte 0 (the low counter byte) differs between blocks that share
+// ctr >> 8.  Byte 0 feeds one column of round 1 (t0), and t0 feeds one T-table
+// term of each column of round 2, so everything else of rounds 1-2 is computed
+// once per 256-block group (27 lookups) and each block costs 1 + 4 lookups for
+// rounds 1-2 instead of 32.  Values are bit-identical to aes128_encrypt.
+struct PrgGroup {
+  uint32_t k0;              // round-1 column 0 without its T0 term
+  uint32_t u0, u1, u2, u3;  // round-2 columns without their t0 terms
+};
+
+// T-table lookup of byte K of w in table TBL
+template <int TBL, int K>
+__device__ __forceinline__ uint32_t aes_t(uint32_t w, uint32_t lanebase) {
+  constexpr int OFF = (TBL & 1) * 128 + (TBL >> 1) * 65536;
+  return aes_lds<OFF>(aes_addr<K>(w, lanebase));
+}
+
+// group state for the 256 counters sharing ctr >> 8
+__device__ __forceinline__ void prg_group(const AesKey& key, uint32_t lanebase, uint64_t ctr,
+                                          PrgGroup& g) {
+  const uint32_t a0 = (uint32_t)ctr ^ key.rk[0], a1 = (uint32_t)(ctr >> 32) ^ key.rk[1],
+                 a2 = kPrgNonceLo ^ key.rk[2], a3 = kPrgNonceHi ^ key.rk[3];
+  g.k0 = aes_t<1, 1>(a1, lanebase) ^ aes_t<2, 2>(a2, lanebase) ^ aes_t<3, 3>(a3, lanebase) ^ key.rk[4];
+  const uint32_t t1 = aes_t<0, 0>(a1, lanebase) ^ aes_t<1, 1>(a2, lanebase) ^ aes_t<2, 2>(a3, lanebase) ^
+                      aes_t<3, 3>(a0, lanebase) ^ key.rk[5];
+  const uint32_t t2 = aes_t<0, 0>(a2, lanebase) ^ aes_t<1, 1>(a3, lanebase) ^ aes_t<2, 2>(a0, lanebase) ^
+                      aes_t<3, 3>(a1, lanebase) ^ key.rk[6];
+  const uint32_t t3 = aes_t<0, 0>(a3, lanebase) ^ aes_t<1, 1>(a0, lanebase) ^ aes_t<2, 2>(a1, lanebase) ^
+                      aes_t<3, 3>(a2, lanebase) ^ key.rk[7];
+  g.u0 = aes_t<1, 1>(t1, lanebase) ^ aes_t<2, 2>(t2, lanebase) ^ aes_t<3, 3>(t3, lanebase) ^ key.rk[8];
+  g.u1 = aes_t<0, 0>(t1, lanebase) ^ aes_t<1, 1>(t2, lanebase) ^ aes_t<2, 2>(t3, lanebase) ^ key.rk[9];
+  g.u2 = aes_t<0, 0>(t2, lanebase) ^ aes_t<1, 1>(t3, lanebase) ^ aes_t<3, 3>(t1, lanebase) ^ key.rk[10];
+  g.u3 = aes_t<0, 0>(t3, lanebase) ^ aes_t<2, 2>(t1, lanebase) ^ aes_t<3, 3>(t2, lanebase) ^ key.rk[11];
+}
+
+// rounds R0..9 and the final round on state (s0..s3) = output of round R0-1
+template <int R0>
+__device__ __forceinline__ void aes128_tail(const AesKey& key, uint32_t lanebase, uint32_t s0, uint32_t s1,
+                                            uint32_t s2, uint32_t s3, uint32_t& o0, uint32_t& o1,
+                                            uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+  for (int r = R0; r < 10; ++r) {
+    const uint32_t t0 = aes_t<0, 0>(s0, lanebase) ^ aes_t<1, 1>(s1, lanebase) ^ aes_t<2, 2>(s2, lanebase) ^
+                        aes_t<3, 3>(s3, lanebase) ^ key.rk[4 * r + 0];
+    const uint32_t t1 = aes_t<0, 0>(s1, lanebase) ^ aes_t<1, 1>(s2, lanebase) ^ aes_t<2, 2>(s3, lanebase) ^
+                        aes_t<3, 3>(s0, lanebase) ^ key.rk[4 * r + 1];
+    const uint32_t t2 = aes_t<0, 0>(s2, lanebase) ^ aes_t<1, 1>(s3, lanebase) ^ aes_t<2, 2>(s0, lanebase) ^
+                        aes_t<3, 3>(s1, lanebase) ^ key.rk[4 * r + 2];
+    const uint32_t t3 = aes_t<0, 0>(s3, lanebase) ^ aes_t<1, 1>(s0, lanebase) ^ aes_t<2, 2>(s1, lanebase) ^
+                        aes_t<3, 3>(s2, lanebase) ^ key.rk[4 * r + 3];
+    s0 = t0;
+    s1 = t1;
+    s2 = t2;
+    s3 = t3;
+  }
+  // final round: S[x] sits in byte 0 of T2/T3, byte 1 of T0/T3, byte 2 of T0/T1, byte 3 of T1/T2
+#define SCLGPU_AES_LAST2(w0, w1, w2, w3)                                                          \
+  __byte_perm(__byte_perm(aes_t<2, 0>(w0, lanebase), aes_t<3, 1>(w1, lanebase), 0x0050),          \
+              __byte_perm(aes_t<0, 2>(w2, lanebase), aes_t<1, 3>(w3, lanebase), 0x7200), 0x7610)
+  o0 = SCLGPU_AES_LAST2(s0, s1, s2, s3) ^ key.rk[40];
+  o1 = SCLGPU_AES_LAST2(s1, s2, s3, s0) ^ key.rk[41];
+  o2 = SCLGPU_AES_LAST2(s2, s3, s0, s1) ^ key.rk[42];
+  o3 = SCLGPU_AES_LAST2(s3, s0, s1, s2) ^ key.rk[43];
+#undef SCLGPU_AES_LAST2
+}
+
+// keystream block whose counter has low 32 bits ctr_lo and lies in group g
+__device__ __forceinline__ void prg_block_grouped(const AesKey& key, uint32_t lanebase, const PrgGroup& g,
+                                                  uint32_t ctr_lo, uint32_t& o0, uint32_t& o1, uint32_t& o2,
+                                                  uint32_t& o3) {
+  const uint32_t t0 = aes_t<0, 0>(ctr_lo ^ key.rk[0], lanebase) ^ g.k0;
+  const uint32_t s0 = aes_t<0, 0>(t0, lanebase) ^ g.u0;
+  const uint32_t s1 = aes_t<3, 3>(t0, lanebase) ^ g.u1;
+  const uint32_t s2 = aes_t<2, 2>(t0, lanebase) ^ g.u2;
+  const uint32_t s3 = aes_t<1, 1>(t0, lanebase) ^ g.u3;
+  aes128_tail<3>(key, lanebase, s0, s1, s2, s3, o0, o1, o2, o3);
+}
+
 // keystream block `ctr` of the PRG (prg.cc:82-84): plaintext = LE64(ctr) || LE64(nonce)
 __device__ __forceinline__ void prg_block(const AesKey& key, uint32_t lanebase, uint64_t ctr,
                                           uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {

@@ -217,6 +217,127 @@ k_share_fused(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
   }
 }
 
+// ================================= shamirSecretShare, Fp61, tuned (the C2 kernel)
+// Same contract as k_share_fused<F61, T>; differences (DESIGN.md "share kernel"):
+//  * AES blocks are produced one at a time in a rolled loop with counter-mode
+//    caching (prg_group / prg_block_grouped) and staged through shared memory
+//    ([k][thread] u64, conflict-free), so the code stays small (no instruction
+//    cache misses) and the coefficients are re-read into registers only once;
+//  * the Horner step is 5 instructions (h61_step): 2 IMAD.WIDE, one shift and an
+//    IADD3 / IADD3.X pair;
+//  * four evaluation points are interleaved per rolled iteration (ILP 4).
+// State invariant: y = y0 + y1*2^32 < 2^63 is congruent to the Horner value.
+// One Horner step y <- y*x + c (mod p), x < 2^16, x8 = 8*x.
+//   u  = y0*x + c                     (IMAD.WIDE)          < 2^61 + 2^48
+//   v8 = y1*(8x) = 8*(y1*x)           (IMAD.WIDE)          < 2^50
+//   y1*x*2^32 = vl*2^32 + vh*2^61 with vh = v8 >> 32, vl = (v8 mod 2^32) >> 3, and 2^61 = 1
+//   y' = u + vh + vl*2^32             (IADD3, IADD3.X)     < 2^62 + 2^49
+// VLMODE selects how vl is formed: 0 = shift (ALU pipe), 1 = mul.hi by 2^29 (FMA
+// pipe), 2 = alternate by coefficient index -- a pipe-balancing knob only.
+template <int VLMODE>
+__device__ __forceinline__ void h61_step(uint32_t& y0, uint32_t& y1, uint32_t x, uint32_t x8, uint64_t c,
+                                         uint32_t two29, int k) {
+  uint64_t pr, v8;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(pr) : "r"(y0), "r"(x));
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(v8) : "r"(y1), "r"(x8));
+  const uint32_t vlo = (uint32_t)v8, vh = (uint32_t)(v8 >> 32);
+  uint32_t vl;
+  if (VLMODE == 1 || (VLMODE == 2 && (k & 1))) {
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(vl) : "r"(vlo), "r"(two29));
+  } else {
+    vl = vlo >> 3;
+  }
+  const uint64_t u = pr + c;  // ptxas folds this into the IMAD.WIDE addend
+  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;"
+      : "=r"(y0), "=r"(y1)
+      : "r"((uint32_t)u), "r"(vh), "r"((uint32_t)(u >> 32)), "r"(vl));
+}
+
+__device__ __forceinline__ uint64_t h61_finish(uint32_t y0, uint32_t y1) {
+  const uint64_t y = (uint64_t)y0 | ((uint64_t)y1 << 32);
+  const uint64_t r = (y & F61::P) + (y >> 61);
+  return r >= F61::P ? r - F61::P : r;
+}
+
+static constexpr uint32_t kShare61StageStride = kAesThreads * 8;  // bytes per coefficient row
+
+template <int T, int VLMODE>
+__global__ void __launch_bounds__(kAesThreads, 1)
+k_share61(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0, uint64_t first_block,
+          const uint64_t* __restrict__ secrets, uint64_t N, uint32_t n, uint64_t* __restrict__ out,
+          uint64_t stride_i, uint64_t stride_j, uint32_t two29) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t dyn = smem_u32(dyn_smem);
+  const uint32_t tbase = aes_table_base(dyn_smem);
+  constexpr uint32_t kStageBytes = (T > 0 ? T : 1) * kShare61StageStride;
+  // the 64 KiB alignment slack of the tables is either before or after them
+  uint32_t stage = (dyn + 15u) & ~15u;
+  if (tbase - stage < kStageBytes) stage = tbase + kAesTableBytes;
+  if (stage + kStageBytes > dyn + kAesDynSmem) __trap();  // cannot happen with <= 4 KiB of static smem
+  aes_fill_tables(tbase, g_t0);
+  __syncthreads();
+  uint32_t lanebase = tbase + (threadIdx.x & 31u) * 4u;
+  asm volatile("" : "+r"(lanebase)::"memory");
+  const uint32_t my_stage = stage + threadIdx.x * 8u;
+
+  constexpr uint32_t B = ((uint32_t)(T + 1) * 8 + 15) / 16;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
+    const uint64_t ctr0 = first_block + j * B;
+    if (T > 0) {
+      PrgGroup g;
+      uint64_t gid = ctr0 >> 8;
+      prg_group(key, lanebase, ctr0, g);
+#pragma unroll 1
+      for (uint32_t b = 0; b < B; ++b) {
+        const uint64_t ctr = ctr0 + b;
+        if ((ctr >> 8) != gid) {  // crossed a 256-block group: rare, at most once per secret
+          gid = ctr >> 8;
+          prg_group(key, lanebase, ctr, g);
+        }
+        uint32_t o0, o1, o2, o3;
+        prg_block_grouped(key, lanebase, g, (uint32_t)ctr, o0, o1, o2, o3);
+        // coefficient 2b (b >= 1) and 2b+1 (<= T); row k-1 of the stage
+        const uint32_t a = my_stage + (2 * b) * kShare61StageStride;
+        if (b >= 1) asm volatile("st.shared.v2.u32 [%0+%3], {%1, %2};" ::"r"(a), "r"(o0), "r"(o1), "n"(-(int)kShare61StageStride) : "memory");
+        if (2 * b + 1 <= (uint32_t)T) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(o2), "r"(o3) : "memory");
+      }
+    }
+    uint64_t c[T + 1];
+    c[0] = secrets[j];
+    asm volatile("" : "+l"(c[0]));
+#pragma unroll
+    for (int k = 1; k <= T; ++k) {
+      uint32_t lo, hi;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(my_stage + (uint32_t)(k - 1) * kShare61StageStride) : "memory");
+      // semi-reduced (<= p + 7) is enough: the Horner state is lazy and h61_finish canonicalises
+      c[k] = ((uint64_t)lo | ((uint64_t)(hi & 0x1FFFFFFFu) << 32)) + (hi >> 29);
+      asm volatile("" : "+l"(c[k]));  // keep it one 64-bit register pair: the IMAD.WIDE addend
+    }
+    uint64_t* d = out + j * stride_j;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < n; i0 += 4, d += 4 * stride_i) {
+      uint32_t ya0 = (uint32_t)c[T], ya1 = (uint32_t)(c[T] >> 32);
+      uint32_t yb0 = ya0, yb1 = ya1, yc0 = ya0, yc1 = ya1, yd0 = ya0, yd1 = ya1;
+      uint32_t xa = i0 + 1;
+      asm volatile("" : "+r"(xa));  // keep the point a plain 32-bit register value
+      const uint32_t xb = xa + 1, xc = xa + 2, xd = xa + 3;
+      const uint32_t xa8 = xa << 3, xb8 = xb << 3, xc8 = xc << 3, xd8 = xd << 3;
+#pragma unroll
+      for (int k = T - 1; k >= 0; --k) {
+        h61_step<VLMODE>(ya0, ya1, xa, xa8, c[k], two29, k);
+        h61_step<VLMODE>(yb0, yb1, xb, xb8, c[k], two29, k);
+        h61_step<VLMODE>(yc0, yc1, xc, xc8, c[k], two29, k);
+        h61_step<VLMODE>(yd0, yd1, xd, xd8, c[k], two29, k);
+      }
+      d[0] = h61_finish(ya0, ya1);
+      if (i0 + 1 < n) d[stride_i] = h61_finish(yb0, yb1);
+      if (i0 + 2 < n) d[2 * stride_i] = h61_finish(yc0, yc1);
+      if (i0 + 3 < n) d[3 * stride_i] = h61_finish(yd0, yd1);
+    }
+  }
+}
+
 // PRG -> coefficient planes, for thresholds without a register-resident
 // instantiation: coeffs[k*N + j], k = 0..t (k = 0 is the secret).
 template <class F>

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -319,6 +320,40 @@ static int share_fused_launch(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& ke
   return SCLGPU_OK;
 }
 
+// tuned Fp61 kernel (k_share61): t <= 15, n <= 65535
+static int g_addmode = -1;
+static int share61_addmode() {
+  if (g_addmode < 0) {
+    const char* e = getenv("SCLGPU_ADDMODE");  // tuning knob: vl by 0 shift (ALU), 1 mul.hi (FMA), 2 alternate
+    g_addmode = e ? atoi(e) : 0;
+    if (g_addmode < 0 || g_addmode > 2) g_addmode = 0;
+  }
+  return g_addmode;
+}
+
+template <int T, int ADDMODE>
+static int share61_launch(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t first_block,
+                          const uint64_t* d_secrets, uint64_t N, uint32_t n, uint64_t* d_out, uint64_t si,
+                          uint64_t sj) {
+  RET(aes_opt_in(ctx, k_share61<T, ADDMODE>));
+  const int grid = grid_for(ctx, N, kAesThreads, 1);
+  k_share61<T, ADDMODE><<<grid, kAesThreads, kAesDynSmem, st>>>(key, ctx->d_t0, first_block, d_secrets, N, n,
+                                                              d_out, si, sj, 1u << 29);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <int T>
+static int share61_mode(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t first_block,
+                        const uint64_t* d_secrets, uint64_t N, uint32_t n, uint64_t* d_out, uint64_t si,
+                        uint64_t sj) {
+  switch (share61_addmode()) {
+    case 0: return share61_launch<T, 0>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
+    case 1: return share61_launch<T, 1>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
+    default: return share61_launch<T, 2>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
+  }
+}
+
 template <class F>
 static constexpr int max_fused_t() {
   return F::BYTES == 8 ? 16 : 8;
@@ -341,6 +376,19 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   typedef typename F::E E;
   if (N == 0 || n == 0) return SCLGPU_OK;
   const AesKey key = aes_expand(seed);
+  if constexpr (F::BYTES == 8) {
+    if (t <= 15 && n <= 0xFFFFu && getenv("SCLGPU_SHARE_GENERIC") == nullptr) {
+#define SCLGPU_CASE61(TT) \
+  case TT: return share61_mode<TT>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
+      switch (t) {
+        SCLGPU_CASE61(0) SCLGPU_CASE61(1) SCLGPU_CASE61(2) SCLGPU_CASE61(3) SCLGPU_CASE61(4) SCLGPU_CASE61(5)
+        SCLGPU_CASE61(6) SCLGPU_CASE61(7) SCLGPU_CASE61(8) SCLGPU_CASE61(9) SCLGPU_CASE61(10) SCLGPU_CASE61(11)
+        SCLGPU_CASE61(12) SCLGPU_CASE61(13) SCLGPU_CASE61(14) SCLGPU_CASE61(15)
+        default: break;
+      }
+#undef SCLGPU_CASE61
+    }
+  }
 #define SCLGPU_CASE(TT) \
   case TT: return share_fused_launch<F, (TT <= max_fused_t<F>() ? TT : 0)>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
   if ((int)t <= max_fused_t<F>()) {
