@@ -445,6 +445,96 @@ k_recover_p(const typename F::E* __restrict__ in, uint64_t N, uint32_t n, uint64
   }
 }
 
+// ===================================== shamirRecoverP, Fp61, party-major, tuned
+// Same contract as k_recover_p<F61> for stride_j == 1 and n <= 2048 (the C2 kernel).
+// HBM-bound by design (DESIGN.md "recover kernel"):
+//  * the Lagrange coefficient is split once per CTA into three 21-bit limbs
+//    (b = b0 + b1*2^21 + b2*2^42) and the share into its two 32-bit words, so a
+//    term is six IMAD.WIDE.U32 whose 64-bit addend IS the running sum: products are
+//    < 2^53, 2048 of them fit 64 bits, no carry or reduction inside the loop;
+//  * VEC = 2 secrets per thread through 128-bit loads, eight planes requested
+//    before the first product is formed (the generic kernel had one load in flight);
+//  * one recombination per secret: sum_k,h acc[k][h] * 2^(21k+32h), each term a
+//    61-bit rotation because 2^61 = 1 (mod p).
+__device__ __forceinline__ uint64_t f61_rot(uint64_t acc, int s) {  // acc * 2^s mod p, 0 <= s < 61
+  uint64_t x = (acc & F61::P) + (acc >> 61);
+  x = x >= F61::P ? x - F61::P : x;
+  return s == 0 ? x : (((x << s) & F61::P) | (x >> (61 - s)));
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_recover61_pm(const uint64_t* __restrict__ in, uint64_t N, uint32_t n, uint64_t stride_i,
+               const uint64_t* __restrict__ basis, uint64_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  uint4* lb = reinterpret_cast<uint4*>(dyn_smem);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t b = basis[i];
+    lb[i] = make_uint4((uint32_t)(b & 0x1FFFFFu), (uint32_t)((b >> 21) & 0x1FFFFFu), (uint32_t)(b >> 42), 0u);
+  }
+  __syncthreads();
+  constexpr int BATCH = 8;
+  const uint64_t units = N / VEC;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += stride) {
+    uint64_t acc[VEC][6];
+#pragma unroll
+    for (int s = 0; s < VEC; ++s)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[s][k] = 0;
+    const uint64_t* src = in + u * VEC;
+    uint32_t i0 = 0;
+    auto term = [&](const uint64_t (&v)[VEC], uint32_t i) {
+      const uint4 b = lb[i];
+#pragma unroll
+      for (int s = 0; s < VEC; ++s) {
+        const uint32_t a0 = (uint32_t)v[s], a1 = (uint32_t)(v[s] >> 32);
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[s][0]) : "r"(a0), "r"(b.x));
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[s][1]) : "r"(a0), "r"(b.y));
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[s][2]) : "r"(a0), "r"(b.z));
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[s][3]) : "r"(a1), "r"(b.x));
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[s][4]) : "r"(a1), "r"(b.y));
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[s][5]) : "r"(a1), "r"(b.z));
+      }
+    };
+    for (; i0 + BATCH <= n; i0 += BATCH) {
+      uint64_t v[BATCH][VEC];
+      const uint64_t* p = src + (uint64_t)i0 * stride_i;
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k, p += stride_i) {
+        // volatile: the eight requests are issued back to back, before any product
+        if constexpr (VEC == 2) {
+          asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v[k][0]), "=l"(v[k][1]) : "l"(p));
+        } else {
+          asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v[k][0]) : "l"(p));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) term(v[k], i0 + k);
+    }
+    for (; i0 < n; ++i0) {
+      uint64_t v[VEC];
+      const uint64_t* p = src + (uint64_t)i0 * stride_i;
+#pragma unroll
+      for (int s = 0; s < VEC; ++s) v[s] = __ldg(p + s);
+      term(v, i0);
+    }
+    uint64_t r[VEC];
+#pragma unroll
+    for (int s = 0; s < VEC; ++s) {
+      // weights 2^0, 2^21, 2^42, 2^32, 2^53, 2^74 = 2^13
+      const uint64_t t = f61_rot(acc[s][0], 0) + f61_rot(acc[s][1], 21) + f61_rot(acc[s][2], 42) +
+                         f61_rot(acc[s][3], 32) + f61_rot(acc[s][4], 53) + f61_rot(acc[s][5], 13);  // < 2^64
+      r[s] = F61::from_raw(t);
+    }
+    if constexpr (VEC == 2) {
+      reinterpret_cast<ulonglong2*>(out)[u] = make_ulonglong2(r[0], r[1]);
+    } else {
+      out[u] = r[0];
+    }
+  }
+}
+
 // ============================================================ shamirRecoverD
 // shamir.h:117-140.  mat is (n_checks+1) x m: rows 0..n_checks-1 interpolate
 // through shares 0..m-1 to alphas[m+r]; the last row interpolates to x.

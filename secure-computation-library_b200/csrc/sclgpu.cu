@@ -493,6 +493,21 @@ static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
                         uint32_t n, uint64_t si, uint64_t sj, const typename F::E* d_basis,
                         typename F::E* d_out) {
   if (N == 0) return SCLGPU_OK;
+  if constexpr (F::BYTES == 8) {
+    // party-major planes, the device-native layout: HBM-bound kernel
+    if (sj == 1 && n >= 1 && n <= 2048 && getenv("SCLGPU_RECOVER_GENERIC") == nullptr) {
+      const bool vec2 = (N % 2 == 0) && (si % 2 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(d_shares) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+      const size_t lsm = (size_t)n * 16;
+      if (vec2) {
+        k_recover61_pm<2><<<grid_for(ctx, N / 2, 256, 3), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
+      } else {
+        k_recover61_pm<1><<<grid_for(ctx, N, 256, 4), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
+      }
+      CKL();
+      return SCLGPU_OK;
+    }
+  }
   const size_t smem = (size_t)n * sizeof(typename F::E);
   if (smem > 48 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_p: more than 48 KiB of basis");
   k_recover_p<F><<<grid_for(ctx, N, 256, 8), 256, smem, st>>>(d_shares, N, n, si, sj, d_basis, d_out);

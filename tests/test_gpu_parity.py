@@ -296,6 +296,38 @@ def test_dev_path_party_major_and_secret_major(ctx, pkg, orc):
                 assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(secrets.shape), secrets)
 
 
+@pytest.mark.parametrize("n,N", [(1, 64), (3, 1000), (8, 4096), (9, 4097), (32, 1 << 16), (33, 2050), (100, 513), (2048, 96)])
+def test_recover_p_party_major_kernel_vs_oracle(ctx, pkg, orc, n, N):
+    """k_recover61_pm (party-major planes, limb-split Lagrange coefficients) on ARBITRARY
+    share words, i.e. the full linear map and not only consistent sharings, against
+    shamirRecoverP of the oracle; default nodes and custom (alphas, x)."""
+    import torch
+
+    ctx.use_torch_stream()
+    B = pkg.binding
+    raw = orc.vector_random(61, "recover pm", 7, N * n)          # canonical residues
+    raw[:3] = [0, (1 << 61) - 2, 1]                                # edge residues first
+    sm = raw.reshape(N, n)                                        # SCL's [N][n]
+    d_pm = torch.from_numpy(np.ascontiguousarray(sm.T).view(np.int64)).cuda()
+    d_out = torch.empty(N, dtype=torch.int64, device="cuda")
+    ctx.recover_p_dev(61, d_pm, N, n, d_out, B.PARTY_MAJOR)
+    torch.cuda.synchronize()
+    K = min(N, 2048 if n <= 100 else 4)                           # the real oracle recomputes its basis per secret
+    assert np.array_equal(d_out[:K].cpu().numpy().view(np.uint64), orc.recover_p(61, sm[:K]))
+    if n <= 100:
+        alphas = orc.from_ints([3 * i + 2 for i in range(n)], 61)
+        ctx.recover_p_dev(61, d_pm, N, n, d_out, B.PARTY_MAJOR, alphas=alphas, x=5)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out[:K].cpu().numpy().view(np.uint64), orc.recover_p(61, sm[:K], alphas, 5))
+    # the generic kernel (secret-major input) must agree everywhere
+    d_sm = torch.from_numpy(sm.view(np.int64)).cuda()
+    d_out2 = torch.empty(N, dtype=torch.int64, device="cuda")
+    ctx.recover_p_dev(61, d_pm, N, n, d_out, B.PARTY_MAJOR)
+    ctx.recover_p_dev(61, d_sm, N, n, d_out2, B.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, d_out2)
+
+
 def test_sharded_gpu_engine(ctx, pkg, orc):
     """The N>1 driver logic with the GPU engine: slices shared with the offset counter
     concatenate to the one-PRG batch (what tests/dist_worker.py checks under gloo)."""
