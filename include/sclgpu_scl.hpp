@@ -1,0 +1,287 @@
+// include/sclgpu_scl.hpp -- the host side above the C ABI, in the reference's own
+// language: batched overloads of SCL's hot-path functions on SCL's own types.
+//
+// Header-only C++20.  It is compiled in the USER's SCL build (it includes the
+// reference's headers, which are not part of this repository) and calls
+// libsclgpu.so through include/sclgpu.h only.  Each function names the SCL
+// function it batches; semantics, argument meaning, exception types and what()
+// strings are the reference's.  "Batched" always means: exactly what a loop of N
+// calls of the SCL function on the same util::PRG would produce, including the
+// state the PRG is left in.
+//
+//   scl::ss::shamirSecretShare(secret, t, n, prg)        shamir.h:52-68
+//     -> sclgpu::shamirSecretShare(ctx, secrets, t, n, prg) : Matrix (N x n), row j = SCL's result for secret j
+//   scl::ss::shamirRecoverP(shares[, alphas, x])         shamir.h:82-104
+//     -> sclgpu::shamirRecoverP(ctx, shares[, alphas, x])   : Vector (N)
+//   scl::ss::shamirRecoverD(shares, t)                   shamir.h:117-155
+//     -> sclgpu::shamirRecoverD(ctx, shares, t[, flags])    : Vector (N); throws as SCL unless flags != nullptr
+//   scl::math::Vector<FF>::random(n, prg)                vector.h:508-519
+//     -> sclgpu::randomVector<FF>(ctx, n, prg)
+//   Vector add / subtract / multiplyEntryWise / scalarMultiply / dot / sum   vector.h:192-301
+//   Matrix::multiply(Vector)                             matrix.h:498-513
+//   Beaver combination e*b + d*a + c + e*d               test/scl/protocol/beaver.h:57-61
+//
+// There is no CPU fallback: Context's constructor throws when no B200 is usable.
+#ifndef SCLGPU_SCL_HPP
+#define SCLGPU_SCL_HPP
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "scl/math/fp.h"
+#include "scl/math/matrix.h"
+#include "scl/math/vector.h"
+#include "scl/util/prg.h"
+#include "sclgpu.h"
+
+namespace sclgpu {
+
+namespace detail {
+
+// util::PRG keeps its block counter private and offers no seek (prg.h:167-169).
+// A batched draw must leave the PRG where N sequential SCL calls would, so the
+// counter is reached through an explicit template instantiation (access checks do
+// not apply to explicit-instantiation arguments) -- the reference stays unmodified.
+template <auto Member>
+struct PrgCounterAccess {
+  friend long& prgCounter(scl::util::PRG& prg) { return prg.*Member; }
+};
+long& prgCounter(scl::util::PRG& prg);
+template struct PrgCounterAccess<&scl::util::PRG::m_counter>;
+
+template <class FF>
+struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
+
+#define SCLGPU_SCL_ABI(FIELD, SUF, BYTES_)                                                                    \
+  template <>                                                                                                 \
+  struct Abi<scl::math::FF<FIELD>> {                                                                          \
+    static constexpr std::size_t BYTES = BYTES_;                                                              \
+    static constexpr auto random = &sclgpu_##SUF##_random;                                                    \
+    static constexpr auto share = &sclgpu_##SUF##_shamir_share;                                               \
+    static constexpr auto recover_p = &sclgpu_##SUF##_recover_p;                                              \
+    static constexpr auto recover_d = &sclgpu_##SUF##_recover_d;                                              \
+    static constexpr auto vec_add = &sclgpu_##SUF##_vec_add;                                                  \
+    static constexpr auto vec_sub = &sclgpu_##SUF##_vec_sub;                                                  \
+    static constexpr auto vec_mul = &sclgpu_##SUF##_vec_mul;                                                  \
+    static constexpr auto vec_scale = &sclgpu_##SUF##_vec_scale;                                              \
+    static constexpr auto vec_muladd = &sclgpu_##SUF##_vec_muladd;                                            \
+    static constexpr auto dot = &sclgpu_##SUF##_dot;                                                          \
+    static constexpr auto sum = &sclgpu_##SUF##_sum;                                                          \
+    static constexpr auto matvec = &sclgpu_##SUF##_matvec;                                                    \
+  }
+SCLGPU_SCL_ABI(scl::math::ff::Mersenne61, fp61, 8);
+SCLGPU_SCL_ABI(scl::math::ff::Mersenne127, fp127, 16);
+#undef SCLGPU_SCL_ABI
+
+// SCL elements are trivially copyable wrappers around one uint64_t / __uint128_t
+// holding the canonical residue (ff.h:313-314), i.e. exactly FF::write's bytes.
+template <class FF, class P>
+auto* raw(P* p) {
+  static_assert(sizeof(FF) == Abi<FF>::BYTES, "unexpected SCL element layout");
+  if constexpr (Abi<FF>::BYTES == 8) {
+    if constexpr (std::is_const_v<P>) return reinterpret_cast<const std::uint64_t*>(p);
+    else return reinterpret_cast<std::uint64_t*>(p);
+  } else {
+    if constexpr (std::is_const_v<P>) return reinterpret_cast<const void*>(p);
+    else return reinterpret_cast<void*>(p);
+  }
+}
+
+inline std::uint64_t shareBlocks(std::size_t bytes, std::size_t t) { return ((t + 1) * bytes + 15) / 16; }
+
+}  // namespace detail
+
+// One context per device per process (calls are serialised by the caller, as SCL
+// itself is single-threaded).
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    if (sclgpu_init(device, &m_ctx) != SCLGPU_OK) {
+      throw std::runtime_error("sclgpu: no usable sm_100 device (there is no CPU fallback)");
+    }
+  }
+  ~Context() { sclgpu_destroy(m_ctx); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  sclgpu_ctx* get() const { return m_ctx; }
+  std::uint64_t launches() const { return sclgpu_launch_count(m_ctx); }
+
+  // SCLGPU_EINVAL -> std::invalid_argument, ELOGIC/EDETECT -> std::logic_error,
+  // with the reference's own message (sclgpu_last_error).
+  void check(int rc) const {
+    if (rc == SCLGPU_OK) return;
+    const std::string msg = sclgpu_last_error(m_ctx);
+    if (rc == SCLGPU_EINVAL) throw std::invalid_argument(msg);
+    if (rc == SCLGPU_ELOGIC || rc == SCLGPU_EDETECT) throw std::logic_error(msg);
+    throw std::runtime_error(std::string("sclgpu: ") + sclgpu_strerror(rc) + ": " + msg);
+  }
+
+ private:
+  sclgpu_ctx* m_ctx = nullptr;
+};
+
+// ---- Vector<FF>::random(n, prg), vector.h:508-519 (ONE next() of n*byteSize bytes)
+template <class FF>
+scl::math::Vector<FF> randomVector(Context& ctx, std::size_t n, scl::util::PRG& prg) {
+  using A = detail::Abi<FF>;
+  std::vector<FF> v(n);
+  long& ctr = detail::prgCounter(prg);
+  const auto seed = prg.Seed();
+  ctx.check(A::random(ctx.get(), seed.data(), (std::uint64_t)ctr, n, detail::raw<FF>(v.data())));
+  ctr += (long)((n * A::BYTES + 15) / 16);
+  return scl::math::Vector<FF>(std::move(v));
+}
+
+// ---- shamirSecretShare on every element of `secrets`, shamir.h:52-68
+template <class FF>
+scl::math::Matrix<FF> shamirSecretShare(Context& ctx, const scl::math::Vector<FF>& secrets, std::size_t t,
+                                        std::size_t n, scl::util::PRG& prg) {
+  using A = detail::Abi<FF>;
+  const std::size_t N = secrets.size();
+  if (N == 0 || n == 0) {
+    detail::prgCounter(prg) += (long)(N * detail::shareBlocks(A::BYTES, t));
+    return scl::math::Matrix<FF>();
+  }
+  scl::math::Matrix<FF> shares(N, n);
+  long& ctr = detail::prgCounter(prg);
+  const auto seed = prg.Seed();
+  ctx.check(A::share(ctx.get(), detail::raw<FF>(secrets.toStlVector().data()), N, (std::uint32_t)t,
+                     (std::uint32_t)n, seed.data(), (std::uint64_t)ctr, detail::raw<FF>(&shares(0, 0))));
+  ctr += (long)(N * detail::shareBlocks(A::BYTES, t));
+  return shares;
+}
+
+// ---- shamirRecoverP(shares), shamir.h:100-104: row j of `shares` = one sharing
+template <class FF>
+scl::math::Vector<FF> shamirRecoverP(Context& ctx, const scl::math::Matrix<FF>& shares) {
+  using A = detail::Abi<FF>;
+  std::vector<FF> out(shares.rows());
+  if (shares.rows() == 0) return scl::math::Vector<FF>(std::move(out));
+  ctx.check(A::recover_p(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(shares)(0, 0)),
+                         shares.rows(), (std::uint32_t)shares.cols(), nullptr, nullptr,
+                         detail::raw<FF>(out.data())));
+  return scl::math::Vector<FF>(std::move(out));
+}
+
+// ---- shamirRecoverP(shares, alphas, x), shamir.h:82-87
+template <class FF>
+scl::math::Vector<FF> shamirRecoverP(Context& ctx, const scl::math::Matrix<FF>& shares,
+                                     const scl::math::Vector<FF>& alphas, const FF& x) {
+  using A = detail::Abi<FF>;
+  if (alphas.size() != shares.cols()) throw std::invalid_argument("Vec sizes mismatch");  // vector.h:483
+  std::vector<FF> out(shares.rows());
+  if (shares.rows() == 0) return scl::math::Vector<FF>(std::move(out));
+  ctx.check(A::recover_p(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(shares)(0, 0)),
+                         shares.rows(), (std::uint32_t)shares.cols(),
+                         detail::raw<FF>(alphas.toStlVector().data()), detail::raw<FF>(&x),
+                         detail::raw<FF>(out.data())));
+  return scl::math::Vector<FF>(std::move(out));
+}
+
+// ---- shamirRecoverD(shares, t), shamir.h:152-155.  With flags == nullptr the call
+// throws std::logic_error("error detected during recovery") if ANY sharing is
+// inconsistent (what the loop over SCL's function would do at the first one).
+// With flags != nullptr nothing is thrown for inconsistent sharings: (*flags)[j] = 1
+// and result[j] = 0 for those.
+template <class FF>
+scl::math::Vector<FF> shamirRecoverD(Context& ctx, const scl::math::Matrix<FF>& shares, std::size_t t,
+                                     std::vector<std::uint8_t>* flags = nullptr) {
+  using A = detail::Abi<FF>;
+  const std::size_t N = shares.rows();
+  std::vector<FF> out(N);
+  std::vector<std::uint8_t> err(N);
+  std::uint64_t n_bad = 0;
+  const int rc = A::recover_d(
+      ctx.get(), N ? detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(shares)(0, 0)) : nullptr, N,
+      (std::uint32_t)shares.cols(), (std::uint32_t)t, nullptr, 0, 0, nullptr, detail::raw<FF>(out.data()),
+      err.data(), &n_bad);
+  if (rc == SCLGPU_EDETECT && flags != nullptr) {
+    *flags = std::move(err);
+    return scl::math::Vector<FF>(std::move(out));
+  }
+  ctx.check(rc);
+  if (flags != nullptr) *flags = std::move(err);
+  return scl::math::Vector<FF>(std::move(out));
+}
+
+// ---- Vector entrywise operations, vector.h:192-301 ("Vec sizes mismatch", :481-485)
+namespace detail {
+template <class FF, class Fn>
+scl::math::Vector<FF> binop(Context& ctx, Fn fn, const scl::math::Vector<FF>& a, const scl::math::Vector<FF>& b) {
+  if (a.size() != b.size()) throw std::invalid_argument("Vec sizes mismatch");
+  std::vector<FF> out(a.size());
+  ctx.check(fn(ctx.get(), raw<FF>(a.toStlVector().data()), raw<FF>(b.toStlVector().data()), a.size(),
+               raw<FF>(out.data())));
+  return scl::math::Vector<FF>(std::move(out));
+}
+}  // namespace detail
+
+template <class FF>
+scl::math::Vector<FF> add(Context& ctx, const scl::math::Vector<FF>& a, const scl::math::Vector<FF>& b) {
+  return detail::binop<FF>(ctx, detail::Abi<FF>::vec_add, a, b);
+}
+template <class FF>
+scl::math::Vector<FF> subtract(Context& ctx, const scl::math::Vector<FF>& a, const scl::math::Vector<FF>& b) {
+  return detail::binop<FF>(ctx, detail::Abi<FF>::vec_sub, a, b);
+}
+template <class FF>
+scl::math::Vector<FF> multiplyEntryWise(Context& ctx, const scl::math::Vector<FF>& a,
+                                        const scl::math::Vector<FF>& b) {
+  return detail::binop<FF>(ctx, detail::Abi<FF>::vec_mul, a, b);
+}
+template <class FF>
+scl::math::Vector<FF> scalarMultiply(Context& ctx, const scl::math::Vector<FF>& a, const FF& s) {
+  std::vector<FF> out(a.size());
+  ctx.check(detail::Abi<FF>::vec_scale(ctx.get(), detail::raw<FF>(a.toStlVector().data()), detail::raw<FF>(&s),
+                                       a.size(), detail::raw<FF>(out.data())));
+  return scl::math::Vector<FF>(std::move(out));
+}
+template <class FF>
+FF dot(Context& ctx, const scl::math::Vector<FF>& a, const scl::math::Vector<FF>& b) {
+  if (a.size() != b.size()) throw std::invalid_argument("Vec sizes mismatch");
+  FF out;
+  ctx.check(detail::Abi<FF>::dot(ctx.get(), detail::raw<FF>(a.toStlVector().data()),
+                                 detail::raw<FF>(b.toStlVector().data()), a.size(), detail::raw<FF>(&out)));
+  return out;
+}
+template <class FF>
+FF sum(Context& ctx, const scl::math::Vector<FF>& a) {
+  FF out;
+  ctx.check(detail::Abi<FF>::sum(ctx.get(), detail::raw<FF>(a.toStlVector().data()), a.size(),
+                                 detail::raw<FF>(&out)));
+  return out;
+}
+// z = e*b + d*a + c + e*d over Vectors (the Beaver combination, beaver.h:57-61)
+template <class FF>
+scl::math::Vector<FF> beaverCombine(Context& ctx, const scl::math::Vector<FF>& e, const scl::math::Vector<FF>& b,
+                                    const scl::math::Vector<FF>& d, const scl::math::Vector<FF>& a,
+                                    const scl::math::Vector<FF>& c) {
+  const std::size_t n = e.size();
+  if (b.size() != n || d.size() != n || a.size() != n || c.size() != n)
+    throw std::invalid_argument("Vec sizes mismatch");
+  std::vector<FF> z(n);
+  ctx.check(detail::Abi<FF>::vec_muladd(ctx.get(), detail::raw<FF>(e.toStlVector().data()),
+                                        detail::raw<FF>(b.toStlVector().data()),
+                                        detail::raw<FF>(d.toStlVector().data()),
+                                        detail::raw<FF>(a.toStlVector().data()),
+                                        detail::raw<FF>(c.toStlVector().data()), n, detail::raw<FF>(z.data())));
+  return scl::math::Vector<FF>(std::move(z));
+}
+
+// ---- Matrix::multiply(Vector), matrix.h:498-513
+template <class FF>
+scl::math::Vector<FF> multiply(Context& ctx, const scl::math::Matrix<FF>& A, const scl::math::Vector<FF>& x) {
+  if (A.cols() != x.size()) throw std::invalid_argument("matmul: this->cols() != vec.size()");  // matrix.h:500
+  std::vector<FF> y(A.rows());
+  ctx.check(detail::Abi<FF>::matvec(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(A)(0, 0)),
+                                    (std::uint32_t)A.rows(), (std::uint32_t)A.cols(),
+                                    detail::raw<FF>(x.toStlVector().data()), detail::raw<FF>(y.data())));
+  return scl::math::Vector<FF>(std::move(y));
+}
+
+}  // namespace sclgpu
+
+#endif  // SCLGPU_SCL_HPP

@@ -1,0 +1,177 @@
+// tests/cpp/test_shim.cc -- TEST: the C++ host mirror (include/sclgpu_scl.hpp) used
+// exactly as an SCL user would, on SCL's own types, checked in-process against the
+// reference's own CPU functions (the unmodified reference sources are compiled into
+// this test binary, like oracle/_ref; see tests/cpp/Makefile).  Bit-exact or abort.
+//
+// The cases follow the reference's own tests: test/scl/ss/test_shamir.cc:34-109
+// (share -> recoverP, recoverD ok / tampered -> "error detected during recovery",
+// custom alphas), test/scl/math/test_vector.cc, test_matrix.cc:175-222 (mat-vec),
+// test/scl/util/test_prg.cc (determinism of the stream after a draw).
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "scl/math/fp.h"
+#include "scl/math/matrix.h"
+#include "scl/math/vector.h"
+#include "scl/ss/shamir.h"
+#include "scl/util/prg.h"
+#include "sclgpu_scl.hpp"
+
+using scl::util::PRG;
+namespace ss = scl::ss;
+namespace math = scl::math;
+
+static int g_checks = 0;
+#define REQUIRE(cond)                                                          \
+  do {                                                                         \
+    ++g_checks;                                                                \
+    if (!(cond)) {                                                             \
+      std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);   \
+      std::exit(1);                                                            \
+    }                                                                          \
+  } while (0)
+
+template <class F>
+static bool throwsLogic(F&& f, const std::string& what) {
+  try {
+    f();
+  } catch (const std::logic_error& e) {
+    return what == e.what();
+  } catch (...) {
+    return false;
+  }
+  return false;
+}
+template <class F>
+static bool throwsInvalid(F&& f, const std::string& what) {
+  try {
+    f();
+  } catch (const std::invalid_argument& e) {
+    return what == e.what();
+  } catch (...) {
+    return false;
+  }
+  return false;
+}
+
+int main() {
+  using Fp61 = math::Fp<61>;
+  using Fp127 = math::Fp<127>;
+  sclgpu::Context ctx(0);  // throws without a B200: no CPU fallback
+
+  // ---- test_shamir.cc:34-40 in batch form: share(123, t=3, n=4) -> recoverP
+  {
+    PRG a = PRG::create("shamir passive"), b = PRG::create("shamir passive");
+    math::Vector<Fp61> secret = {Fp61(123), Fp61(124)};
+    const auto m = sclgpu::shamirSecretShare(ctx, secret, 2, 5, b);
+    const auto s0 = ss::shamirSecretShare(Fp61(123), 2, 5, a);
+    const auto s1 = ss::shamirSecretShare(Fp61(124), 2, 5, a);
+    for (int i = 0; i < 5; ++i) REQUIRE(m(0, i) == s0[i] && m(1, i) == s1[i]);
+    REQUIRE(m(0, 0).toString() == "bc6378a9608f2f4");  // SURVEY 8c golden vector
+    REQUIRE(sclgpu::shamirRecoverP(ctx, m)[0] == Fp61(123));
+  }
+
+  // ---- batches, both fields, PRG state, recoverP
+  for (auto [N, t, n] : {std::tuple<std::size_t, std::size_t, std::size_t>{3000, 2, 5}, {1500, 15, 32}, {1, 0, 1}, {257, 7, 16}}) {
+    PRG sprg = PRG::create("secrets");
+    const auto secrets = math::Vector<Fp61>::random(N, sprg);
+    PRG cpu = PRG::create("shamir bench"), gpu = PRG::create("shamir bench");
+    (void)cpu.next(48);
+    (void)gpu.next(48);
+    const auto got = sclgpu::shamirSecretShare(ctx, secrets, t, n, gpu);
+    REQUIRE(got.rows() == N && got.cols() == n);
+    for (std::size_t j = 0; j < N; ++j) {
+      const auto want = ss::shamirSecretShare(secrets[j], t, n, cpu);
+      for (std::size_t i = 0; i < n; ++i) REQUIRE(got(j, i) == want[i]);
+    }
+    REQUIRE(cpu.next(40) == gpu.next(40));
+    const auto rec = sclgpu::shamirRecoverP(ctx, got);
+    for (std::size_t j = 0; j < N; ++j) REQUIRE(rec[j] == secrets[j]);
+    // test_shamir.cc:42-66: reconstruct at x = 27 from the same nodes
+    const auto alphas = math::Vector<Fp61>::range(1, n + 1);
+    const auto at27 = sclgpu::shamirRecoverP(ctx, got, alphas, Fp61(27));
+    for (std::size_t j = 0; j < N; j += 97) {
+      std::vector<Fp61> row(n);
+      for (std::size_t i = 0; i < n; ++i) row[i] = got(j, i);
+      REQUIRE(at27[j] == ss::shamirRecoverP(math::Vector<Fp61>(row), alphas, Fp61(27)));
+    }
+  }
+  {
+    const std::size_t N = 600, t = 7, n = 16;
+    PRG sprg = PRG::create("secrets127");
+    const auto secrets = math::Vector<Fp127>::random(N, sprg);
+    PRG cpu = PRG::create("m127"), gpu = PRG::create("m127");
+    auto got = sclgpu::shamirSecretShare(ctx, secrets, t, n, gpu);
+    for (std::size_t j = 0; j < N; ++j) {
+      const auto want = ss::shamirSecretShare(secrets[j], t, n, cpu);
+      for (std::size_t i = 0; i < n; ++i) REQUIRE(got(j, i) == want[i]);
+    }
+    REQUIRE(cpu.next(16) == gpu.next(16));
+    // ---- test_shamir.cc:68-79: recoverD ok, then a tampered share -> throws
+    const auto ok = sclgpu::shamirRecoverD(ctx, got, t);
+    for (std::size_t j = 0; j < N; ++j) REQUIRE(ok[j] == secrets[j]);
+    got(5, 14) = got(5, 14) + Fp127(1);   // index 2t: never checked by the reference (shamir.h:129)
+    got(6, 15) = Fp127(4);                // beyond 2t: never read
+    const auto still_ok = sclgpu::shamirRecoverD(ctx, got, t);
+    REQUIRE(still_ok[5] == secrets[5] && still_ok[6] == secrets[6]);
+    got(9, 2) = Fp127(4);                 // test_shamir.cc:76 "shares[2] = 4"
+    got(11, 13) = got(11, 13) + Fp127(1);
+    REQUIRE(throwsLogic([&] { (void)sclgpu::shamirRecoverD(ctx, got, t); }, "error detected during recovery"));
+    std::vector<std::uint8_t> flags;
+    const auto out = sclgpu::shamirRecoverD(ctx, got, t, &flags);
+    for (std::size_t j = 0; j < N; ++j) {
+      std::vector<Fp127> row(n);
+      for (std::size_t i = 0; i < n; ++i) row[i] = got(j, i);
+      bool threw = false;
+      Fp127 want;
+      try {
+        want = ss::shamirRecoverD(math::Vector<Fp127>(row), t);
+      } catch (const std::logic_error&) {
+        threw = true;
+      }
+      REQUIRE(threw == (flags[j] != 0));
+      REQUIRE(threw == (j == 9 || j == 11));
+      if (!threw) REQUIRE(out[j] == want);
+    }
+    // not enough shares (shamir.h:122-124)
+    math::Matrix<Fp127> few(3, 2 * t - 1);
+    REQUIRE(throwsLogic([&] { (void)sclgpu::shamirRecoverD(ctx, few, t); },
+                        "not enough shares provided to detect errors"));
+  }
+
+  // ---- Vector::random, entrywise ops, dot, sum, Beaver combination, mat-vec
+  {
+    const std::size_t n = 10001;
+    PRG a = PRG::create("vec"), b = PRG::create("vec");
+    (void)a.next(5);  // a 5-byte draw still consumes one whole block (prg.cc:129-133)
+    (void)b.next(5);
+    const auto v = sclgpu::randomVector<Fp61>(ctx, n, b);
+    REQUIRE(v.equals(math::Vector<Fp61>::random(n, a)));
+    const auto w = sclgpu::randomVector<Fp61>(ctx, n, b);
+    REQUIRE(w.equals(math::Vector<Fp61>::random(n, a)));
+    const auto v127 = sclgpu::randomVector<Fp127>(ctx, 333, b);
+    REQUIRE(v127.equals(math::Vector<Fp127>::random(333, a)));
+    REQUIRE(sclgpu::add(ctx, v, w).equals(v.add(w)));
+    REQUIRE(sclgpu::subtract(ctx, v, w).equals(v.subtract(w)));
+    REQUIRE(sclgpu::multiplyEntryWise(ctx, v, w).equals(v.multiplyEntryWise(w)));
+    REQUIRE(sclgpu::scalarMultiply(ctx, v, w[3]).equals(v.scalarMultiply(w[3])));
+    REQUIRE(sclgpu::dot(ctx, v, w) == v.dot(w));
+    REQUIRE(sclgpu::sum(ctx, v) == v.sum());
+    const auto e = v, bb = w, d = sclgpu::add(ctx, v, v), aa = sclgpu::multiplyEntryWise(ctx, w, w), c = sclgpu::subtract(ctx, w, v);
+    const auto z = e.multiplyEntryWise(bb).add(d.multiplyEntryWise(aa)).add(c).add(e.multiplyEntryWise(d));
+    REQUIRE(sclgpu::beaverCombine(ctx, e, bb, d, aa, c).equals(z));
+    REQUIRE(throwsInvalid([&] { (void)sclgpu::add(ctx, v, v127.size() ? math::Vector<Fp61>(3) : v); }, "Vec sizes mismatch"));
+
+    PRG ma = PRG::create("mat A"), xa = PRG::create("vec x");
+    const auto A = math::Matrix<Fp61>::random(64, 64, ma);
+    const auto x = math::Vector<Fp61>::random(64, xa);
+    const auto y = sclgpu::multiply(ctx, A, x);
+    REQUIRE(y.equals(A.multiply(x)));
+    REQUIRE(y[0].toString() == "1172bf06cc5d2e8b");  // SURVEY 8c golden vector
+    REQUIRE(throwsInvalid([&] { (void)sclgpu::multiply(ctx, A, v); }, "matmul: this->cols() != vec.size()"));
+  }
+  std::printf("SHIM_OK checks=%d launches=%llu\n", g_checks, (unsigned long long)ctx.launches());
+  return 0;
+}
