@@ -17,6 +17,7 @@
 
 #include "../../include/sclgpu.h"
 #include "kernels.cuh"
+#include "share_tc.h"
 
 using namespace sclgpu;
 
@@ -36,6 +37,8 @@ struct sclgpu_ctx {
   std::string last_error;
   std::set<const void*> smem_opted;   // kernels with the 192 KiB opt-in done
   std::map<std::string, void*> basis_cache;  // (field, nodes, xs) -> device matrix
+  std::map<uint32_t, void*> tc_bmat_cache;   // (t, n) -> Vandermonde limb image of k_share61_tc
+  bool tc_prepared = false;
 };
 
 static constexpr int kMaxPartials = 2048;
@@ -173,6 +176,7 @@ extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
+  for (auto& kv : ctx->tc_bmat_cache) cudaFree(kv.second);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
     if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
@@ -320,6 +324,67 @@ static int share_fused_launch(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& ke
   return SCLGPU_OK;
 }
 
+// tensor-core Fp61 kernel (share_tc.cu): t <= 15, n <= 32.  The B operand holds the
+// bytes of C[i][k][a] = (i+1)^k * 2^(8a) mod p (the Vandermonde entry of party i,
+// matrix.h:445-460, pre-multiplied by the weight of coefficient byte a): small
+// constants, computed here once per (t, n) and kept on the device.
+static int g_share_tc = -1;
+static bool share_tc_enabled() {
+  if (g_share_tc < 0) {
+    const char* e = getenv("SCLGPU_SHARE_TC");  // 0 = integer-pipe kernel (k_share61), 1 = tcgen05 kernel
+    g_share_tc = e ? (atoi(e) != 0) : 1;
+  }
+  return g_share_tc != 0;
+}
+
+static int share61_tc_bmat(sclgpu_ctx* ctx, cudaStream_t st, uint32_t t, uint32_t n, const void** d_bmat) {
+  const uint32_t key = (t << 8) | n;
+  auto it = ctx->tc_bmat_cache.find(key);
+  if (it != ctx->tc_bmat_cache.end()) {
+    *d_bmat = it->second;
+    return SCLGPU_OK;
+  }
+  std::vector<uint8_t> img(kTcBmatBytes, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    uint64_t pw = 1;  // (i+1)^k
+    for (uint32_t k = 0; k <= t; ++k) {
+      for (uint32_t a = 0; a < 8; ++a) {
+        const uint64_t c = F61::mul(pw, 1ull << (8 * a));
+        for (uint32_t s = 0; s < 8; ++s) img[tc_bmat_offset(i * 8 + s, k * 8 + a)] = (uint8_t)(c >> (8 * s));
+      }
+      pw = F61::mul(pw, (uint64_t)(i + 1));
+    }
+  }
+  void* d = nullptr;
+  CK(cudaMalloc(&d, kTcBmatBytes));
+  cudaError_t e = cudaMemcpyAsync(d, img.data(), kTcBmatBytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // img is a local
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return cuda_fail(ctx, e, "share_tc constants");
+  }
+  ctx->tc_bmat_cache[key] = d;
+  *d_bmat = d;
+  return SCLGPU_OK;
+}
+
+static int share61_tc_on(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t first_block,
+                         const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_out,
+                         uint64_t si, uint64_t sj) {
+  if (!ctx->tc_prepared) {
+    CK(share61_tc_prepare());
+    ctx->tc_prepared = true;
+  }
+  const void* d_bmat = nullptr;
+  RET(share61_tc_bmat(ctx, st, t, n, &d_bmat));
+  const uint64_t tiles = (N + 127) / 128;
+  const int grid = (int)std::min<uint64_t>((tiles + kTcGroups - 1) / kTcGroups, (uint64_t)ctx->sm_count);
+  ctx->launches++;
+  cudaError_t e = share61_tc_launch(st, grid, key, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n, d_out, si, sj);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
+  return SCLGPU_OK;
+}
+
 // tuned Fp61 kernel (k_share61): t <= 15, n <= 65535
 static int g_addmode = -1;
 static int share61_addmode() {
@@ -377,6 +442,8 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   if (N == 0 || n == 0) return SCLGPU_OK;
   const AesKey key = aes_expand(seed);
   if constexpr (F::BYTES == 8) {
+    if (t <= kTcMaxT && n <= kTcMaxParties && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr)
+      return share61_tc_on(ctx, st, key, first_block, d_secrets, N, t, n, d_out, si, sj);
     if (t <= 15 && n <= 0xFFFFu && getenv("SCLGPU_SHARE_GENERIC") == nullptr) {
 #define SCLGPU_CASE61(TT) \
   case TT: return share61_mode<TT>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);

@@ -1,0 +1,256 @@
+// share_tc.cu -- shamirSecretShare for Fp61 on the 5th-generation tensor cores.
+//
+// Reference path replaced: ss::shamirSecretShare (include/scl/ss/shamir.h:52-68) =
+// Vector::random(t+1, prg) (vector.h:508-519, prg.cc:124-146), c[0] = secret,
+// n Horner evaluations at x = 1..n (poly.h:56-64) -- N calls on one PRG.
+//
+// Formulation (DESIGN.md "tensor-core share kernel").  The shares of one secret are
+// the Vandermonde product  share_i = sum_k c_k * (i+1)^k  (the reference's own
+// test/scl/math/test_matrix.cc:342-365 states this identity).  A coefficient is
+// used through its eight BYTES c_k = sum_a c_{k,a} 2^(8a) -- the raw little-endian
+// keystream word, no reduction needed because the map is linear -- and the constant
+//     C_{i,k,a} = (i+1)^k * 2^(8a) mod p       (61 bits)
+// through its eight bytes C_{i,k,a} = sum_s C_{i,k,a,s} 2^(8s).  Then
+//     share_i = sum_s 2^(8s) * acc_{i,s},   acc_{i,s} = sum_{k,a} c_{k,a} * C_{i,k,a,s}
+// and acc is a u8 x u8 -> s32 matrix product with K = 8(t+1) <= 128 (acc < 2^23):
+//     D[128 secrets][8 parties x 8 limbs] += A[128 secrets][K] * B[K][64]
+// issued as tcgen05.mma.kind::i8 (M=128, N=64, K=32 per instruction), A = the
+// coefficient bytes exactly as the PRG emits them (one 128-byte row per secret,
+// K-major, 128B-swizzled), B = the constant limbs (32 KiB, built on the host once per
+// (t, n), resident in shared memory), D in tensor memory.  The epilogue reads the
+// eight 23-bit limbs of a share with tcgen05.ld and recombines them mod 2^61 - 1.
+//
+// One CTA per SM, 384 threads = 3 groups of 4 warps; a group owns one 128-secret
+// tile at a time: every thread draws its secret's keystream (T-table AES-CTR,
+// aes_ctr.cuh) straight into its A row, one elected thread issues the MMAs for the
+// group, each warp drains its own 32 TMEM lanes.  Groups run unsynchronised with
+// respect to each other, so one group's AES (LSU + ALU pipes) overlaps another's
+// MMA and epilogue.  Two 64-column accumulators per group: the MMA of pass p+1 runs
+// under the epilogue of pass p.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "aes_ctr.cuh"
+#include "field.cuh"
+#include "share_tc.h"
+
+namespace sclgpu {
+
+static constexpr uint32_t kTcATile = 16384;  // 128 rows x 128 B
+static constexpr uint32_t kTcPassCols = 64;  // 8 parties x 8 limbs per MMA pass
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows), version 1 (sm_100).
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor: D = s32, A = B = u8, both K-major, M = 128, N = 64
+static constexpr uint32_t kTcIdesc = (2u << 4) | ((kTcPassCols >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void group_sync(uint32_t g) {
+  asm volatile("bar.sync %0, 128;" ::"r"(g + 1u) : "memory");
+}
+
+// 32 lanes x 64 columns of 32 bits: thread l of the warp gets lane (base + l)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+        "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+        "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+        "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// share = sum_s v[s] * 2^(8s) mod p, v[s] < 2^23; canonical result
+__device__ __forceinline__ uint64_t tc_combine(const uint32_t* v) {
+  const uint32_t p01 = v[0] + (v[1] << 8), p23 = v[2] + (v[3] << 8);  // < 2^32
+  const uint32_t p45 = v[4] + (v[5] << 8), p67 = v[6] + (v[7] << 8);
+  // p67 * 2^48 = (p67 mod 2^13) * 2^48 + (p67 >> 13) * 2^61, and 2^61 = 1
+  const uint64_t R = (uint64_t)p01 + ((uint64_t)p23 << 16) + ((uint64_t)p45 << 32) +
+                     ((uint64_t)(p67 & 0x1FFFu) << 48) + (uint64_t)(p67 >> 13);  // < 2^64
+  const uint64_t r = (R & F61::P) + (R >> 61);
+  return r >= F61::P ? r - F61::P : r;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_share61_tc(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
+             const uint4* __restrict__ g_bmat, uint64_t first_block, const uint64_t* __restrict__ secrets,
+             uint64_t N, uint32_t t, uint32_t n, uint64_t* __restrict__ out, uint64_t stride_i,
+             uint64_t stride_j) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t dyn = smem_u32(dyn_smem);
+  const uint32_t tbase = aes_table_base(dyn_smem);        // AES tables, 64 KiB aligned (aes_ctr.cuh)
+  const uint32_t a_base = (dyn + 1023u) & ~1023u;         // 3 A tiles below the tables
+  const uint32_t b_base = tbase + kAesTableBytes;         // B limbs above them
+  const uint32_t ctl = b_base + kTcBmatBytes;             // 6 mbarriers + the TMEM base address
+  if (a_base + kTcGroups * kTcATile > tbase || ctl + 64u > dyn + kTcDynSmem) __trap();
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  aes_fill_tables(tbase, g_t0);
+  for (uint32_t e = tid; e < kTcBmatBytes / 16; e += kTcThreads) {
+    const uint4 w = __ldg(g_bmat + e);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ctl + 48u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint32_t i = 0; i < 2 * kTcGroups; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctl + 8u * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B was written through the generic proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(ctl + 48u) : "memory");
+
+  uint32_t lanebase = tbase + (tid & 31u) * 4u;
+  asm volatile("" : "+r"(lanebase)::"memory");
+
+  const uint32_t g = tid >> 7, gt = tid & 127u;            // group, thread in group = row of the tile
+  const uint32_t a_tile = a_base + g * kTcATile;
+  const uint32_t xr = gt & 7u;
+  const uint32_t row = a_tile + (gt >> 3) * 1024u + xr * 128u;
+  const uint32_t acc0 = tmem + g * (2u * kTcPassCols);     // two 64-column accumulators
+  const uint32_t lane_off = ((warp & 3u) * 32u) << 16;     // this warp's TMEM lanes
+  const uint32_t mbar0 = ctl + 16u * g, mbar1 = mbar0 + 8u;
+  uint32_t ph0 = 0, ph1 = 0;
+
+  const uint32_t nblk = ((t + 1u) * 8u + 15u) / 16u;       // keystream blocks per secret (prg.cc:129-133)
+  const uint32_t ksteps = ((t + 1u) * 8u + 31u) / 32u;     // K = 32 bytes per MMA
+  const uint32_t npass = (n + 7u) / 8u;
+  const uint64_t tiles = (N + 127u) / 128u;
+
+  auto issue_pass = [&](uint32_t p) {  // one elected thread
+    const uint32_t d = acc0 + (p & 1u) * kTcPassCols;
+    for (uint32_t ks = 0; ks < ksteps; ++ks)
+      tc_mma(d, tc_desc(a_tile + ks * 32u), tc_desc(b_base + p * (kTcPassCols * 128u) + ks * 32u), ks);
+    tc_commit((p & 1u) ? mbar1 : mbar0);
+  };
+
+  for (uint64_t tile = (uint64_t)blockIdx.x * kTcGroups + g; tile < tiles; tile += (uint64_t)gridDim.x * kTcGroups) {
+    const uint64_t j = tile * 128u + gt;
+    const bool valid = j < N;
+    if (valid) {
+      const uint64_t sec = secrets[j];
+      const uint64_t ctr0 = first_block + j * nblk;
+      if (t == 0) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(row + (xr << 4)), "r"((uint32_t)sec), "r"((uint32_t)(sec >> 32)), "r"(0u) : "memory");
+      } else {
+        PrgGroup grp;
+        uint64_t gid = ctr0 >> 8;
+        prg_group(key, lanebase, ctr0, grp);
+#pragma unroll 1
+        for (uint32_t b = 0; b < nblk; ++b) {
+          const uint64_t ctr = ctr0 + b;
+          if ((ctr >> 8) != gid) {  // crossed a 256-block group: at most once per secret
+            gid = ctr >> 8;
+            prg_group(key, lanebase, ctr, grp);
+          }
+          uint32_t o0, o1, o2, o3;
+          prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+          if (b == 0) {  // slot 0 of the draw is replaced by the secret (shamir.h:56-57)
+            o0 = (uint32_t)sec;
+            o1 = (uint32_t)(sec >> 32);
+          }
+          // block b = coefficients 2b, 2b+1 = 16-byte chunk b of the row (chunk ^ row%8: 128B swizzle)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((b ^ xr) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        }
+      }
+    }
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A rows -> visible to the tensor core
+    group_sync(g);
+    if (gt == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_pass(0);
+      if (npass > 1) issue_pass(1);
+    }
+    for (uint32_t p = 0; p < npass; ++p) {
+      if (p & 1u) {
+        mbar_wait(mbar1, ph1);
+        ph1 ^= 1u;
+      } else {
+        mbar_wait(mbar0, ph0);
+        ph0 ^= 1u;
+      }
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[64];
+      tmem_ld64(acc0 + (p & 1u) * kTcPassCols + lane_off, v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      group_sync(g);  // every warp of the group has drained this accumulator
+      if (gt == 0 && p + 2u < npass) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_pass(p + 2u);
+      }
+      if (valid) {
+        uint64_t* dst = out + j * stride_j + (uint64_t)(p * 8u) * stride_i;
+#pragma unroll
+        for (uint32_t ii = 0; ii < 8; ++ii) {
+          if (p * 8u + ii < n) dst[(uint64_t)ii * stride_i] = tc_combine(v + 8 * ii);
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+cudaError_t share61_tc_prepare() {
+  return cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
+}
+
+cudaError_t share61_tc_launch(cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+                              uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
+                              uint64_t* d_out, uint64_t stride_i, uint64_t stride_j) {
+  k_share61_tc<<<grid, kTcThreads, kTcDynSmem, st>>>(key, d_t0, reinterpret_cast<const uint4*>(d_bmat), first_block,
+                                                    d_secrets, N, t, n, d_out, stride_i, stride_j);
+  return cudaGetLastError();
+}
+
+}  // namespace sclgpu
