@@ -59,7 +59,7 @@ def workload_config(args, world):
                     " (BASELINE configs[1])",
         "field": "Fp61", "n": NPARTIES, "t": T, "secrets_per_gpu": 1 << args.log2_secrets,
         "secrets_total": (1 << args.log2_secrets) * world, "sharding": f"batch x{world}, no collective",
-        "prg": "AES-128-CTR fused into the share kernel (seed 'shamir bench')",
+        "prg": "AES-128-CTR fused into the share kernel (seed 'shamir bench'): coefficients are drawn inside the timed region",
         "l2": "inputs larger than L2 (share planes 8*n*N bytes >> 126 MB); no explicit flush",
     }
 
@@ -291,7 +291,8 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         share_gbs = ALGO_BYTES_SHARE * N / (share_ms * 1e-3) / 1e9
         rec_gbs = ALGO_BYTES_RECOVER * N / (rec_ms * 1e-3) / 1e9
-        dominant = "k_share_fused<F61,15>" if share_ms >= rec_ms else "k_recover_p<F61>"
+        share_kernel = "k_share61<15>" if os.environ.get("SCLGPU_SHARE_TC", "1") == "0" else "k_share61_tc"
+        dominant = share_kernel if share_ms >= rec_ms else "k_recover61_pm<2>"
         dom_gbs = share_gbs if share_ms >= rec_ms else rec_gbs
         traffic = None
         try:
@@ -307,7 +308,9 @@ def run_b200(args):
             "kernels": {"share_ms": share_ms, "recover_ms": rec_ms, "share_GBps": share_gbs, "recover_GBps": rec_gbs},
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_secret": ALGO_BYTES_SHARE if share_ms >= rec_ms else ALGO_BYTES_RECOVER},
+                         "algorithmic_bytes_per_secret": ALGO_BYTES_SHARE if share_ms >= rec_ms else ALGO_BYTES_RECOVER,
+                         "note": "the share kernel's limiter is the shared-memory (LSU) pipe of the fused T-table AES-CTR, "
+                                 "not HBM; see profiles/ and DESIGN.md section 3"},
             "int_roofline": {"unit": "IMAD/s", "algorithmic_imads_per_secret": ALGO_IMADS_PER_SECRET,
                              "achieved": ALGO_IMADS_PER_SECRET * N / (ms_per_step * 1e-3),
                              "peak_imad32": imad_peak, "peak_imad_wide": imadw_peak,

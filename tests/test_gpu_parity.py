@@ -384,3 +384,20 @@ def test_full_size_c2_properties(ctx, pkg, orc):
     ctx.vec_op_dev(61, 0, d_sec, d_sec, N, d_want)
     torch.cuda.synchronize()
     assert torch.equal(d_sum, d_want)
+
+
+# ------------------------------------------------------------------ both Fp61 share kernels
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_share_kernel_paths_vs_oracle(tc):
+    """tools/tc_check.py sweeps (t, n, N) on the device-pointer path against the plain-C oracle;
+    SCLGPU_SHARE_TC selects the tcgen05 kernel (1, the default) or the integer-pipe kernel (0).
+    A separate process because the library reads the knob once."""
+    import os
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SCLGPU_SHARE_TC=tc)
+    r = subprocess.run([sys.executable, os.path.join(repo, "tools", "tc_check.py")], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "TC_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
