@@ -331,8 +331,11 @@ static int share_fused_launch(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& ke
 static int g_share_tc = -1;
 static bool share_tc_enabled() {
   if (g_share_tc < 0) {
-    const char* e = getenv("SCLGPU_SHARE_TC");  // 0 = integer-pipe kernel (k_share61), 1 = tcgen05 kernel
-    g_share_tc = e ? (atoi(e) != 0) : 1;
+    // 0 = integer-pipe kernel (k_share61); tcgen05 kernels: 1 = A operand in shared memory (3 groups),
+    // 2 / 3 = A operand in tensor memory with 4 / 5 groups of warps (3 is the default)
+    const char* e = getenv("SCLGPU_SHARE_TC");
+    g_share_tc = e ? atoi(e) : 3;
+    if (g_share_tc < 0 || g_share_tc > 3) g_share_tc = 3;
   }
   return g_share_tc != 0;
 }
@@ -378,9 +381,10 @@ static int share61_tc_on(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, ui
   const void* d_bmat = nullptr;
   RET(share61_tc_bmat(ctx, st, t, n, &d_bmat));
   const uint64_t tiles = (N + 127) / 128;
-  const int grid = (int)std::min<uint64_t>((tiles + kTcGroups - 1) / kTcGroups, (uint64_t)ctx->sm_count);
+  const int groups = tc_variant_groups(g_share_tc);
+  const int grid = (int)std::min<uint64_t>((tiles + groups - 1) / groups, (uint64_t)ctx->sm_count);
   ctx->launches++;
-  cudaError_t e = share61_tc_launch(st, grid, key, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n, d_out, si, sj);
+  cudaError_t e = share61_tc_launch(g_share_tc, st, grid, key, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n, d_out, si, sj);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
   return SCLGPU_OK;
 }

@@ -47,7 +47,8 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
 }
 
 // instruction descriptor: D = s32, A = B = u8, both K-major, M = 128, N = 64
-static constexpr uint32_t kTcIdesc = (2u << 4) | ((kTcPassCols >> 3) << 17) | ((128u >> 4) << 24);
+static constexpr uint32_t tc_idesc(uint32_t n_cols) { return (2u << 4) | ((n_cols >> 3) << 17) | ((128u >> 4) << 24); }
+static constexpr uint32_t kTcIdesc = tc_idesc(kTcPassCols);
 
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -92,6 +93,20 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
         "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
         "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
         "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -241,15 +256,216 @@ k_share61_tc(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_
   }
 }
 
-cudaError_t share61_tc_prepare() {
-  return cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
+
+// ---------------------------------------------------------------------------
+// Variant with the A operand in TENSOR MEMORY: every thread writes its secret's
+// coefficient bytes into its own TMEM lane (tcgen05.st, 4 columns per keystream
+// block), and the MMA reads A from TMEM (`tcgen05.mma ... [d], [a], b_desc`).
+// Shared memory then carries only the table lookups and the B limbs: the A-tile
+// stores and the four A re-reads per tile of the variant above (5 of its 41 LSU
+// wavefronts per secret) disappear, and with no A tiles in shared memory a fourth
+// group of warps fits.  TMEM per group: 32 columns of A + NBUF accumulators of 64.
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
-cudaError_t share61_tc_launch(cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+// GROUPS x 128 threads; NBUF accumulators of PCOLS columns (PCOLS/8 parties per MMA pass) per group
+template <int GROUPS, int NBUF, int PCOLS>
+__global__ void __launch_bounds__(128 * GROUPS, 1)
+k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
+              const uint4* __restrict__ g_bmat, uint64_t first_block, const uint64_t* __restrict__ secrets,
+              uint64_t N, uint32_t t, uint32_t n, uint64_t* __restrict__ out, uint64_t stride_i,
+              uint64_t stride_j) {
+  constexpr uint32_t kThreads = 128 * GROUPS;
+  constexpr uint32_t kColsPerGroup = 32u + NBUF * PCOLS;
+  constexpr uint32_t kPassParties = PCOLS / 8;
+  static_assert(GROUPS * kColsPerGroup <= 512, "tensor memory has 512 columns");
+  static_assert(PCOLS == 32 || PCOLS == 64, "pass width");
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t dyn = smem_u32(dyn_smem);
+  const uint32_t tbase = aes_table_base(dyn_smem);
+  const uint32_t b_base = tbase + kAesTableBytes;
+  const uint32_t ctl = b_base + kTcBmatBytes;             // 2*GROUPS mbarriers + the TMEM base address
+  if (ctl + 128u > dyn + kTcDynSmem) __trap();
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  aes_fill_tables(tbase, g_t0);
+  for (uint32_t e = tid; e < kTcBmatBytes / 16; e += kThreads) {
+    const uint4 w = __ldg(g_bmat + e);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ctl + 120u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint32_t i = 0; i < 2 * GROUPS; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctl + 8u * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(ctl + 120u) : "memory");
+
+  uint32_t lanebase = tbase + (tid & 31u) * 4u;
+  asm volatile("" : "+r"(lanebase)::"memory");
+
+  const uint32_t g = tid >> 7, gt = tid & 127u;
+  const uint32_t a_tm = tmem + g * kColsPerGroup;          // 32 columns: 128 coefficient bytes per lane
+  const uint32_t acc0 = a_tm + 32u;
+  const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
+  const uint32_t mbar0 = ctl + 16u * g, mbar1 = mbar0 + 8u;
+  uint32_t ph0 = 0, ph1 = 0;
+
+  const uint32_t nblk = ((t + 1u) * 8u + 15u) / 16u;
+  const uint32_t ksteps = ((t + 1u) * 8u + 31u) / 32u;
+  const uint32_t npass = (n + kPassParties - 1u) / kPassParties;
+  const uint64_t tiles = (N + 127u) / 128u;
+
+  auto issue_pass = [&](uint32_t p) {
+    const uint32_t b = (NBUF == 2) ? (p & 1u) : 0u;
+    for (uint32_t ks = 0; ks < ksteps; ++ks)
+      tc_mma_ts(acc0 + b * PCOLS, a_tm + ks * 8u, tc_desc(b_base + p * (PCOLS * 128u) + ks * 32u), tc_idesc(PCOLS), ks);
+    tc_commit(b ? mbar1 : mbar0);
+  };
+
+  for (uint64_t tile = (uint64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (uint64_t)gridDim.x * GROUPS) {
+    const uint64_t j = tile * 128u + gt;
+    const bool valid = j < N;
+    const uint64_t jj = valid ? j : N - 1;                 // tail lanes recompute the last secret (never stored)
+    const uint64_t sec = secrets[jj];
+    const uint64_t ctr0 = first_block + jj * nblk;
+    const uint32_t a_lane = a_tm + lane_off;
+    if (t == 0) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %3};" ::"r"(a_lane), "r"((uint32_t)sec), "r"((uint32_t)(sec >> 32)), "r"(0u) : "memory");
+    } else {
+      PrgGroup grp;
+      uint64_t gid = ctr0 >> 8;
+      prg_group(key, lanebase, ctr0, grp);
+#pragma unroll 1
+      for (uint32_t b = 0; b < nblk; ++b) {
+        const uint64_t ctr = ctr0 + b;
+        if ((ctr >> 8) != gid) {
+          gid = ctr >> 8;
+          prg_group(key, lanebase, ctr, grp);
+        }
+        uint32_t o0, o1, o2, o3;
+        prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+        if (b == 0) {
+          o0 = (uint32_t)sec;
+          o1 = (uint32_t)(sec >> 32);
+        }
+        __syncwarp();
+        // keystream block b = coefficients 2b, 2b+1 = K bytes [16b, 16b+16) = TMEM columns 4b..4b+3 of this lane
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    group_sync(g);
+    if (gt == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_pass(0);
+      if (NBUF == 2 && npass > 1) issue_pass(1);
+    }
+    for (uint32_t p = 0; p < npass; ++p) {
+      if (NBUF == 2 && (p & 1u)) {
+        mbar_wait(mbar1, ph1);
+        ph1 ^= 1u;
+      } else {
+        mbar_wait(mbar0, ph0);
+        ph0 ^= 1u;
+      }
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = acc0 + ((NBUF == 2) ? (p & 1u) : 0u) * PCOLS + lane_off;
+      uint64_t* dst = out + j * stride_j + (uint64_t)(p * kPassParties) * stride_i;
+      uint32_t v[32];
+      tmem_ld32(acc, v);
+      if (PCOLS == 32) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync(g);  // accumulator drained by every warp of the group: it may be overwritten
+        if (gt == 0 && p + NBUF < npass) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_pass(p + NBUF);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (uint32_t ii = 0; ii < 4; ++ii)
+          if (p * kPassParties + ii < n) dst[(uint64_t)ii * stride_i] = tc_combine(v + 8 * ii);
+      }
+      if (PCOLS == 64) {
+        tmem_ld32(acc + 32u, v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync(g);
+        if (gt == 0 && p + NBUF < npass) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_pass(p + NBUF);
+        }
+        if (valid) {
+#pragma unroll
+          for (uint32_t ii = 0; ii < 4; ++ii)
+            if (p * kPassParties + 4u + ii < n) dst[(uint64_t)(4u + ii) * stride_i] = tc_combine(v + 8 * ii);
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// (variant, groups, accumulators, columns per pass).  Measured at 2^26 secrets, n=32, t=15 on B200
+// (gpurun, CUDA events): A in shared memory 3 groups 13.45 ms | (3,2,64) 12.72 | (4,1,64) 11.70 |
+// (4,2,32) 13.11 | (5,1,64) 11.33 | (5,2,32) 12.42 | (6,1,32) 12.27 | (7,1,32) 12.25 | (8,1,32) 12.19.
+// Kept: the two best.
+#define SCLGPU_TCM_VARIANTS(X) X(2, 4, 1, 64) X(3, 5, 1, 64)
+
+cudaError_t share61_tc_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
+#define X(V, G, NB, PC) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share61_tcm<G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
+  SCLGPU_TCM_VARIANTS(X)
+#undef X
+  return e;
+}
+
+int tc_variant_groups(int variant) {
+#define X(V, G, NB, PC) \
+  if (variant == V) return G;
+  SCLGPU_TCM_VARIANTS(X)
+#undef X
+  return kTcGroups;
+}
+
+cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
                               uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
                               uint64_t* d_out, uint64_t stride_i, uint64_t stride_j) {
-  k_share61_tc<<<grid, kTcThreads, kTcDynSmem, st>>>(key, d_t0, reinterpret_cast<const uint4*>(d_bmat), first_block,
-                                                    d_secrets, N, t, n, d_out, stride_i, stride_j);
+  const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
+  bool done = false;
+#define X(V, G, NB, PC)                                                                                          \
+  if (variant == V) {                                                                                            \
+    k_share61_tcm<G, NB, PC><<<grid, 128 * G, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,   \
+                                                               d_out, stride_i, stride_j);                       \
+    done = true;                                                                                                 \
+  }
+  SCLGPU_TCM_VARIANTS(X)
+#undef X
+  if (!done)
+    k_share61_tc<<<grid, kTcThreads, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
   return cudaGetLastError();
 }
 

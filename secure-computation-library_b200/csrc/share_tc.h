@@ -23,7 +23,10 @@ static inline uint32_t tc_bmat_offset(uint32_t r, uint32_t kk) {
 }
 
 cudaError_t share61_tc_prepare();
-cudaError_t share61_tc_launch(cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+// variant 1: A in shared memory, 3 groups; variants >= 2: A in tensor memory with
+// (groups, accumulators per group, columns per MMA pass) as listed in share_tc.cu
+int tc_variant_groups(int variant);
+cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
                               uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
                               uint64_t* d_out, uint64_t stride_i, uint64_t stride_j);
 

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Device-resident timing of every BASELINE.json config (C1..C5) with CUDA events:
+a development / reporting tool (bench.py is the contract; these are not bench lines).
+Prints one JSON object; GB/s figures are ALGORITHMIC bytes / event time.
+Usage: cfg_bench.py [reps]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as entry
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+pkg = entry.load_package(); B = pkg.binding
+ctx = pkg.Context(0); ctx.use_torch_stream()
+dev = "cuda"
+
+def timeit(fn):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def i64(*shape): return torch.empty(shape, dtype=torch.int64, device=dev)
+res = {}
+
+def shamir(tag, field, n, t, N, detect):
+    w = 1 if field == 61 else 2
+    eb = 8 * w
+    sec, sh, out = i64(N, w), i64(n, N, w), i64(N, w)
+    err = torch.empty(N, dtype=torch.uint8, device=dev)
+    ctx.random_dev(field, "secrets", 0, N, sec)
+    r = {"field": field, "n": n, "t": t, "N": N}
+    r["share_ms"] = timeit(lambda: ctx.shamir_share_dev(field, sec, N, t, n, "shamir bench", 0, sh, B.PARTY_MAJOR))
+    if detect:
+        r["recover_d_ms"] = timeit(lambda: ctx.recover_d_dev(field, sh, N, n, t, out, err, B.PARTY_MAJOR))
+        rec = r["recover_d_ms"]
+        r["flags"] = int(err.sum().item())
+    else:
+        r["recover_p_ms"] = timeit(lambda: ctx.recover_p_dev(field, sh, N, n, out, B.PARTY_MAJOR))
+        rec = r["recover_p_ms"]
+    r["ok"] = bool(torch.equal(out, sec))
+    r["secrets_per_s"] = N / ((r["share_ms"] + rec) * 1e-3)
+    r["share_GBps"] = (eb + n * eb) * N / r["share_ms"] / 1e6
+    r["recover_GBps"] = ((min(n, 2 * t) if detect else n) * eb + eb) * N / rec / 1e6
+    res[tag] = r
+    del sec, sh, out, err
+
+shamir("C1_fp61_n5_t2_2^20", 61, 5, 2, 1 << 20, False)
+shamir("C2_fp61_n32_t15_2^26", 61, 32, 15, 1 << 26, False)
+shamir("C3_fp127_n16_t7_2^24_recoverD", 127, 16, 7, 1 << 24, True)
+shamir("C3b_fp61_n16_t7_2^24_recoverD", 61, 16, 7, 1 << 24, True)
+torch.cuda.empty_cache()
+
+# C4: PRG -> 2^28 Fp61 elements (2 GiB keystream)
+n4 = 1 << 28
+buf = i64(n4)
+r = {"elements": n4}
+r["keystream_ms"] = timeit(lambda: ctx.prg_expand_dev("prg bench", 0, 8 * n4, buf))
+r["fp61_random_ms"] = timeit(lambda: ctx.random_dev(61, "prg bench", 0, n4, buf))
+r["keystream_GBps"] = 8 * n4 / r["keystream_ms"] / 1e6
+r["blocks_per_s"] = (n4 / 2) / (r["keystream_ms"] * 1e-3)
+res["C4_prg_2^28_fp61"] = r
+del buf; torch.cuda.empty_cache()
+
+# C5: Fp61 mat-vec 8192 x 8192 and Beaver mul-add on 2^26 elements
+rows = cols = 8192
+A, x, y = i64(rows, cols), i64(cols), i64(rows)
+ctx.random_dev(61, "mat A", 0, rows * cols, A); ctx.random_dev(61, "vec x", 0, cols, x)
+r = {"rows": rows, "cols": cols}
+r["matvec_ms"] = timeit(lambda: ctx.matvec_dev(61, A, rows, cols, x, y))
+r["matvec_GBps"] = 8 * rows * cols / r["matvec_ms"] / 1e6
+del A; torch.cuda.empty_cache()
+n5 = 1 << 26
+vs = [i64(n5) for _ in range(6)]
+for k, v in enumerate(vs[:5]): ctx.random_dev(61, "ebdac"[k], 0, n5, v)
+r["muladd_ms"] = timeit(lambda: ctx.beaver_dev(61, vs[0], vs[1], vs[2], vs[3], vs[4], n5, vs[5]))
+r["muladd_GBps"] = 48 * n5 / r["muladd_ms"] / 1e6
+r["vec_mul_ms"] = timeit(lambda: ctx.vec_op_dev(61, 2, vs[0], vs[1], n5, vs[5]))
+r["vec_mul_GBps"] = 24 * n5 / r["vec_mul_ms"] / 1e6
+r["dot_ms"] = timeit(lambda: ctx.vec_op_dev(61, 4, vs[0], vs[1], n5, vs[5]))
+r["dot_GBps"] = 16 * n5 / r["dot_ms"] / 1e6
+res["C5_fp61_matvec_muladd"] = r
+print(json.dumps(res, indent=1))
