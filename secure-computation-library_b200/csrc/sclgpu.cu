@@ -340,8 +340,12 @@ static bool share_tc_enabled() {
   return g_share_tc != 0;
 }
 
-static int share61_tc_bmat(sclgpu_ctx* ctx, cudaStream_t st, uint32_t t, uint32_t n, const void** d_bmat) {
-  const uint32_t key = (t << 8) | n;
+// B image for field F: row r = party*BYTES + limb, column kk = coeff*BYTES + byte
+template <class F>
+static int share_tc_bmat(sclgpu_ctx* ctx, cudaStream_t st, uint32_t t, uint32_t n, const void** d_bmat) {
+  typedef typename F::E E;
+  constexpr uint32_t EB = F::BYTES;
+  const uint32_t key = ((uint32_t)EB << 16) | (t << 8) | n;
   auto it = ctx->tc_bmat_cache.find(key);
   if (it != ctx->tc_bmat_cache.end()) {
     *d_bmat = it->second;
@@ -349,13 +353,16 @@ static int share61_tc_bmat(sclgpu_ctx* ctx, cudaStream_t st, uint32_t t, uint32_
   }
   std::vector<uint8_t> img(kTcBmatBytes, 0);
   for (uint32_t i = 0; i < n; ++i) {
-    uint64_t pw = 1;  // (i+1)^k
+    E pw = F::one();  // (i+1)^k
     for (uint32_t k = 0; k <= t; ++k) {
-      for (uint32_t a = 0; a < 8; ++a) {
-        const uint64_t c = F61::mul(pw, 1ull << (8 * a));
-        for (uint32_t s = 0; s < 8; ++s) img[tc_bmat_offset(i * 8 + s, k * 8 + a)] = (uint8_t)(c >> (8 * s));
+      E c = pw;       // (i+1)^k * 2^(8a)
+      for (uint32_t a = 0; a < EB; ++a) {
+        uint8_t bytes[16];
+        std::memcpy(bytes, &c, EB);  // little-endian canonical residue = its 8-bit limbs
+        for (uint32_t s = 0; s < EB; ++s) img[tc_bmat_offset(i * EB + s, k * EB + a)] = bytes[s];
+        c = F::mul(c, F::from_u32(256));
       }
-      pw = F61::mul(pw, (uint64_t)(i + 1));
+      pw = F::mul(pw, F::from_u32(i + 1));
     }
   }
   void* d = nullptr;
@@ -371,20 +378,28 @@ static int share61_tc_bmat(sclgpu_ctx* ctx, cudaStream_t st, uint32_t t, uint32_
   return SCLGPU_OK;
 }
 
-static int share61_tc_on(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t first_block,
-                         const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_out,
-                         uint64_t si, uint64_t sj) {
+template <class F>
+static int share_tc_on(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t first_block,
+                       const typename F::E* d_secrets, uint64_t N, uint32_t t, uint32_t n, typename F::E* d_out,
+                       uint64_t si, uint64_t sj) {
   if (!ctx->tc_prepared) {
-    CK(share61_tc_prepare());
+    CK(share_tc_prepare());
     ctx->tc_prepared = true;
   }
   const void* d_bmat = nullptr;
-  RET(share61_tc_bmat(ctx, st, t, n, &d_bmat));
+  RET(share_tc_bmat<F>(ctx, st, t, n, &d_bmat));
   const uint64_t tiles = (N + 127) / 128;
-  const int groups = tc_variant_groups(g_share_tc);
+  int variant = g_share_tc;
+  if (F::BYTES == 16 && variant == 1) variant = 3;  // the shared-memory-A kernel exists for Fp61 only
+  const int groups = tc_variant_groups(variant);
   const int grid = (int)std::min<uint64_t>((tiles + groups - 1) / groups, (uint64_t)ctx->sm_count);
   ctx->launches++;
-  cudaError_t e = share61_tc_launch(g_share_tc, st, grid, key, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n, d_out, si, sj);
+  cudaError_t e;
+  if constexpr (F::BYTES == 8) {
+    e = share61_tc_launch(variant, st, grid, key, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n, d_out, si, sj);
+  } else {
+    e = share127_tc_launch(variant, st, grid, key, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n, d_out, si, sj);
+  }
   if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
   return SCLGPU_OK;
 }
@@ -447,7 +462,7 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   const AesKey key = aes_expand(seed);
   if constexpr (F::BYTES == 8) {
     if (t <= kTcMaxT && n <= kTcMaxParties && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr)
-      return share61_tc_on(ctx, st, key, first_block, d_secrets, N, t, n, d_out, si, sj);
+      return share_tc_on<F61>(ctx, st, key, first_block, d_secrets, N, t, n, d_out, si, sj);
     if (t <= 15 && n <= 0xFFFFu && getenv("SCLGPU_SHARE_GENERIC") == nullptr) {
 #define SCLGPU_CASE61(TT) \
   case TT: return share61_mode<TT>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
@@ -459,6 +474,10 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
       }
 #undef SCLGPU_CASE61
     }
+  }
+  if constexpr (F::BYTES == 16) {
+    if (t <= kTcMaxT127 && n <= kTcMaxParties127 && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr)
+      return share_tc_on<F127>(ctx, st, key, first_block, d_secrets, N, t, n, d_out, si, sj);
   }
 #define SCLGPU_CASE(TT) \
   case TT: return share_fused_launch<F, (TT <= max_fused_t<F>() ? TT : 0)>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);

@@ -274,16 +274,37 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 
-// GROUPS x 128 threads; NBUF accumulators of PCOLS columns (PCOLS/8 parties per MMA pass) per group
-template <int GROUPS, int NBUF, int PCOLS>
+// Fp127 (mersenne127.cc:60-97 semantics): sixteen 23-bit limbs at 2^(8s) -> canonical residue mod 2^127 - 1
+__device__ __forceinline__ E127 tc_combine127(const uint32_t* v) {
+  uint32_t q[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) q[m] = v[2 * m] + (v[2 * m + 1] << 8);  // < 2^32, weight 2^(16m)
+  // even pairs are word-aligned: E = q0 | q2<<32 | q4<<64 | q6<<96; odd pairs form O, weight 2^16
+  const E127 e{(uint64_t)q[0] | ((uint64_t)q[2] << 32), (uint64_t)q[4] | ((uint64_t)q[6] << 32)};
+  const uint64_t olo = (uint64_t)q[1] | ((uint64_t)q[3] << 32), ohi = (uint64_t)q[5] | ((uint64_t)q[7] << 32);
+  // O * 2^16 = (O mod 2^111) * 2^16 + (O >> 111) * 2^127, and 2^127 = 1
+  E127 x{olo << 16, ((ohi << 16) | (olo >> 48)) & F127::PHI};
+  const uint64_t wrap = ohi >> 47;
+  x.lo += wrap;
+  x.hi += (x.lo < wrap);  // < 2^127 + 2^17
+  return F127::add(F127::from_raw(e), F127::from_raw(x));
+}
+
+// GROUPS x 128 threads; NBUF accumulators of PCOLS columns (PCOLS / F::BYTES parties per MMA pass) per
+// group.  F = F61: K = 8(t+1) bytes, t <= 15, n <= 32.  F = F127: K = 16(t+1) bytes, t <= 7, n <= 16;
+// coefficient k is keystream block k of the secret's draw (vector.h:508-519 with 16-byte elements).
+template <class F, int GROUPS, int NBUF, int PCOLS>
 __global__ void __launch_bounds__(128 * GROUPS, 1)
-k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
-              const uint4* __restrict__ g_bmat, uint64_t first_block, const uint64_t* __restrict__ secrets,
-              uint64_t N, uint32_t t, uint32_t n, uint64_t* __restrict__ out, uint64_t stride_i,
-              uint64_t stride_j) {
+k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
+            const uint4* __restrict__ g_bmat, uint64_t first_block, const typename F::E* __restrict__ secrets,
+            uint64_t N, uint32_t t, uint32_t n, typename F::E* __restrict__ out, uint64_t stride_i,
+            uint64_t stride_j) {
+  typedef typename F::E E;
+  constexpr uint32_t EB = F::BYTES;                        // bytes = 8-bit limbs per element
   constexpr uint32_t kThreads = 128 * GROUPS;
   constexpr uint32_t kColsPerGroup = 32u + NBUF * PCOLS;
-  constexpr uint32_t kPassParties = PCOLS / 8;
+  constexpr uint32_t kPassParties = PCOLS / EB;
+  constexpr uint32_t kLdParties = 32u / EB;                // parties per 32-column TMEM load
   static_assert(GROUPS * kColsPerGroup <= 512, "tensor memory has 512 columns");
   static_assert(PCOLS == 32 || PCOLS == 64, "pass width");
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -325,8 +346,8 @@ k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
   const uint32_t mbar0 = ctl + 16u * g, mbar1 = mbar0 + 8u;
   uint32_t ph0 = 0, ph1 = 0;
 
-  const uint32_t nblk = ((t + 1u) * 8u + 15u) / 16u;
-  const uint32_t ksteps = ((t + 1u) * 8u + 31u) / 32u;
+  const uint32_t nblk = ((t + 1u) * EB + 15u) / 16u;       // keystream blocks per secret (prg.cc:129-133)
+  const uint32_t ksteps = ((t + 1u) * EB + 31u) / 32u;     // K = 32 bytes per MMA
   const uint32_t npass = (n + kPassParties - 1u) / kPassParties;
   const uint64_t tiles = (N + 127u) / 128u;
 
@@ -336,35 +357,62 @@ k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
       tc_mma_ts(acc0 + b * PCOLS, a_tm + ks * 8u, tc_desc(b_base + p * (PCOLS * 128u) + ks * 32u), tc_idesc(PCOLS), ks);
     tc_commit(b ? mbar1 : mbar0);
   };
+  auto emit = [&](const uint32_t (&v)[32], E* dst, uint32_t first_party) {
+#pragma unroll
+    for (uint32_t ii = 0; ii < kLdParties; ++ii) {
+      if (first_party + ii < n) {
+        if constexpr (EB == 8) {
+          dst[(uint64_t)ii * stride_i] = tc_combine(v + 8 * ii);
+        } else {
+          dst[(uint64_t)ii * stride_i] = tc_combine127(v + 16 * ii);
+        }
+      }
+    }
+  };
 
   for (uint64_t tile = (uint64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (uint64_t)gridDim.x * GROUPS) {
     const uint64_t j = tile * 128u + gt;
     const bool valid = j < N;
     const uint64_t jj = valid ? j : N - 1;                 // tail lanes recompute the last secret (never stored)
-    const uint64_t sec = secrets[jj];
+    uint32_t s0, s1, s2 = 0, s3 = 0;                       // the secret = coefficient 0 (shamir.h:56-57)
+    if constexpr (EB == 8) {
+      const uint64_t sec = secrets[jj];
+      s0 = (uint32_t)sec;
+      s1 = (uint32_t)(sec >> 32);
+    } else {
+      const E sec = secrets[jj];
+      s0 = (uint32_t)sec.lo;
+      s1 = (uint32_t)(sec.lo >> 32);
+      s2 = (uint32_t)sec.hi;
+      s3 = (uint32_t)(sec.hi >> 32);
+    }
     const uint64_t ctr0 = first_block + jj * nblk;
     const uint32_t a_lane = a_tm + lane_off;
-    if (t == 0) {
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %3};" ::"r"(a_lane), "r"((uint32_t)sec), "r"((uint32_t)(sec >> 32)), "r"(0u) : "memory");
-    } else {
+    if (t == 0 || EB == 16) {
+      // Fp61, t = 0: one block is consumed, none of it is used.  Fp127: block 0 is slot 0 of the draw,
+      // consumed and replaced by the secret.
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+    }
+    if (t != 0) {
       PrgGroup grp;
-      uint64_t gid = ctr0 >> 8;
-      prg_group(key, lanebase, ctr0, grp);
+      const uint32_t b0 = (EB == 16) ? 1u : 0u;
+      uint64_t gid = (ctr0 + b0) >> 8;
+      prg_group(key, lanebase, ctr0 + b0, grp);
 #pragma unroll 1
-      for (uint32_t b = 0; b < nblk; ++b) {
+      for (uint32_t b = b0; b < nblk; ++b) {
         const uint64_t ctr = ctr0 + b;
-        if ((ctr >> 8) != gid) {
+        if ((ctr >> 8) != gid) {  // crossed a 256-block group: at most once per secret
           gid = ctr >> 8;
           prg_group(key, lanebase, ctr, grp);
         }
         uint32_t o0, o1, o2, o3;
         prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
-        if (b == 0) {
-          o0 = (uint32_t)sec;
-          o1 = (uint32_t)(sec >> 32);
+        if (EB == 8 && b == 0) {
+          o0 = s0;
+          o1 = s1;
         }
         __syncwarp();
-        // keystream block b = coefficients 2b, 2b+1 = K bytes [16b, 16b+16) = TMEM columns 4b..4b+3 of this lane
+        // keystream block b = K bytes [16b, 16b+16) of the row = TMEM columns 4b..4b+3 of this lane
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
       }
     }
@@ -387,7 +435,7 @@ k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = acc0 + ((NBUF == 2) ? (p & 1u) : 0u) * PCOLS + lane_off;
-      uint64_t* dst = out + j * stride_j + (uint64_t)(p * kPassParties) * stride_i;
+      E* dst = out + j * stride_j + (uint64_t)(p * kPassParties) * stride_i;
       uint32_t v[32];
       tmem_ld32(acc, v);
       if (PCOLS == 32) {
@@ -398,11 +446,7 @@ k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
           issue_pass(p + NBUF);
         }
       }
-      if (valid) {
-#pragma unroll
-        for (uint32_t ii = 0; ii < 4; ++ii)
-          if (p * kPassParties + ii < n) dst[(uint64_t)ii * stride_i] = tc_combine(v + 8 * ii);
-      }
+      if (valid) emit(v, dst, p * kPassParties);
       if (PCOLS == 64) {
         tmem_ld32(acc + 32u, v);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -411,11 +455,7 @@ k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_pass(p + NBUF);
         }
-        if (valid) {
-#pragma unroll
-          for (uint32_t ii = 0; ii < 4; ++ii)
-            if (p * kPassParties + 4u + ii < n) dst[(uint64_t)(4u + ii) * stride_i] = tc_combine(v + 8 * ii);
-        }
+        if (valid) emit(v, dst + (uint64_t)kLdParties * stride_i, p * kPassParties + kLdParties);
       }
     }
   }
@@ -434,10 +474,11 @@ k_share61_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g
 // Kept: the two best.
 #define SCLGPU_TCM_VARIANTS(X) X(2, 4, 1, 64) X(3, 5, 1, 64)
 
-cudaError_t share61_tc_prepare() {
+cudaError_t share_tc_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
-#define X(V, G, NB, PC) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share61_tcm<G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
+#define X(V, G, NB, PC)                                                                                                                       \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
   SCLGPU_TCM_VARIANTS(X)
 #undef X
   return e;
@@ -456,16 +497,28 @@ cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesK
                               uint64_t* d_out, uint64_t stride_i, uint64_t stride_j) {
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
   bool done = false;
-#define X(V, G, NB, PC)                                                                                          \
-  if (variant == V) {                                                                                            \
-    k_share61_tcm<G, NB, PC><<<grid, 128 * G, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,   \
-                                                               d_out, stride_i, stride_j);                       \
-    done = true;                                                                                                 \
+#define X(V, G, NB, PC)                                                                                               \
+  if (variant == V) {                                                                                                 \
+    k_share_tcm<F61, G, NB, PC><<<grid, 128 * G, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
+                                                                  d_out, stride_i, stride_j);                         \
+    done = true;                                                                                                      \
   }
   SCLGPU_TCM_VARIANTS(X)
 #undef X
   if (!done)
     k_share61_tc<<<grid, kTcThreads, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+  return cudaGetLastError();
+}
+
+cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0,
+                               const void* d_bmat, uint64_t first_block, const E127* d_secrets, uint64_t N, uint32_t t,
+                               uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j) {
+  const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
+  if (variant == 2) {
+    k_share_tcm<F127, 4, 1, 64><<<grid, 512, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+  } else {
+    k_share_tcm<F127, 5, 1, 64><<<grid, 640, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+  }
   return cudaGetLastError();
 }
 

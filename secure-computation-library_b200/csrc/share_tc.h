@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "aes_ctr.cuh"
+#include "field.cuh"
 
 namespace sclgpu {
 
@@ -13,7 +14,8 @@ static constexpr int kTcGroups = 3;                   // 128-secret tiles in fli
 static constexpr int kTcThreads = 128 * kTcGroups;    // 4 warps per group
 static constexpr uint32_t kTcBmatBytes = 32768;       // 32 parties x 8 limbs rows of K = 128 bytes
 static constexpr uint32_t kTcDynSmem = 232448;        // 227 KiB: A tiles | AES tables | B limbs | barriers
-static constexpr uint32_t kTcMaxT = 15, kTcMaxParties = 32;
+static constexpr uint32_t kTcMaxT = 15, kTcMaxParties = 32;        // Fp61:  K = 8(t+1)  <= 128 bytes, 8 limbs per party
+static constexpr uint32_t kTcMaxT127 = 7, kTcMaxParties127 = 16;   // Fp127: K = 16(t+1) <= 128 bytes, 16 limbs per party
 
 // Offset of byte (row r = party*8 + limb, column kk = coeff*8 + byte) in the B image:
 // K-major rows of 128 bytes, 8-row groups of 1 KiB, 16-byte chunks XOR-swizzled by r%8
@@ -22,12 +24,16 @@ static inline uint32_t tc_bmat_offset(uint32_t r, uint32_t kk) {
   return (r >> 3) * 1024u + (r & 7u) * 128u + (((kk >> 4) ^ (r & 7u)) << 4) + (kk & 15u);
 }
 
-cudaError_t share61_tc_prepare();
+cudaError_t share_tc_prepare();
 // variant 1: A in shared memory, 3 groups; variants >= 2: A in tensor memory with
 // (groups, accumulators per group, columns per MMA pass) as listed in share_tc.cu
 int tc_variant_groups(int variant);
 cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
                               uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
                               uint64_t* d_out, uint64_t stride_i, uint64_t stride_j);
+
+cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const AesKey& key, const uint32_t* d_t0,
+                               const void* d_bmat, uint64_t first_block, const E127* d_secrets, uint64_t N, uint32_t t,
+                               uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j);
 
 }  // namespace sclgpu
