@@ -38,6 +38,7 @@ struct sclgpu_ctx {
   std::set<const void*> smem_opted;   // kernels with the 192 KiB opt-in done
   std::map<std::string, void*> basis_cache;  // (field, nodes, xs) -> device matrix
   std::map<uint32_t, void*> tc_bmat_cache;   // (t, n) -> Vandermonde limb image of k_share61_tc
+  std::map<const void*, void*> rd_bmat_cache;  // Lagrange check matrix (device) -> its limb image for k_recover_d_tc
   bool tc_prepared = false;
 };
 
@@ -177,6 +178,7 @@ extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
   for (auto& kv : ctx->tc_bmat_cache) cudaFree(kv.second);
+  for (auto& kv : ctx->rd_bmat_cache) cudaFree(kv.second);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
     if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
@@ -572,6 +574,8 @@ static int basis_rows(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* nod
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
     ctx->basis_cache.clear();
+    for (auto& kv : ctx->rd_bmat_cache) cudaFree(kv.second);  // keyed by the pointers just freed
+    ctx->rd_bmat_cache.clear();
   }
   ctx->basis_cache[key] = dm;
   *d_mat = reinterpret_cast<const E*>(dm);
@@ -638,6 +642,49 @@ static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
                         uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
                         const typename F::E* d_mat, typename F::E* d_out, uint8_t* d_err) {
   if (N == 0) return SCLGPU_OK;
+  if (recover_d_tc_fits<F>(m, n_checks) && getenv("SCLGPU_RECOVER_GENERIC") == nullptr) {
+    // tensor-core kernel: limb image of the (n_checks+1) x m matrix, row r*BYTES+s, column k*BYTES+a
+    typedef typename F::E E;
+    constexpr uint32_t EB = F::BYTES;
+    void* d_img = nullptr;
+    auto it = ctx->rd_bmat_cache.find(d_mat);
+    if (it != ctx->rd_bmat_cache.end()) {
+      d_img = it->second;
+    } else {
+      const uint32_t rows = n_checks + 1;
+      std::vector<E> hm((size_t)rows * m);
+      CK(cudaMemcpyAsync(hm.data(), d_mat, hm.size() * sizeof(E), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<uint8_t> img(kTcBmatBytes, 0);
+      for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t k = 0; k < m; ++k) {
+          E c = hm[(size_t)r * m + k];
+          for (uint32_t a = 0; a < EB; ++a) {
+            uint8_t bytes[16];
+            std::memcpy(bytes, &c, EB);
+            for (uint32_t s = 0; s < EB; ++s) img[tc_bmat_offset(r * EB + s, k * EB + a)] = bytes[s];
+            c = F::mul(c, F::from_u32(256));
+          }
+        }
+      CK(cudaMalloc(&d_img, kTcBmatBytes));
+      cudaError_t e = cudaMemcpyAsync(d_img, img.data(), kTcBmatBytes, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        cudaFree(d_img);
+        return cuda_fail(ctx, e, "recover_d_tc constants");
+      }
+      ctx->rd_bmat_cache[d_mat] = d_img;
+    }
+    ctx->launches++;
+    cudaError_t e;
+    if constexpr (EB == 8) {
+      e = recover_d61_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, ctx->d_count);
+    } else {
+      e = recover_d127_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, ctx->d_count);
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
+    return SCLGPU_OK;
+  }
   const size_t smem = (size_t)(n_checks + 1) * m * sizeof(typename F::E);
   if (smem > 200 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_d: check matrix exceeds shared memory");
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_recover_d<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

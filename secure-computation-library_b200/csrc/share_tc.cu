@@ -29,6 +29,7 @@
 // under the epilogue of pass p.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "aes_ctr.cuh"
@@ -473,6 +474,190 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
 // (4,2,32) 13.11 | (5,1,64) 11.33 | (5,2,32) 12.42 | (6,1,32) 12.27 | (7,1,32) 12.25 | (8,1,32) 12.19.
 // Kept: the two best.
 #define SCLGPU_TCM_VARIANTS(X) X(2, 4, 1, 64) X(3, 5, 1, 64)
+
+// ===================================================== shamirRecoverD on tensor cores
+// shamir.h:117-140: y_r = sum_{k<m} shares[k] * L_r[k] for the n_checks rows interpolating to
+// alphas[m+r] (compared with shares[m+r]) and the final row interpolating to x.  The same
+// byte-limb product as the share kernel: A = the first m shares of a secret (m*BYTES <= 128
+// bytes, written by its thread into its TMEM lane), B = bytes of L_r[k] * 2^(8a) (built on the
+// host from the device-computed Lagrange rows), D = (n_checks+1) x BYTES limb columns.  No AES,
+// so shared memory holds only B; the kernel is HBM-bound (reads d+t shares per secret once).
+template <class F, int GROUPS>
+__global__ void __launch_bounds__(128 * GROUPS, 1)
+k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict__ in, uint64_t N,
+               uint64_t stride_i, uint64_t stride_j, uint32_t m, uint32_t n_checks,
+               typename F::E* __restrict__ out, uint8_t* __restrict__ err,
+               unsigned long long* __restrict__ n_bad) {
+  typedef typename F::E E;
+  constexpr uint32_t EB = F::BYTES;
+  constexpr uint32_t kThreads = 128 * GROUPS;
+  constexpr uint32_t PCOLS = 64;
+  constexpr uint32_t kColsPerGroup = 32u + PCOLS;
+  constexpr uint32_t kMaxM = 128u / EB;                    // shares in one 128-byte A row
+  constexpr uint32_t kLdRows = 32u / EB;                   // output rows per 32-column TMEM load
+  static_assert(GROUPS * kColsPerGroup <= 512, "tensor memory has 512 columns");
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t dyn = smem_u32(dyn_smem);
+  const uint32_t b_base = (dyn + 1023u) & ~1023u;
+  const uint32_t ctl = b_base + kTcBmatBytes;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t e = tid; e < kTcBmatBytes / 16; e += kThreads) {
+    const uint4 w = __ldg(g_bmat + e);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ctl + 120u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint32_t i = 0; i < GROUPS; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctl + 8u * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(ctl + 120u) : "memory");
+
+  const uint32_t g = tid >> 7, gt = tid & 127u;
+  const uint32_t a_tm = tmem + g * kColsPerGroup;
+  const uint32_t acc0 = a_tm + 32u;
+  const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
+  const uint32_t a_lane = a_tm + lane_off;
+  const uint32_t mbar = ctl + 8u * g;
+  uint32_t ph = 0;
+  const uint32_t ksteps = (m * EB + 31u) / 32u;
+  const uint32_t rows = n_checks + 1u;
+  const uint32_t npass = (rows * EB + PCOLS - 1u) / PCOLS;
+  const uint64_t tiles = (N + 127u) / 128u;
+  unsigned long long local_bad = 0;
+
+  auto issue_pass = [&](uint32_t p) {
+    for (uint32_t ks = 0; ks < ksteps; ++ks)
+      tc_mma_ts(acc0, a_tm + ks * 8u, tc_desc(b_base + p * (PCOLS * 128u) + ks * 32u), tc_idesc(PCOLS), ks);
+    tc_commit(mbar);
+  };
+
+  for (uint64_t tile = (uint64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (uint64_t)gridDim.x * GROUPS) {
+    const uint64_t j = tile * 128u + gt;
+    const bool valid = j < N;
+    const E* src = in + (valid ? j : N - 1) * stride_j;
+    // the m interpolation shares: all requested before the first is consumed
+    E a[kMaxM];
+#pragma unroll
+    for (uint32_t k = 0; k < kMaxM; ++k) a[k] = (k < m) ? src[(uint64_t)k * stride_i] : F::zero();
+    if constexpr (EB == 8) {
+#pragma unroll
+      for (uint32_t c = 0; c < kMaxM / 2; ++c) {
+        if (2 * c < m)  // warp-uniform
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * c),
+                       "r"((uint32_t)a[2 * c]), "r"((uint32_t)(a[2 * c] >> 32)), "r"((uint32_t)a[2 * c + 1]),
+                       "r"((uint32_t)(a[2 * c + 1] >> 32))
+                       : "memory");
+      }
+    } else {
+#pragma unroll
+      for (uint32_t c = 0; c < kMaxM; ++c) {
+        if (c < m)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * c),
+                       "r"((uint32_t)a[c].lo), "r"((uint32_t)(a[c].lo >> 32)), "r"((uint32_t)a[c].hi),
+                       "r"((uint32_t)(a[c].hi >> 32))
+                       : "memory");
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    group_sync(g);
+    if (gt == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_pass(0);
+    }
+    bool bad = false;
+    E result = F::zero();
+    for (uint32_t p = 0; p < npass; ++p) {
+      // the shares this pass is checked against: requested before waiting for the MMA
+      constexpr uint32_t kPassRows = PCOLS / EB;
+      E chk[kPassRows];
+#pragma unroll
+      for (uint32_t rr = 0; rr < kPassRows; ++rr) {
+        const uint32_t r = p * kPassRows + rr;
+        chk[rr] = (r < n_checks) ? src[(uint64_t)(m + r) * stride_i] : F::zero();
+      }
+      mbar_wait(mbar, ph);
+      ph ^= 1u;
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[32];
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        tmem_ld32(acc0 + lane_off + 32u * h, v);
+        if (h == 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          group_sync(g);  // accumulator drained: the next pass may overwrite it
+          if (gt == 0 && p + 1u < npass) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_pass(p + 1u);
+          }
+        }
+#pragma unroll
+        for (uint32_t ii = 0; ii < kLdRows; ++ii) {
+          const uint32_t rr = h * kLdRows + ii, r = p * kPassRows + rr;
+          E y;
+          if constexpr (EB == 8) y = tc_combine(v + 8 * ii);
+          else y = tc_combine127(v + 16 * ii);
+          if (r < n_checks) bad = bad || !F::eq(y, chk[rr]);
+          else if (r == n_checks) result = y;
+        }
+      }
+    }
+    if (valid) {
+      out[j] = bad ? F::zero() : result;
+      err[j] = bad ? 1 : 0;
+      local_bad += bad;
+    }
+  }
+  if (local_bad) atomicAdd(n_bad, local_bad);
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+static constexpr int kRdGroups = 4;
+static constexpr uint32_t kRdDynSmem = 120u * 1024u;  // > half of an SM's shared memory: one CTA (one TMEM owner) per SM
+
+template <class F>
+static cudaError_t recover_d_tc_launch_t(cudaStream_t st, int sm_count, const void* d_bmat, const typename F::E* d_in,
+                                         uint64_t N, uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
+                                         typename F::E* d_out, uint8_t* d_err, unsigned long long* d_count) {
+  static bool prepared = false;
+  if (!prepared) {
+    cudaError_t e = cudaFuncSetAttribute(k_recover_d_tc<F, kRdGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdDynSmem);
+    if (e != cudaSuccess) return e;
+    prepared = true;
+  }
+  const uint64_t tiles = (N + 127) / 128;
+  const int grid = (int)std::min<uint64_t>((tiles + kRdGroups - 1) / kRdGroups, (uint64_t)sm_count);
+  k_recover_d_tc<F, kRdGroups><<<grid, 128 * kRdGroups, kRdDynSmem, st>>>(reinterpret_cast<const uint4*>(d_bmat), d_in, N, si, sj, m,
+                                                                         n_checks, d_out, d_err, d_count);
+  return cudaGetLastError();
+}
+
+cudaError_t recover_d61_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const uint64_t* d_in, uint64_t N,
+                                  uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks, uint64_t* d_out, uint8_t* d_err,
+                                  unsigned long long* d_count) {
+  return recover_d_tc_launch_t<F61>(st, sm_count, d_bmat, d_in, N, si, sj, m, n_checks, d_out, d_err, d_count);
+}
+cudaError_t recover_d127_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_in, uint64_t N,
+                                   uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks, E127* d_out, uint8_t* d_err,
+                                   unsigned long long* d_count) {
+  return recover_d_tc_launch_t<F127>(st, sm_count, d_bmat, d_in, N, si, sj, m, n_checks, d_out, d_err, d_count);
+}
 
 cudaError_t share_tc_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);

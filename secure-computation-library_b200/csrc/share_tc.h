@@ -36,4 +36,16 @@ cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const Aes
                                const void* d_bmat, uint64_t first_block, const E127* d_secrets, uint64_t N, uint32_t t,
                                uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j);
 
+// shamirRecoverD on tensor cores: m*BYTES <= 128 and (n_checks+1)*BYTES <= 128 (two 64-column passes)
+template <class F>
+static inline bool recover_d_tc_fits(uint32_t m, uint32_t n_checks) {
+  return m >= 1 && m * F::BYTES <= 128u && (n_checks + 1u) * F::BYTES <= 128u;
+}
+cudaError_t recover_d61_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const uint64_t* d_in, uint64_t N,
+                                  uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks, uint64_t* d_out, uint8_t* d_err,
+                                  unsigned long long* d_count);
+cudaError_t recover_d127_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_in, uint64_t N,
+                                   uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks, E127* d_out, uint8_t* d_err,
+                                   unsigned long long* d_count);
+
 }  // namespace sclgpu
