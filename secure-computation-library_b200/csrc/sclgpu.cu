@@ -2,8 +2,10 @@
 // include/sclgpu.h.  Pure CUDA runtime; no torch types cross this boundary.
 //
 // Host-side arithmetic is limited to the AES-128 key schedule (PRG::create /
-// aes128LoadKey, src/scl/util/prg.cc:54-101); all field arithmetic, including the
-// Lagrange bases, runs on the device.
+// aes128LoadKey, src/scl/util/prg.cc:54-101) and the constant limb images of the
+// tensor-core kernels (powers of the evaluation points / Lagrange rows times 2^(8a),
+// a few hundred field multiplications per (field, t, n), cached); everything that
+// scales with the batch, and the Lagrange bases themselves, runs on the device.
 #include <cuda_runtime.h>
 
 #include <algorithm>
