@@ -30,19 +30,46 @@ __device__ __forceinline__ uint32_t aes_prologue(const uint32_t* __restrict__ g_
   return lanebase;
 }
 
+// -------------------------------------------------------------------------
+// Keystream blocks [first_block, first_block + n_blocks) with counter-mode caching: a
+// warp takes one 256-counter group at a time (all counters sharing ctr >> 8), computes
+// the group's rounds-1/2 state once (prg_group, 27 lookups) and then eight blocks per
+// lane (ctr = group*256 + 32k + lane) at 133 lookups each instead of 160.  For every k
+// the warp's 32 blocks are consecutive, so consumers store coalesced.
+template <class Fn>
+__device__ __forceinline__ void prg_for_each_block(const AesKey& key, uint32_t lanebase, uint64_t first_block,
+                                                   uint64_t n_blocks, Fn&& fn) {
+  if (n_blocks == 0) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t g_first = first_block >> 8, g_last = (first_block + n_blocks - 1) >> 8;
+  for (uint64_t grp_idx = g_first + warp; grp_idx <= g_last; grp_idx += warps) {
+    PrgGroup grp;
+    prg_group(key, lanebase, grp_idx << 8, grp);
+#pragma unroll 1
+    for (uint32_t k = 0; k < 8; ++k) {
+      const uint64_t ctr = (grp_idx << 8) + 32u * k + lane;
+      if (ctr >= first_block && ctr - first_block < n_blocks) {
+        uint32_t o0, o1, o2, o3;
+        prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+        fn(ctr - first_block, o0, o1, o2, o3);
+      }
+    }
+  }
+}
+
 // =========================================================== PRG::next bytes
-// prg.cc:124-146.  Thread = one 16-byte block, written as one 128-bit store.
+// prg.cc:124-146.  Thread = one 16-byte block at a time, written as one 128-bit store.
 __global__ void __launch_bounds__(kAesThreads, 1)
 k_prg_bytes(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
             uint64_t first_block, uint64_t n_bytes, uint8_t* __restrict__ out) {
   const uint32_t lanebase = aes_prologue(g_t0);
   const uint64_t n_full = n_bytes >> 4;
   const uint64_t n_blocks = (n_bytes + 15) >> 4;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += stride) {
-    uint32_t o0, o1, o2, o3;
-    prg_block(key, lanebase, first_block + b, o0, o1, o2, o3);
+  prg_for_each_block(key, lanebase, first_block, n_blocks,
+                     [&](uint64_t b, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
     if (b < n_full && aligned) {
       reinterpret_cast<uint4*>(out)[b] = make_uint4(o0, o1, o2, o3);
     } else {
@@ -51,7 +78,7 @@ k_prg_bytes(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
       const int m = left < 16 ? (int)left : 16;
       for (int i = 0; i < m; ++i) out[b * 16 + i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
     }
-  }
+  });
 }
 
 // ===================================== Vector::random / FF::random elements
@@ -62,12 +89,10 @@ __global__ void __launch_bounds__(kAesThreads, 1)
 k_random(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0, uint64_t first_block,
          uint64_t n, typename F::E* __restrict__ out) {
   const uint32_t lanebase = aes_prologue(g_t0);
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t per_block = (F::BYTES == 16 || ONE_PER_BLOCK) ? 1 : 2;
   const uint64_t n_blocks = (n + per_block - 1) / per_block;
-  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += stride) {
-    uint32_t o0, o1, o2, o3;
-    prg_block(key, lanebase, first_block + b, o0, o1, o2, o3);
+  prg_for_each_block(key, lanebase, first_block, n_blocks,
+                     [&](uint64_t b, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
     const uint64_t w0 = (uint64_t)o0 | ((uint64_t)o1 << 32), w1 = (uint64_t)o2 | ((uint64_t)o3 << 32);
     if constexpr (F::BYTES == 16) {
       out[b] = F127::from_raw(E127{w0, w1});
@@ -75,13 +100,14 @@ k_random(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0, 
       out[b] = F61::from_raw(w0);
     } else {
       const uint64_t e0 = F61::from_raw(w0), e1 = F61::from_raw(w1);
-      if (2 * b + 1 < n) {
-        reinterpret_cast<ulonglong2*>(out)[b] = make_ulonglong2(e0, e1);  // cudaMalloc'd: 16B aligned
+      if (2 * b + 1 < n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        reinterpret_cast<ulonglong2*>(out)[b] = make_ulonglong2(e0, e1);
       } else {
         out[2 * b] = e0;
+        if (2 * b + 1 < n) out[2 * b + 1] = e1;
       }
     }
-  }
+  });
 }
 
 // FF::read on packed bytes (ff.h:63-67): n elements, bytes little-endian
@@ -791,6 +817,46 @@ k_matvec61_v2(const uint64_t* __restrict__ A, uint32_t rows, uint32_t cols,
     }
     uint64_t s = block_reduce_sum<F61>(F61::acc_reduce(acc));
     if (threadIdx.x == 0) y[r] = s;
+  }
+}
+
+// Fp61, one WARP per row (cols even, 16-byte aligned rows): four independent 128-bit loads
+// of A in flight per lane, x through the read-only path (64 KiB at C5: L1/L2 resident), a
+// shuffle tree at the end -- no block barrier between rows.  HBM-bound: 8 bytes per modmul.
+__global__ void __launch_bounds__(256)
+k_matvec61_warp(const uint64_t* __restrict__ A, uint32_t rows, uint32_t cols,
+                const uint64_t* __restrict__ x, uint64_t* __restrict__ y) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t c2 = cols >> 1;
+  const ulonglong2* x2 = reinterpret_cast<const ulonglong2*>(x);
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(A + (uint64_t)r * cols);
+    F61::Acc acc = F61::acc_zero();
+    uint32_t c = lane;
+    for (; c + 96u < c2; c += 128u) {
+      ulonglong2 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a[k].x), "=l"(a[k].y) : "l"(row + c + 32 * k));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const ulonglong2 xv = __ldg(x2 + c + 32 * k);
+        F61::mac(acc, a[k].x, xv.x);
+        F61::mac(acc, a[k].y, xv.y);
+      }
+      F61::acc_fold(acc);  // 8 products per round: far below the 32-term bound
+    }
+    for (; c < c2; c += 32u) {
+      const ulonglong2 av = __ldg(row + c), xv = __ldg(x2 + c);
+      F61::mac(acc, av.x, xv.x);
+      F61::mac(acc, av.y, xv.y);
+      F61::acc_fold(acc);
+    }
+    uint64_t s = F61::acc_reduce(acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s = F61::add(s, __shfl_down_sync(0xffffffffu, s, off));
+    if (lane == 0) y[r] = s;
   }
 }
 

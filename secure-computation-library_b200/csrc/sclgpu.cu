@@ -1214,7 +1214,12 @@ static int matvec_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, u
   const int grid = (int)std::min<uint64_t>(rows, (uint64_t)ctx->sm_count * 8);
   if constexpr (F::BYTES == 8) {
     if ((cols & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
-      k_matvec61_v2<<<grid, 256, 0, st>>>(A, rows, cols, x, y);
+      if (cols >= 256) {  // one warp per row
+        const int wgrid = (int)std::min<uint64_t>(((uint64_t)rows + 7) / 8, (uint64_t)ctx->sm_count * 8);
+        k_matvec61_warp<<<wgrid, 256, 0, st>>>(A, rows, cols, x, y);
+      } else {
+        k_matvec61_v2<<<grid, 256, 0, st>>>(A, rows, cols, x, y);
+      }
       CKL();
       return SCLGPU_OK;
     }

@@ -251,7 +251,8 @@ def test_matvec_golden_and_vs_oracle(ctx, orc, port, golden):
         A = port.vector_random(f, "mat A", 0, rows * cols).reshape((rows, cols) + (() if f == 61 else (2,)))
         x = port.vector_random(f, "vec x", 0, cols)
         assert ints(port, ctx.matvec(f, A, x), f) == [int(h, 16) for h in c["hex"]]
-    for field, rows, cols in [(61, 300, 1024), (61, 7, 4097), (61, 1, 1), (127, 64, 513), (61, 128, 8192)]:
+    for field, rows, cols in [(61, 300, 1024), (61, 7, 4097), (61, 1, 1), (127, 64, 513), (61, 128, 8192), (61, 33, 258),
+                              (61, 5, 1000), (61, 2049, 256)]:
         A = orc.vector_random(field, "mat A", 0, rows * cols).reshape((rows, cols) + (() if field == 61 else (2,)))
         x = orc.vector_random(field, "vec x", 0, cols)
         assert np.array_equal(ctx.matvec(field, A, x), orc.matvec(field, A, x)), (field, rows, cols)
