@@ -313,7 +313,7 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
   const uint32_t tbase = aes_table_base(dyn_smem);
   const uint32_t b_base = tbase + kAesTableBytes;
   const uint32_t ctl = b_base + kTcBmatBytes;             // 2*GROUPS mbarriers + the TMEM base address
-  if (ctl + 128u > dyn + kTcDynSmem) __trap();
+  if (ctl + 128u > dyn + kTcmDynSmem) __trap();
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
   aes_fill_tables(tbase, g_t0);
@@ -662,8 +662,8 @@ cudaError_t recover_d127_tc_launch(cudaStream_t st, int sm_count, const void* d_
 cudaError_t share_tc_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
 #define X(V, G, NB, PC)                                                                                                                       \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
   SCLGPU_TCM_VARIANTS(X)
 #undef X
   return e;
@@ -684,7 +684,7 @@ cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesK
   bool done = false;
 #define X(V, G, NB, PC)                                                                                               \
   if (variant == V) {                                                                                                 \
-    k_share_tcm<F61, G, NB, PC><<<grid, 128 * G, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
+    k_share_tcm<F61, G, NB, PC><<<grid, 128 * G, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
                                                                   d_out, stride_i, stride_j);                         \
     done = true;                                                                                                      \
   }
@@ -700,9 +700,9 @@ cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const Aes
                                uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j) {
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
   if (variant == 2) {
-    k_share_tcm<F127, 4, 1, 64><<<grid, 512, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    k_share_tcm<F127, 4, 1, 64><<<grid, 512, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
   } else {
-    k_share_tcm<F127, 5, 1, 64><<<grid, 640, kTcDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    k_share_tcm<F127, 5, 1, 64><<<grid, 640, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
   }
   return cudaGetLastError();
 }

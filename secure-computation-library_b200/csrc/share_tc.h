@@ -14,6 +14,10 @@ static constexpr int kTcGroups = 3;                   // 128-secret tiles in fli
 static constexpr int kTcThreads = 128 * kTcGroups;    // 4 warps per group
 static constexpr uint32_t kTcBmatBytes = 32768;       // 32 parties x 8 limbs rows of K = 128 bytes
 static constexpr uint32_t kTcDynSmem = 232448;        // 227 KiB: A tiles | AES tables | B limbs | barriers
+// A operand in tensor memory: [1 KiB .. 64 KiB) unused | AES tables | B limbs | barriers.  Requesting exactly
+// what is addressed leaves ~4 KiB of the SM's shared memory for a small co-resident CTA (e.g. the HBM-bound
+// reconstruction kernel of another stream).
+static constexpr uint32_t kTcmDynSmem = (65536u - 1024u) + 131072u + kTcBmatBytes + 128u;
 static constexpr uint32_t kTcMaxT = 15, kTcMaxParties = 32;        // Fp61:  K = 8(t+1)  <= 128 bytes, 8 limbs per party
 static constexpr uint32_t kTcMaxT127 = 7, kTcMaxParties127 = 16;   // Fp127: K = 16(t+1) <= 128 bytes, 16 limbs per party
 
