@@ -20,7 +20,16 @@ namespace sclgpu {
 
 struct AesKey {
   uint32_t rk[44];  // 11 round keys x 4 LE column words (host-expanded, prg.cc:54-75)
+  // 2^8, 2^16, 2^24 as RUN-TIME values (set by the host): multiplying by them moves byte
+  // extraction from the ALU pipe (PRMT) to the FMA pipe (IMAD / IMAD.HI), see aes_addr_fma
+  uint32_t k8, k16, k24;
 };
+
+// Measured on B200 (2^26 secrets, n=32, t=15): share 11.1 ms with PRMT addresses, 12.9 ms with the
+// FMA-pipe form below (IMAD.HI is a multi-issue instruction); keystream 2.11 vs 2.40 ms.  Off.
+#ifndef SCLGPU_AES_FMA_ADDR
+#define SCLGPU_AES_FMA_ADDR 0
+#endif
 
 static constexpr uint32_t kPrgNonceLo = 0x89ABCDEFu;  // PRG_NONCE, prg.h:34-36
 static constexpr uint32_t kPrgNonceHi = 0x01234567u;
@@ -140,6 +149,35 @@ __device__ __forceinline__ uint32_t aes_t(uint32_t w, uint32_t lanebase) {
   return aes_lds<OFF>(aes_addr<K>(w, lanebase));
 }
 
+// The same lookup address, formed on the FMA pipe for the two end bytes (the ALU pipe is the
+// co-critical pipe of the fused kernels, the FMA pipe is idle):
+//   byte 3:  lanebase + (w >> 24) * 256  =  mad.lo(mul.hi(w, 2^8), 2^8, lanebase)
+//   byte 0:  lanebase + (w & 255) * 256  =  mad.hi(w * 2^24, 2^16, lanebase)
+// bytes 1 and 2 would need three multiplies each and stay on PRMT.
+template <int K>
+__device__ __forceinline__ uint32_t aes_addr_fma(const AesKey& key, uint32_t w, uint32_t lanebase) {
+#if SCLGPU_AES_FMA_ADDR
+  if (K == 3) {
+    uint32_t t, a;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(key.k8));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(t), "r"(key.k8), "r"(lanebase));
+    return a;
+  }
+  if (K == 0) {
+    uint32_t t, a;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(key.k24));
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(t), "r"(key.k16), "r"(lanebase));
+    return a;
+  }
+#endif
+  return aes_addr<K>(w, lanebase);
+}
+template <int TBL, int K>
+__device__ __forceinline__ uint32_t aes_tk(const AesKey& key, uint32_t w, uint32_t lanebase) {
+  constexpr int OFF = (TBL & 1) * 128 + (TBL >> 1) * 65536;
+  return aes_lds<OFF>(aes_addr_fma<K>(key, w, lanebase));
+}
+
 // group state for the 256 counters sharing ctr >> 8
 __device__ __forceinline__ void prg_group(const AesKey& key, uint32_t lanebase, uint64_t ctr,
                                           PrgGroup& g) {
@@ -165,14 +203,14 @@ __device__ __forceinline__ void aes128_tail(const AesKey& key, uint32_t lanebase
                                             uint32_t& o2, uint32_t& o3) {
 #pragma unroll
   for (int r = R0; r < 10; ++r) {
-    const uint32_t t0 = aes_t<0, 0>(s0, lanebase) ^ aes_t<1, 1>(s1, lanebase) ^ aes_t<2, 2>(s2, lanebase) ^
-                        aes_t<3, 3>(s3, lanebase) ^ key.rk[4 * r + 0];
-    const uint32_t t1 = aes_t<0, 0>(s1, lanebase) ^ aes_t<1, 1>(s2, lanebase) ^ aes_t<2, 2>(s3, lanebase) ^
-                        aes_t<3, 3>(s0, lanebase) ^ key.rk[4 * r + 1];
-    const uint32_t t2 = aes_t<0, 0>(s2, lanebase) ^ aes_t<1, 1>(s3, lanebase) ^ aes_t<2, 2>(s0, lanebase) ^
-                        aes_t<3, 3>(s1, lanebase) ^ key.rk[4 * r + 2];
-    const uint32_t t3 = aes_t<0, 0>(s3, lanebase) ^ aes_t<1, 1>(s0, lanebase) ^ aes_t<2, 2>(s1, lanebase) ^
-                        aes_t<3, 3>(s2, lanebase) ^ key.rk[4 * r + 3];
+    const uint32_t t0 = aes_tk<0, 0>(key, s0, lanebase) ^ aes_tk<1, 1>(key, s1, lanebase) ^ aes_tk<2, 2>(key, s2, lanebase) ^
+                        aes_tk<3, 3>(key, s3, lanebase) ^ key.rk[4 * r + 0];
+    const uint32_t t1 = aes_tk<0, 0>(key, s1, lanebase) ^ aes_tk<1, 1>(key, s2, lanebase) ^ aes_tk<2, 2>(key, s3, lanebase) ^
+                        aes_tk<3, 3>(key, s0, lanebase) ^ key.rk[4 * r + 1];
+    const uint32_t t2 = aes_tk<0, 0>(key, s2, lanebase) ^ aes_tk<1, 1>(key, s3, lanebase) ^ aes_tk<2, 2>(key, s0, lanebase) ^
+                        aes_tk<3, 3>(key, s1, lanebase) ^ key.rk[4 * r + 2];
+    const uint32_t t3 = aes_tk<0, 0>(key, s3, lanebase) ^ aes_tk<1, 1>(key, s0, lanebase) ^ aes_tk<2, 2>(key, s1, lanebase) ^
+                        aes_tk<3, 3>(key, s2, lanebase) ^ key.rk[4 * r + 3];
     s0 = t0;
     s1 = t1;
     s2 = t2;
@@ -180,8 +218,8 @@ __device__ __forceinline__ void aes128_tail(const AesKey& key, uint32_t lanebase
   }
   // final round: S[x] sits in byte 0 of T2/T3, byte 1 of T0/T3, byte 2 of T0/T1, byte 3 of T1/T2
 #define SCLGPU_AES_LAST2(w0, w1, w2, w3)                                                          \
-  __byte_perm(__byte_perm(aes_t<2, 0>(w0, lanebase), aes_t<3, 1>(w1, lanebase), 0x0050),          \
-              __byte_perm(aes_t<0, 2>(w2, lanebase), aes_t<1, 3>(w3, lanebase), 0x7200), 0x7610)
+  __byte_perm(__byte_perm(aes_tk<2, 0>(key, w0, lanebase), aes_tk<3, 1>(key, w1, lanebase), 0x0050),          \
+              __byte_perm(aes_tk<0, 2>(key, w2, lanebase), aes_tk<1, 3>(key, w3, lanebase), 0x7200), 0x7610)
   o0 = SCLGPU_AES_LAST2(s0, s1, s2, s3) ^ key.rk[40];
   o1 = SCLGPU_AES_LAST2(s1, s2, s3, s0) ^ key.rk[41];
   o2 = SCLGPU_AES_LAST2(s2, s3, s0, s1) ^ key.rk[42];
@@ -194,8 +232,8 @@ __device__ __forceinline__ void prg_block_grouped(const AesKey& key, uint32_t la
                                                   uint32_t ctr_lo, uint32_t& o0, uint32_t& o1, uint32_t& o2,
                                                   uint32_t& o3) {
   const uint32_t t0 = aes_t<0, 0>(ctr_lo ^ key.rk[0], lanebase) ^ g.k0;
-  const uint32_t s0 = aes_t<0, 0>(t0, lanebase) ^ g.u0;
-  const uint32_t s1 = aes_t<3, 3>(t0, lanebase) ^ g.u1;
+  const uint32_t s0 = aes_tk<0, 0>(key, t0, lanebase) ^ g.u0;
+  const uint32_t s1 = aes_tk<3, 3>(key, t0, lanebase) ^ g.u1;
   const uint32_t s2 = aes_t<2, 2>(t0, lanebase) ^ g.u2;
   const uint32_t s3 = aes_t<1, 1>(t0, lanebase) ^ g.u3;
   aes128_tail<3>(key, lanebase, s0, s1, s2, s3, o0, o1, o2, o3);

@@ -115,6 +115,9 @@ static AesKey aes_expand(const uint8_t seed[16]) {
     }
     k.rk[i] = k.rk[i - 4] ^ t;
   }
+  k.k8 = 1u << 8;
+  k.k16 = 1u << 16;
+  k.k24 = 1u << 24;
   return k;
 }
 
