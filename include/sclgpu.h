@@ -141,6 +141,32 @@ int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const uint64_t* d_coeff
 int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N,
                                          uint32_t t, uint32_t n, void* d_shares, int layout);
 
+/* ---- ss::additiveShare (include/scl/ss/additive.h:42-53), called N times on one PRG
+ * Secret j: n-1 shares drawn with FF::random (ff.h:72-76: ONE whole keystream block
+ * per share, bytes beyond byteSize dropped) from blocks
+ * [first_block + j*(n-1), first_block + (j+1)*(n-1)), last share = secret - sum.
+ * Consumes N*(n-1) blocks.  n >= 1 (the reference's loop bound n-1 is unsigned).
+ * additive_recover: the reconstruction the reference documents, shares.sum()
+ * (additive.h:38-39, vector.h:262-267), per sharing.
+ * Host versions use SCLGPU_SECRET_MAJOR ([N][n], row j = SCL's Vector for secret j). */
+int sclgpu_fp61_additive_share(sclgpu_ctx* ctx, const uint64_t* secrets, uint64_t N, uint32_t n,
+                               const uint8_t seed[16], uint64_t first_block, uint64_t* shares);
+int sclgpu_fp127_additive_share(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t n,
+                                const uint8_t seed[16], uint64_t first_block, void* shares);
+int sclgpu_fp61_additive_share_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N, uint32_t n,
+                                   const uint8_t seed[16], uint64_t first_block, uint64_t* d_shares,
+                                   int layout);
+int sclgpu_fp127_additive_share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_t n,
+                                    const uint8_t seed[16], uint64_t first_block, void* d_shares,
+                                    int layout);
+int sclgpu_fp61_additive_recover(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t n,
+                                 uint64_t* out);
+int sclgpu_fp127_additive_recover(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n, void* out);
+int sclgpu_fp61_additive_recover_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N, uint32_t n,
+                                     int layout, uint64_t* d_out);
+int sclgpu_fp127_additive_recover_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n,
+                                      int layout, void* d_out);
+
 /* ---- math::computeLagrangeBasis (lagrange.h:55-71) --------------------------
  * out[i] = prod_{j != i} (x - nodes[j]) / (nodes[i] - nodes[j]).  nodes == NULL
  * means Vector::range(1, n+1) (vector.h:491-505).  Computed on the device.

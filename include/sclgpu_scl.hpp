@@ -15,6 +15,8 @@
 //     -> sclgpu::shamirRecoverP(ctx, shares[, alphas, x])   : Vector (N)
 //   scl::ss::shamirRecoverD(shares, t)                   shamir.h:117-155
 //     -> sclgpu::shamirRecoverD(ctx, shares, t[, flags])    : Vector (N); throws as SCL unless flags != nullptr
+//   scl::ss::additiveShare(secret, n, prg)               additive.h:42-53
+//     -> sclgpu::additiveShare(ctx, secrets, n, prg)        : Matrix (N x n); sclgpu::additiveReconstruct = row sums
 //   scl::math::Vector<FF>::random(n, prg)                vector.h:508-519
 //     -> sclgpu::randomVector<FF>(ctx, n, prg)
 //   Vector add / subtract / multiplyEntryWise / scalarMultiply / dot / sum   vector.h:192-301
@@ -62,6 +64,8 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto random = &sclgpu_##SUF##_random;                                                    \
     static constexpr auto share = &sclgpu_##SUF##_shamir_share;                                               \
     static constexpr auto recover_p = &sclgpu_##SUF##_recover_p;                                              \
+    static constexpr auto additive_share = &sclgpu_##SUF##_additive_share;                                    \
+    static constexpr auto additive_recover = &sclgpu_##SUF##_additive_recover;                                \
     static constexpr auto recover_d = &sclgpu_##SUF##_recover_d;                                              \
     static constexpr auto vec_add = &sclgpu_##SUF##_vec_add;                                                  \
     static constexpr auto vec_sub = &sclgpu_##SUF##_vec_sub;                                                  \
@@ -152,6 +156,34 @@ scl::math::Matrix<FF> shamirSecretShare(Context& ctx, const scl::math::Vector<FF
                      (std::uint32_t)n, seed.data(), (std::uint64_t)ctr, detail::raw<FF>(&shares(0, 0))));
   ctr += (long)(N * detail::shareBlocks(A::BYTES, t));
   return shares;
+}
+
+// ---- additiveShare on every element of `secrets`, additive.h:42-53: n-1 FF::random draws per
+// secret (one keystream block each) and secret - sum.  Reconstruction (shares.sum(), additive.h:38-39)
+// per row: additiveReconstruct.
+template <class FF>
+scl::math::Matrix<FF> additiveShare(Context& ctx, const scl::math::Vector<FF>& secrets, std::size_t n,
+                                    scl::util::PRG& prg) {
+  using A = detail::Abi<FF>;
+  const std::size_t N = secrets.size();
+  if (n == 0) throw std::invalid_argument("additiveShare needs n >= 1");
+  if (N == 0) return scl::math::Matrix<FF>();
+  scl::math::Matrix<FF> shares(N, n);
+  long& ctr = detail::prgCounter(prg);
+  const auto seed = prg.Seed();
+  ctx.check(A::additive_share(ctx.get(), detail::raw<FF>(secrets.toStlVector().data()), N, (std::uint32_t)n,
+                              seed.data(), (std::uint64_t)ctr, detail::raw<FF>(&shares(0, 0))));
+  ctr += (long)(N * (n - 1));
+  return shares;
+}
+template <class FF>
+scl::math::Vector<FF> additiveReconstruct(Context& ctx, const scl::math::Matrix<FF>& shares) {
+  using A = detail::Abi<FF>;
+  std::vector<FF> out(shares.rows());
+  if (shares.rows() == 0) return scl::math::Vector<FF>(std::move(out));
+  ctx.check(A::additive_recover(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(shares)(0, 0)),
+                                shares.rows(), (std::uint32_t)shares.cols(), detail::raw<FF>(out.data())));
+  return scl::math::Vector<FF>(std::move(out));
 }
 
 // ---- shamirRecoverP(shares), shamir.h:100-104: row j of `shares` = one sharing

@@ -143,6 +143,10 @@ class PortOracle(_Base):
                 g(n).restype = None
             g("shamir_share").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
             g("shamir_share").restype = None
+            g("additive_share").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
+            g("additive_share").restype = None
+            g("additive_recover").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
+            g("additive_recover").restype = None
             g("lagrange").argtypes = [_vp, C.c_uint64, _vp, _vp]
             g("lagrange").restype = C.c_int
             g("recover_p").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp]
@@ -198,6 +202,20 @@ class PortOracle(_Base):
         N = _nelem(secrets, field)
         out = empty(field, N, n)
         self._f(field, "shamir_share")(_p(secrets), N, t, n, seed16(seed), first_block, _p(out))
+        return out
+
+    def additive_share(self, field, secrets, n, seed, first_block=0):
+        secrets = _c(secrets)
+        N = _nelem(secrets, field)
+        out = empty(field, N, n)
+        self._f(field, "additive_share")(_p(secrets), N, n, seed16(seed), first_block, _p(out))
+        return out
+
+    def additive_recover(self, field, shares):
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        out = empty(field, N)
+        self._f(field, "additive_recover")(_p(shares), N, n, _p(out))
         return out
 
     def lagrange(self, field, nodes, x: int):
@@ -287,6 +305,10 @@ class RefOracle(_Base):
                 g(n).restype = None
             g("shamir_share").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
             g("shamir_share").restype = None
+            g("additive_share").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
+            g("additive_share").restype = None
+            g("additive_recover").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
+            g("additive_recover").restype = None
             g("recover_p").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp]
             g("recover_p").restype = None
             g("recover_d").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp]
@@ -356,6 +378,21 @@ class RefOracle(_Base):
         N = _nelem(secrets, field)
         out = empty(field, N, n)
         self._f(field, "shamir_share")(_p(secrets), N, t, n, s, sl, first_block, _p(out))
+        return out
+
+    def additive_share(self, field, secrets, n, seed, first_block=0):
+        s, sl = self._seed(seed)
+        secrets = _c(secrets)
+        N = _nelem(secrets, field)
+        out = empty(field, N, n)
+        self._f(field, "additive_share")(_p(secrets), N, n, s, sl, first_block, _p(out))
+        return out
+
+    def additive_recover(self, field, shares):
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        out = empty(field, N)
+        self._f(field, "additive_recover")(_p(shares), N, n, _p(out))
         return out
 
     def lagrange(self, field, nodes, x: int):

@@ -13,6 +13,7 @@
 //     math::FF<F>::random                (include/scl/math/ff.h:72-76)
 //     ss::shamirSecretShare              (include/scl/ss/shamir.h:52-68)
 //     ss::shamirRecoverP / shamirRecoverD(include/scl/ss/shamir.h:82-155)
+//     ss::additiveShare                  (include/scl/ss/additive.h:42-53)
 //     math::computeLagrangeBasis         (include/scl/math/lagrange.h:55-71)
 //     math::Matrix<T>::multiply(Vector)  (include/scl/math/matrix.h:498-513)
 //     Vector add/subtract/multiplyEntryWise/scalarMultiply/dot/sum
@@ -31,6 +32,7 @@
 #include "scl/math/lagrange.h"
 #include "scl/math/matrix.h"
 #include "scl/math/vector.h"
+#include "scl/ss/additive.h"
 #include "scl/ss/shamir.h"
 #include "scl/util/prg.h"
 
@@ -110,6 +112,30 @@ void shamirShare(const unsigned char* secrets, uint64_t N, uint64_t t,
     const T secret = T::read(secrets + j * bs);
     const auto sh = scl::ss::shamirSecretShare(secret, t, n, prg);
     writeVec(sh, shares + j * n * bs);
+  }
+}
+
+// ss::additiveShare(secret, n, prg) per secret on one PRG; reconstruction is
+// shares.sum() (additive.h:38-39).
+template <typename T>
+void additiveShare(const unsigned char* secrets, uint64_t N, uint64_t n,
+                   const unsigned char* seed, uint64_t seed_len, uint64_t skip,
+                   unsigned char* shares) {
+  PRG prg = makePrg(seed, seed_len, skip);
+  const std::size_t bs = T::byteSize();
+  for (uint64_t j = 0; j < N; ++j) {
+    const T secret = T::read(secrets + j * bs);
+    const auto sh = scl::ss::additiveShare(secret, n, prg);
+    writeVec(sh, shares + j * n * bs);
+  }
+}
+
+template <typename T>
+void additiveRecover(const unsigned char* shares, uint64_t N, uint64_t n,
+                     unsigned char* out) {
+  const std::size_t bs = T::byteSize();
+  for (uint64_t j = 0; j < N; ++j) {
+    readVec<T>(shares + j * n * bs, n).sum().write(out + j * bs);
   }
 }
 
@@ -325,6 +351,17 @@ double benchShareRecover(uint64_t N, uint64_t t, uint64_t n, int detect,
       const unsigned char* seed, uint64_t seed_len, uint64_t skip,             \
       unsigned char* shares) {                                                 \
     shamirShare<T>(secrets, N, t, n, seed, seed_len, skip, shares);            \
+  }                                                                            \
+  void sclref_##SUF##_additive_share(                                          \
+      const unsigned char* secrets, uint64_t N, uint64_t n,                    \
+      const unsigned char* seed, uint64_t seed_len, uint64_t skip,             \
+      unsigned char* shares) {                                                 \
+    additiveShare<T>(secrets, N, n, seed, seed_len, skip, shares);             \
+  }                                                                            \
+  void sclref_##SUF##_additive_recover(const unsigned char* shares,            \
+                                       uint64_t N, uint64_t n,                 \
+                                       unsigned char* out) {                   \
+    additiveRecover<T>(shares, N, n, out);                                     \
   }                                                                            \
   void sclref_##SUF##_recover_p(const unsigned char* shares, uint64_t N,       \
                                 uint64_t n, const unsigned char* alphas,       \

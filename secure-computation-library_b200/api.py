@@ -224,6 +224,31 @@ class Context:
     def shamir_share_coeffs_dev(self, field: int, coeffs, N: int, t: int, n: int, shares, layout: int = B.PARTY_MAJOR):
         self._check(self._f(field, "shamir_share_coeffs_dev")(self._ctx, _dp(coeffs), N, t, n, _dp(shares), layout))
 
+    # ------------------------------------------------------------ additive sharing
+    def additive_share(self, field: int, secrets, n: int, seed, first_block: int = 0) -> np.ndarray:
+        """ss::additiveShare (additive.h:42-53) of every secret; consumes N*(n-1) blocks."""
+        if n < 1:
+            raise InvalidArgument("additiveShare needs n >= 1")
+        secrets = _c(secrets)
+        N = _nelem(secrets, field)
+        out = empty(field, N, n)
+        self._check(self._f(field, "additive_share")(self._ctx, _p(secrets), N, n, seed16(seed), first_block, _p(out)))
+        return out
+
+    def additive_share_dev(self, field: int, secrets, N: int, n: int, seed, first_block: int, shares,
+                           layout: int = B.PARTY_MAJOR):
+        self._check(self._f(field, "additive_share_dev")(self._ctx, _dp(secrets), N, n, seed16(seed), first_block, _dp(shares), layout))
+
+    def additive_recover(self, field: int, shares) -> np.ndarray:
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        out = empty(field, N)
+        self._check(self._f(field, "additive_recover")(self._ctx, _p(shares), N, n, _p(out)))
+        return out
+
+    def additive_recover_dev(self, field: int, shares, N: int, n: int, out, layout: int = B.PARTY_MAJOR):
+        self._check(self._f(field, "additive_recover_dev")(self._ctx, _dp(shares), N, n, layout, _dp(out)))
+
     def lagrange(self, field: int, nodes, x: int, n: int | None = None) -> np.ndarray:
         nodes_a = None if nodes is None else _c(nodes)
         n = _nelem(nodes_a, field) if nodes_a is not None else int(n)

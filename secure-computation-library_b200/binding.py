@@ -86,6 +86,10 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_shamir_share", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_shamir_share_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _int)
         _sig(lib, f"sclgpu_{f}_shamir_share_coeffs_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _int)
+        _sig(lib, f"sclgpu_{f}_additive_share", _int, _vp, _vp, _u64, _u32, _vp, _u64, _vp)
+        _sig(lib, f"sclgpu_{f}_additive_share_dev", _int, _vp, _vp, _u64, _u32, _vp, _u64, _vp, _int)
+        _sig(lib, f"sclgpu_{f}_additive_recover", _int, _vp, _vp, _u64, _u32, _vp)
+        _sig(lib, f"sclgpu_{f}_additive_recover_dev", _int, _vp, _vp, _u64, _u32, _int, _vp)
         _sig(lib, f"sclgpu_{f}_lagrange_basis", _int, _vp, _vp, _u32, _vp, _vp)
         _sig(lib, f"sclgpu_{f}_recover_p", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp)
         _sig(lib, f"sclgpu_{f}_recover_p_dev", _int, _vp, _vp, _u64, _u32, _int, _vp, _vp, _vp)

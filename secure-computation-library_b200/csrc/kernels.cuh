@@ -364,6 +364,74 @@ k_share61(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
   }
 }
 
+// ================================================================ additiveShare
+// include/scl/ss/additive.h:42-53, N calls on one PRG: n-1 x FF::random (ff.h:72-76: ONE
+// whole keystream block per element, bytes beyond byteSize dropped), last share =
+// secret - sum.  Secret j draws blocks [first_block + j(n-1), first_block + (j+1)(n-1)).
+// Thread = one secret; share (j,i) at out[i*stride_i + j*stride_j].  n >= 1.
+template <class F>
+__global__ void __launch_bounds__(kAesThreads, 1)
+k_additive_share(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0, uint64_t first_block,
+                 const typename F::E* __restrict__ secrets, uint64_t N, uint32_t n,
+                 typename F::E* __restrict__ out, uint64_t stride_i, uint64_t stride_j) {
+  typedef typename F::E E;
+  const uint32_t lanebase = aes_prologue(g_t0);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint32_t draws = n - 1u;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
+    E* dst = out + j * stride_j;
+    E sum = F::zero();
+    if (draws) {
+      const uint64_t ctr0 = first_block + j * draws;
+      PrgGroup grp;
+      uint64_t gid = ctr0 >> 8;
+      prg_group(key, lanebase, ctr0, grp);
+#pragma unroll 1
+      for (uint32_t i = 0; i < draws; ++i) {
+        const uint64_t ctr = ctr0 + i;
+        if ((ctr >> 8) != gid) {
+          gid = ctr >> 8;
+          prg_group(key, lanebase, ctr, grp);
+        }
+        uint32_t o0, o1, o2, o3;
+        prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+        E s;
+        if constexpr (F::BYTES == 16) {
+          s = F127::from_raw(E127{(uint64_t)o0 | ((uint64_t)o1 << 32), (uint64_t)o2 | ((uint64_t)o3 << 32)});
+        } else {
+          s = F61::from_raw((uint64_t)o0 | ((uint64_t)o1 << 32));
+        }
+        dst[(uint64_t)i * stride_i] = s;
+        sum = F::add(sum, s);
+      }
+    }
+    dst[(uint64_t)draws * stride_i] = F::sub(secrets[j], sum);
+  }
+}
+
+// reconstruction of additive sharings = Vector::sum per sharing (vector.h:262-267)
+template <class F>
+__global__ void __launch_bounds__(256)
+k_additive_recover(const typename F::E* __restrict__ in, uint64_t N, uint32_t n, uint64_t stride_i,
+                   uint64_t stride_j, typename F::E* __restrict__ out) {
+  typedef typename F::E E;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
+    const E* src = in + j * stride_j;
+    E sum = F::zero();
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      E v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = src[(uint64_t)(i + k) * stride_i];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum = F::add(sum, v[k]);
+    }
+    for (; i < n; ++i) sum = F::add(sum, src[(uint64_t)i * stride_i]);
+    out[j] = sum;
+  }
+}
+
 // PRG -> coefficient planes, for thresholds without a register-resident
 // instantiation: coeffs[k*N + j], k = 0..t (k = 0 is the secret).
 template <class F>

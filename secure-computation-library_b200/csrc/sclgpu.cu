@@ -926,6 +926,119 @@ static int share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, u
 extern "C" int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, uint32_t n, uint64_t* o, int layout) { return share_coeffs_dev<F61>(c, k, N, t, n, o, layout); }
 extern "C" int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, uint32_t n, void* o, int layout) { return share_coeffs_dev<F127>(c, k, N, t, n, o, layout); }
 
+// ------------------------------------------------------------------ additive sharing
+template <class F>
+static int additive_share_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_secrets, uint64_t N, uint32_t n,
+                             const uint8_t seed[16], uint64_t first_block, typename F::E* d_out, uint64_t si,
+                             uint64_t sj) {
+  if (N == 0) return SCLGPU_OK;
+  RET(aes_opt_in(ctx, k_additive_share<F>));
+  const AesKey key = aes_expand(seed);
+  k_additive_share<F><<<grid_for(ctx, N, kAesThreads, 1), kAesThreads, kAesDynSmem, st>>>(key, ctx->d_t0, first_block,
+                                                                                        d_secrets, N, n, d_out, si, sj);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int additive_share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_t n, const uint8_t seed[16],
+                              uint64_t first_block, void* d_shares, int layout) {
+  typedef typename F::E E;
+  if (!ctx || !seed || ((!d_secrets || !d_shares) && N)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n == 0 || n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "additiveShare needs n >= 1");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  uint64_t si, sj;
+  strides_for(layout, N, n, si, sj);
+  return additive_share_on<F>(ctx, ctx->stream, (const E*)d_secrets, N, n, seed, first_block, (E*)d_shares, si, sj);
+}
+
+// host pipeline as share_host: chunks on two streams, party-major on the device, transposed to SCL's [N][n]
+template <class F>
+static int additive_share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t n, const uint8_t seed[16],
+                               uint64_t first_block, void* shares) {
+  typedef typename F::E E;
+  if (!ctx || !seed || ((!secrets || !shares) && N)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n == 0 || n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "additiveShare needs n >= 1");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  DevBuf dsec[2], dpm[2], dsm[2];
+  const int nbuf = N > chunk ? 2 : 1;
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsec[k].alloc(chunk * sizeof(E)));
+    CK(dpm[k].alloc(chunk * n * sizeof(E)));
+    CK(dsm[k].alloc(chunk * n * sizeof(E)));
+  }
+  const E* hs = reinterpret_cast<const E*>(secrets);
+  E* ho = reinterpret_cast<E*>(shares);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    CK(cudaMemcpyAsync(dsec[k].p, hs + c0, nc * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(additive_share_on<F>(ctx, st, dsec[k].as<E>(), nc, n, seed, first_block + c0 * (uint64_t)(n - 1), dpm[k].as<E>(), nc, 1));
+    RET(transpose_on<E>(ctx, st, dpm[k].as<E>(), n, nc, dsm[k].as<E>()));
+    CK(cudaMemcpyAsync(ho + c0 * n, dsm[k].p, nc * n * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int additive_recover_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n, int layout, void* d_out) {
+  typedef typename F::E E;
+  if (!ctx || (((!d_shares && n) || !d_out) && N)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  uint64_t si, sj;
+  strides_for(layout, N, n, si, sj);
+  k_additive_recover<F><<<grid_for(ctx, N, 256, 8), 256, 0, ctx->stream>>>((const E*)d_shares, N, n, si, sj, (E*)d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int additive_recover_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n, void* out) {
+  typedef typename F::E E;
+  if (!ctx || (((!shares && n) || !out) && N)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n, 1) * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  const int nbuf = N > chunk ? 2 : 1;
+  DevBuf dsh[2], dout[2];
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsh[k].alloc(chunk * n * sizeof(E)));
+    CK(dout[k].alloc(chunk * sizeof(E)));
+  }
+  const E* hs = reinterpret_cast<const E*>(shares);
+  E* ho = reinterpret_cast<E*>(out);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n, nc * n * sizeof(E), cudaMemcpyHostToDevice, st));
+    k_additive_recover<F><<<grid_for(ctx, nc, 256, 8), 256, 0, st>>>(dsh[k].as<E>(), nc, n, 1, n, dout[k].as<E>());
+    CKL();
+    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_additive_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return additive_share_host<F61>(c, s, N, n, seed, fb, o); }
+extern "C" int sclgpu_fp127_additive_share(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return additive_share_host<F127>(c, s, N, n, seed, fb, o); }
+extern "C" int sclgpu_fp61_additive_share_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return additive_share_dev<F61>(c, s, N, n, seed, fb, o, layout); }
+extern "C" int sclgpu_fp127_additive_share_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return additive_share_dev<F127>(c, s, N, n, seed, fb, o, layout); }
+extern "C" int sclgpu_fp61_additive_recover(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, uint64_t* o) { return additive_recover_host<F61>(c, s, N, n, o); }
+extern "C" int sclgpu_fp127_additive_recover(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, void* o) { return additive_recover_host<F127>(c, s, N, n, o); }
+extern "C" int sclgpu_fp61_additive_recover_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, uint64_t* o) { return additive_recover_dev<F61>(c, s, N, n, layout, o); }
+extern "C" int sclgpu_fp127_additive_recover_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, void* o) { return additive_recover_dev<F127>(c, s, N, n, layout, o); }
+
 // ------------------------------------------------------------------ lagrange
 template <class F>
 static int lagrange_host(sclgpu_ctx* ctx, const void* nodes, uint32_t n, const void* x, void* out) {

@@ -15,6 +15,7 @@
 #include "scl/math/fp.h"
 #include "scl/math/matrix.h"
 #include "scl/math/vector.h"
+#include "scl/ss/additive.h"
 #include "scl/ss/shamir.h"
 #include "scl/util/prg.h"
 #include "sclgpu_scl.hpp"
@@ -139,6 +140,35 @@ int main() {
     math::Matrix<Fp127> few(3, 2 * t - 1);
     REQUIRE(throwsLogic([&] { (void)sclgpu::shamirRecoverD(ctx, few, t); },
                         "not enough shares provided to detect errors"));
+  }
+
+  // ---- additiveShare (test/scl/ss/test_additive.cc: shares sum to the secret), both fields, PRG state
+  {
+    for (std::size_t n : {1, 2, 5, 33}) {
+      PRG sprg = PRG::create("secrets");
+      const auto secrets = math::Vector<Fp61>::random(700, sprg);
+      PRG cpu = PRG::create("additive"), gpu = PRG::create("additive");
+      (void)cpu.next(3);
+      (void)gpu.next(3);
+      const auto got = sclgpu::additiveShare(ctx, secrets, n, gpu);
+      for (std::size_t j = 0; j < secrets.size(); ++j) {
+        const auto want = ss::additiveShare(secrets[j], n, cpu);
+        for (std::size_t i = 0; i < n; ++i) REQUIRE(got(j, i) == want[i]);
+        REQUIRE(want.sum() == secrets[j]);
+      }
+      REQUIRE(cpu.next(24) == gpu.next(24));
+      REQUIRE(sclgpu::additiveReconstruct(ctx, got).equals(secrets));
+    }
+    PRG sprg = PRG::create("secrets127");
+    const auto s127 = math::Vector<Fp127>::random(99, sprg);
+    PRG cpu = PRG::create("a127"), gpu = PRG::create("a127");
+    const auto got = sclgpu::additiveShare(ctx, s127, 4, gpu);
+    for (std::size_t j = 0; j < 99; ++j) {
+      const auto want = ss::additiveShare(s127[j], 4, cpu);
+      for (std::size_t i = 0; i < 4; ++i) REQUIRE(got(j, i) == want[i]);
+    }
+    REQUIRE(cpu.next(16) == gpu.next(16));
+    REQUIRE(sclgpu::additiveReconstruct(ctx, got).equals(s127));
   }
 
   // ---- Vector::random, entrywise ops, dot, sum, Beaver combination, mat-vec

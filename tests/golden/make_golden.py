@@ -85,6 +85,16 @@ def main():
         g["shamir"].append({"field": field, "t": t, "n": n, "N": N, "seed": seed, "first_block": first,
                             "secrets": hx(secrets, field), "shares": hx(sh, field), "recover_p": hx(rec, field)})
 
+    # --- additiveShare (additive.h:42-53): n-1 FF::random (one block each) + secret - sum
+    g["additive"] = []
+    for field, n, N, seed, first in [(61, 3, 4, "additive", 0), (61, 1, 2, "additive", 3), (61, 5, 3, "shamir bench", 1 << 20),
+                                     (127, 4, 3, "additive", 0), (127, 2, 2, "a127", 9)]:
+        secrets = from_ints([123 + j for j in range(N)], field)
+        sh = r.additive_share(field, secrets, n, seed, first)
+        g["additive"].append({"field": field, "n": n, "N": N, "seed": seed, "first_block": first,
+                              "secrets": hx(secrets, field), "shares": hx(sh, field),
+                              "recover": hx(r.additive_recover(field, sh), field)})
+
     # sum over all shares of 1024 calls (secrets 123..1146), t=15 n=32, PRG("shamir bench")
     secrets = from_ints([123 + j for j in range(1024)], 61)
     sh = r.shamir_share(61, secrets, 15, 32, "shamir bench", 0)

@@ -387,6 +387,48 @@ def test_full_size_c2_properties(ctx, pkg, orc):
     assert torch.equal(d_sum, d_want)
 
 
+# ------------------------------------------------------------------ additive sharing
+def test_additive_golden(ctx, port, golden):
+    for c in golden["additive"]:
+        f = c["field"]
+        secrets = unhex(port, c["secrets"], f)
+        sh = ctx.additive_share(f, secrets, c["n"], c["seed"], c["first_block"])
+        assert ints(port, sh, f) == [int(h, 16) for h in c["shares"]], c
+        assert ints(port, ctx.additive_recover(f, sh), f) == [int(h, 16) for h in c["recover"]]
+
+
+@pytest.mark.parametrize("field,n,N", [(61, 3, 1 << 16), (61, 1, 100), (61, 2, 4097), (61, 40, 3000), (61, 300, 77),
+                                       (127, 3, 1 << 14), (127, 1, 5), (127, 17, 2222)])
+def test_additive_vs_oracle(ctx, pkg, orc, field, n, N):
+    import torch
+
+    secrets = orc.vector_random(field, "secrets", 0, N)
+    first = (1 << 33) - 1000 if orc.kind == "port" else 4321
+    got = ctx.additive_share(field, secrets, n, "additive", first)
+    want = orc.additive_share(field, secrets, n, "additive", first)
+    assert np.array_equal(got, want)
+    assert np.array_equal(ctx.additive_recover(field, got), secrets)
+    assert np.array_equal(ctx.additive_recover(field, got), orc.additive_recover(field, want))
+    # device-pointer path, party-major planes
+    ctx.use_torch_stream()
+    w = 1 if field == 61 else 2
+    d_sec = torch.from_numpy(secrets.view(np.int64)).cuda()
+    d_pm = torch.empty((n, N, w), dtype=torch.int64, device="cuda")
+    d_out = torch.empty((N, w), dtype=torch.int64, device="cuda")
+    ctx.additive_share_dev(field, d_sec, N, n, "additive", first, d_pm, pkg.binding.PARTY_MAJOR)
+    ctx.additive_recover_dev(field, d_pm, N, n, d_out, pkg.binding.PARTY_MAJOR)
+    torch.cuda.synchronize()
+    assert np.array_equal(np.swapaxes(d_pm.cpu().numpy().view(np.uint64), 0, 1).reshape(want.shape), want)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(secrets.shape), secrets)
+
+
+def test_additive_errors(ctx, pkg, port):
+    with pytest.raises(pkg.InvalidArgument):
+        ctx.additive_share(61, port.from_ints([1], 61), 0, "x")
+    e = port.from_ints([], 61)
+    assert ctx.additive_share(61, e, 3, "x").shape[0] == 0
+
+
 # ------------------------------------------------------------------ both Fp61 share kernels
 @pytest.mark.parametrize("tc", ["3", "2", "1", "0"])
 def test_share_kernel_paths_vs_oracle(tc):

@@ -121,6 +121,29 @@ def test_golden_shamir(port, golden):
     assert golden["survey_sum_1023"] == "44672d90dd13206"
 
 
+def test_golden_additive(port, golden):
+    """additiveShare (additive.h:42-53): vectors recorded from the reference; reconstruction = sum."""
+    for c in golden["additive"]:
+        f = c["field"]
+        secrets = unhex(port, c["secrets"], f)
+        sh = port.additive_share(f, secrets, c["n"], c["seed"], c["first_block"])
+        assert ints(port, sh, f) == [int(h, 16) for h in c["shares"]], c
+        assert ints(port, port.additive_recover(f, sh), f) == [int(h, 16) for h in c["recover"]] == ints(port, secrets, f)
+    # the consumption pattern: share i of secret j is FF::random at block first + j(n-1) + i
+    sec = port.from_ints([5, 6, 7], 61)
+    sh = port.additive_share(61, sec, 4, "pattern", 10)
+    assert np.array_equal(sh[:, :3].reshape(-1), port.ff_random(61, "pattern", 10, 9))
+
+
+def test_port_vs_reference_additive(port, ref):
+    for field in (61, 127):
+        sec = port.vector_random(field, "secrets", 0, 300)
+        for n in (1, 2, 7, 40):
+            a = port.additive_share(field, sec, n, "additive", 77)
+            assert np.array_equal(a, ref.additive_share(field, sec, n, "additive", 77))
+            assert np.array_equal(ref.additive_recover(field, a), sec)
+
+
 def test_golden_recover_p_custom(port, golden):
     for c in golden["recover_p_custom"]:
         f = c["field"]
