@@ -278,7 +278,34 @@ def run_b200(args):
         e2e = {"value": world * N / e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N + 8 * N * n,
                "d2h_bytes_per_step": 8 * N * n + 8 * N, "ms_per_step": 1e3 * e_s, "steps": args.e2e_steps,
                "api": "sclgpu_fp61_shamir_share + sclgpu_fp61_recover_p, pinned host buffers, SCL [N][n] layout"}
-        for a in (h_sec, h_sh, h_out):
+        for a in (h_sh,):
+            ctx.host_free(a.view(np.uint8))
+        # the same round trip through the per-party packet entry points (Serializer<Vector<FF>> wire
+        # layout, what a dealer sends / a reconstructing party receives): no [N][n] matrix, no transposition
+        pk_bytes = int(ctx.lib.sclgpu_packet_bytes(8, N))
+        h_pk = [ctx.host_alloc(pk_bytes) for _ in range(n)]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in h_pk])
+
+        def pk_step():
+            ctx._check(ctx.lib.sclgpu_fp61_shamir_share_packets(ctx._ctx, p(h_sec), N, t, n, seed, first_block, ptrs))
+            ctx._check(ctx.lib.sclgpu_fp61_recover_p_packets(ctx._ctx, ptrs, N, n, None, None, p(h_out)))
+
+        h_out[:] = 0
+        pk_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            pk_step()
+        torch.cuda.synchronize()
+        pk_s = (time.perf_counter() - t0) / args.e2e_steps
+        tp = torch.tensor([pk_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        pk_s = float(tp.item())
+        verified = verified and bool(np.array_equal(h_out, h_sec))
+        e2e["packets"] = {"value": world * N / pk_s, "unit": UNIT, "ms_per_step": 1e3 * pk_s,
+                          "api": "sclgpu_fp61_shamir_share_packets + sclgpu_fp61_recover_p_packets (n pinned packet buffers)"}
+        for a in [h_sec, h_out] + h_pk:
             ctx.host_free(a.view(np.uint8))
 
     if rank == 0:

@@ -141,6 +141,29 @@ int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const uint64_t* d_coeff
 int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N,
                                          uint32_t t, uint32_t n, void* d_shares, int layout);
 
+/* ---- per-party packets: Serializer<math::Vector<FF>> wire layout ------------------
+ * What a dealer sends to party i after sharing N secrets is a net::Packet holding the
+ * math::Vector of party i's N shares, i.e. Serializer<Vector<FF>>::write
+ * (vector.h:596-629 -> serializer.h:160-176): a little-endian u32 element count
+ * (StlVecSizeType, serializer.h:111) followed by N x FF::write bytes (ff.h:355-391).
+ * shamir_share_packets: as shamir_share, but the output is n host buffers,
+ *   packets[i] of sclgpu_packet_bytes(byteSize, N) bytes = party i's serialized
+ *   Vector (no [N][n] matrix, no transposition).  N < 2^32 (Packet::SizeType).
+ * recover_p_packets: shamirRecoverP (alphas/x as in recover_p) from the n packets a
+ *   reconstructing party received; SCLGPU_EINVAL ("Vec sizes mismatch") if a
+ *   packet's element count differs from N. */
+uint64_t sclgpu_packet_bytes(uint32_t element_bytes, uint64_t n_elements);
+int sclgpu_fp61_shamir_share_packets(sclgpu_ctx* ctx, const uint64_t* secrets, uint64_t N, uint32_t t,
+                                     uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                     uint8_t* const* packets);
+int sclgpu_fp127_shamir_share_packets(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t t,
+                                      uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                      uint8_t* const* packets);
+int sclgpu_fp61_recover_p_packets(sclgpu_ctx* ctx, const uint8_t* const* packets, uint64_t N, uint32_t n,
+                                  const uint64_t* alphas, const uint64_t* x, uint64_t* out);
+int sclgpu_fp127_recover_p_packets(sclgpu_ctx* ctx, const uint8_t* const* packets, uint64_t N, uint32_t n,
+                                   const void* alphas, const void* x, void* out);
+
 /* ---- ss::additiveShare (include/scl/ss/additive.h:42-53), called N times on one PRG
  * Secret j: n-1 shares drawn with FF::random (ff.h:72-76: ONE whole keystream block
  * per share, bytes beyond byteSize dropped) from blocks

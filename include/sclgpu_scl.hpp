@@ -15,6 +15,9 @@
 //     -> sclgpu::shamirRecoverP(ctx, shares[, alphas, x])   : Vector (N)
 //   scl::ss::shamirRecoverD(shares, t)                   shamir.h:117-155
 //     -> sclgpu::shamirRecoverD(ctx, shares, t[, flags])    : Vector (N); throws as SCL unless flags != nullptr
+//   packet.write(Vector of party i's shares)             net/packet.h:145-149, vector.h:596-629
+//     -> sclgpu::shamirSharePackets(ctx, secrets, t, n, prg) : n net::Packet, ready for channel->send
+//        sclgpu::shamirRecoverP(ctx, packets)                : Vector (N) from the n packets received
 //   scl::ss::additiveShare(secret, n, prg)               additive.h:42-53
 //     -> sclgpu::additiveShare(ctx, secrets, n, prg)        : Matrix (N x n); sclgpu::additiveReconstruct = row sums
 //   scl::math::Vector<FF>::random(n, prg)                vector.h:508-519
@@ -36,6 +39,7 @@
 #include "scl/math/fp.h"
 #include "scl/math/matrix.h"
 #include "scl/math/vector.h"
+#include "scl/net/packet.h"
 #include "scl/util/prg.h"
 #include "sclgpu.h"
 
@@ -64,6 +68,8 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto random = &sclgpu_##SUF##_random;                                                    \
     static constexpr auto share = &sclgpu_##SUF##_shamir_share;                                               \
     static constexpr auto recover_p = &sclgpu_##SUF##_recover_p;                                              \
+    static constexpr auto share_packets = &sclgpu_##SUF##_shamir_share_packets;                               \
+    static constexpr auto recover_p_packets = &sclgpu_##SUF##_recover_p_packets;                              \
     static constexpr auto additive_share = &sclgpu_##SUF##_additive_share;                                    \
     static constexpr auto additive_recover = &sclgpu_##SUF##_additive_recover;                                \
     static constexpr auto recover_d = &sclgpu_##SUF##_recover_d;                                              \
@@ -156,6 +162,47 @@ scl::math::Matrix<FF> shamirSecretShare(Context& ctx, const scl::math::Vector<FF
                      (std::uint32_t)n, seed.data(), (std::uint64_t)ctr, detail::raw<FF>(&shares(0, 0))));
   ctr += (long)(N * detail::shareBlocks(A::BYTES, t));
   return shares;
+}
+
+// ---- shamirSecretShare straight into per-party packets: packets[i] holds what
+// `Packet p; p.write(Vector<FF>(shares of party i))` holds (u32 count + FF::write bytes), so
+// `co_await channel_i->send(packets[i])` is the next line of the dealer's protocol.
+template <class FF>
+std::vector<scl::net::Packet> shamirSharePackets(Context& ctx, const scl::math::Vector<FF>& secrets, std::size_t t,
+                                                 std::size_t n, scl::util::PRG& prg) {
+  using A = detail::Abi<FF>;
+  const std::size_t N = secrets.size();
+  const std::size_t bytes = (std::size_t)sclgpu_packet_bytes((std::uint32_t)A::BYTES, N);
+  std::vector<scl::net::Packet> packets;
+  packets.reserve(n);
+  std::vector<std::uint8_t*> bufs(n);
+  for (std::size_t i = 0; i < n; ++i) {
+    packets.emplace_back(bytes);
+    bufs[i] = packets.back().get();
+  }
+  long& ctr = detail::prgCounter(prg);
+  const auto seed = prg.Seed();
+  ctx.check(A::share_packets(ctx.get(), detail::raw<FF>(secrets.toStlVector().data()), N, (std::uint32_t)t,
+                             (std::uint32_t)n, seed.data(), (std::uint64_t)ctr, bufs.data()));
+  ctr += (long)(N * detail::shareBlocks(A::BYTES, t));
+  for (auto& p : packets) p.setWritePtr((std::ptrdiff_t)bytes);
+  return packets;
+}
+
+// ---- shamirRecoverP(shares) for all N secrets from the n packets received (packet i = the Vector
+// party i sent); the packets' read pointers are not moved.
+template <class FF>
+scl::math::Vector<FF> shamirRecoverP(Context& ctx, const std::vector<scl::net::Packet>& packets) {
+  using A = detail::Abi<FF>;
+  if (packets.empty()) return scl::math::Vector<FF>();
+  std::uint32_t count = 0;
+  std::memcpy(&count, packets[0].get(), sizeof(count));
+  std::vector<const std::uint8_t*> bufs(packets.size());
+  for (std::size_t i = 0; i < packets.size(); ++i) bufs[i] = packets[i].get();
+  std::vector<FF> out(count);
+  ctx.check(A::recover_p_packets(ctx.get(), bufs.data(), count, (std::uint32_t)packets.size(), nullptr, nullptr,
+                                 detail::raw<FF>(out.data())));
+  return scl::math::Vector<FF>(std::move(out));
 }
 
 // ---- additiveShare on every element of `secrets`, additive.h:42-53: n-1 FF::random draws per

@@ -224,6 +224,27 @@ class Context:
     def shamir_share_coeffs_dev(self, field: int, coeffs, N: int, t: int, n: int, shares, layout: int = B.PARTY_MAJOR):
         self._check(self._f(field, "shamir_share_coeffs_dev")(self._ctx, _dp(coeffs), N, t, n, _dp(shares), layout))
 
+    # ------------------------------------------------------------ per-party packets
+    def shamir_share_packets(self, field: int, secrets, t: int, n: int, seed, first_block: int = 0) -> list:
+        """n uint8 arrays: packet i = Serializer<Vector<FF>>::write of party i's shares (u32 count + elements)."""
+        secrets = _c(secrets)
+        N = _nelem(secrets, field)
+        nbytes = int(self.lib.sclgpu_packet_bytes(8 if field == 61 else 16, N))
+        packets = [np.zeros(nbytes, dtype=np.uint8) for _ in range(n)]
+        ptrs = (C.c_void_p * max(n, 1))(*[p.ctypes.data for p in packets])
+        self._check(self._f(field, "shamir_share_packets")(self._ctx, _p(secrets), N, t, n, seed16(seed), first_block, ptrs))
+        return packets
+
+    def recover_p_packets(self, field: int, packets, N: int, alphas=None, x: int | None = None) -> np.ndarray:
+        packets = [np.ascontiguousarray(p, dtype=np.uint8) for p in packets]
+        n = len(packets)
+        ptrs = (C.c_void_p * max(n, 1))(*[p.ctypes.data for p in packets])
+        out = empty(field, N)
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], field)
+        self._check(self._f(field, "recover_p_packets")(self._ctx, ptrs, N, n, _p(A), _p(X), _p(out)))
+        return out
+
     # ------------------------------------------------------------ additive sharing
     def additive_share(self, field: int, secrets, n: int, seed, first_block: int = 0) -> np.ndarray:
         """ss::additiveShare (additive.h:42-53) of every secret; consumes N*(n-1) blocks."""

@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_shamir_share", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_shamir_share_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _int)
         _sig(lib, f"sclgpu_{f}_shamir_share_coeffs_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _int)
+        _sig(lib, f"sclgpu_{f}_shamir_share_packets", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
+        _sig(lib, f"sclgpu_{f}_recover_p_packets", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp)
         _sig(lib, f"sclgpu_{f}_additive_share", _int, _vp, _vp, _u64, _u32, _vp, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_additive_share_dev", _int, _vp, _vp, _u64, _u32, _vp, _u64, _vp, _int)
         _sig(lib, f"sclgpu_{f}_additive_recover", _int, _vp, _vp, _u64, _u32, _vp)
@@ -99,6 +101,7 @@ def load() -> C.CDLL:
              _vp, _vp, _vp, C.POINTER(_u64))
         _sig(lib, f"sclgpu_{f}_vandermonde", _int, _vp, _u32, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_transpose_dev", _int, _vp, _vp, _u64, _u64, _vp)
+    _sig(lib, "sclgpu_packet_bytes", _u64, _u32, _u64)
     _sig(lib, "sclgpu_pipe_microbench", _int, _vp, _int, _u32, C.POINTER(C.c_double))
     _LIB = lib
     return lib

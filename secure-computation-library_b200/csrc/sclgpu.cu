@@ -926,6 +926,55 @@ static int share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, u
 extern "C" int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, uint32_t n, uint64_t* o, int layout) { return share_coeffs_dev<F61>(c, k, N, t, n, o, layout); }
 extern "C" int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, uint32_t n, void* o, int layout) { return share_coeffs_dev<F127>(c, k, N, t, n, o, layout); }
 
+// ------------------------------------------------------------------ per-party packets
+// Serializer<math::Vector<FF>>::write (vector.h:596-629 -> serializer.h:160-176): a u32 element count
+// (StlVecSizeType, serializer.h:111) followed by the elements' FF::write bytes (ff.h:355-391).  Party i's
+// packet is plane i of the device-native layout behind a 4-byte header, so no transposition is needed.
+static constexpr uint64_t kPacketHeader = 4;
+
+template <class F>
+static int share_packets_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t t, uint32_t n,
+                              const uint8_t seed[16], uint64_t first_block, uint8_t* const* packets) {
+  typedef typename F::E E;
+  if (!ctx || !seed || (n && !packets) || (!secrets && N)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n too large");
+  if (N > 0xFFFFFFFFull) return fail(ctx, SCLGPU_EINVAL, "a packet holds at most 2^32 - 1 elements");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t count = (uint32_t)N;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!packets[i]) return fail(ctx, SCLGPU_EINVAL, "null packet buffer");
+    std::memcpy(packets[i], &count, kPacketHeader);
+  }
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  DevBuf dsec[2], dpm[2];
+  const int nbuf = N > chunk ? 2 : 1;
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsec[k].alloc(chunk * sizeof(E)));
+    CK(dpm[k].alloc(chunk * n * sizeof(E)));
+  }
+  const E* hs = reinterpret_cast<const E*>(secrets);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    CK(cudaMemcpyAsync(dsec[k].p, hs + c0, nc * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(share_strided_on<F>(ctx, st, dsec[k].as<E>(), nc, t, n, seed, first_block + c0 * B, dpm[k].as<E>(), nc, 1));
+    for (uint32_t i = 0; i < n; ++i)
+      CK(cudaMemcpyAsync(packets[i] + kPacketHeader + c0 * sizeof(E), dpm[k].as<E>() + (uint64_t)i * nc, nc * sizeof(E),
+                         cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int recover_p_packets_host(sclgpu_ctx* ctx, const uint8_t* const* packets, uint64_t N, uint32_t n,
+                                  const void* alphas, const void* x, void* out);
+
 // ------------------------------------------------------------------ additive sharing
 template <class F>
 static int additive_share_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_secrets, uint64_t N, uint32_t n,
@@ -1094,10 +1143,13 @@ static int recover_p_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   RET(recover_p_basis<F>(ctx, ctx->pipe[0], n, alphas, x, &d_basis));
   uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n, 1) * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
+  chunk &= ~1ull;  // even chunks: 128-bit loads in the plane kernel
+  if (chunk == 0) chunk = N;
   const int nbuf = N > chunk ? 2 : 1;
-  DevBuf dsh[2], dout[2];
+  DevBuf dsh[2], dpm[2], dout[2];
   for (int k = 0; k < nbuf; ++k) {
     CK(dsh[k].alloc(chunk * n * sizeof(E)));
+    CK(dpm[k].alloc(chunk * n * sizeof(E)));
     CK(dout[k].alloc(chunk * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
@@ -1108,13 +1160,63 @@ static int recover_p_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
     if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n, nc * n * sizeof(E), cudaMemcpyHostToDevice, st));
-    RET(recover_p_on<F>(ctx, st, dsh[k].as<E>(), nc, n, 1, n, d_basis, dout[k].as<E>()));
+    // SCL's [N][n] -> party-major planes on the device (coalesced on both sides), then the plane kernel
+    RET(transpose_on<E>(ctx, st, dsh[k].as<E>(), nc, n, dpm[k].as<E>()));
+    RET(recover_p_on<F>(ctx, st, dpm[k].as<E>(), nc, n, nc, 1, d_basis, dout[k].as<E>()));
     CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
   return SCLGPU_OK;
 }
+// shamirRecoverP from the n packets a reconstructing party received (packet i = Vector of party i's
+// shares of all N secrets): the planes go to the device as they are, no transposition.
+template <class F>
+static int recover_p_packets_host(sclgpu_ctx* ctx, const uint8_t* const* packets, uint64_t N, uint32_t n,
+                                  const void* alphas, const void* x, void* out) {
+  typedef typename F::E E;
+  if (!ctx || (n && !packets) || (!out && N)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (N > 0xFFFFFFFFull) return fail(ctx, SCLGPU_EINVAL, "a packet holds at most 2^32 - 1 elements");
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!packets[i]) return fail(ctx, SCLGPU_EINVAL, "null packet buffer");
+    uint32_t count;
+    std::memcpy(&count, packets[i], kPacketHeader);
+    if (count != (uint32_t)N) return fail(ctx, SCLGPU_EINVAL, "Vec sizes mismatch");  // vector.h:483
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  const E* d_basis = nullptr;
+  RET(recover_p_basis<F>(ctx, ctx->pipe[0], n, alphas, x, &d_basis));
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n, 1) * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk)) & ~1ull;  // even: 128-bit loads in the plane kernel
+  if (chunk == 0) chunk = N;
+  const int nbuf = N > chunk ? 2 : 1;
+  DevBuf dsh[2], dout[2];
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsh[k].alloc(chunk * std::max<uint64_t>(n, 1) * sizeof(E)));
+    CK(dout[k].alloc(chunk * sizeof(E)));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  E* ho = reinterpret_cast<E*>(out);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    for (uint32_t i = 0; i < n; ++i)
+      CK(cudaMemcpyAsync(dsh[k].as<E>() + (uint64_t)i * nc, packets[i] + kPacketHeader + c0 * sizeof(E), nc * sizeof(E),
+                         cudaMemcpyHostToDevice, st));
+    RET(recover_p_on<F>(ctx, st, dsh[k].as<E>(), nc, n, nc, 1, d_basis, dout[k].as<E>()));
+    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_shamir_share_packets(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return share_packets_host<F61>(c, s, N, t, n, seed, fb, p); }
+extern "C" int sclgpu_fp127_shamir_share_packets(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return share_packets_host<F127>(c, s, N, t, n, seed, fb, p); }
+extern "C" int sclgpu_fp61_recover_p_packets(sclgpu_ctx* c, const uint8_t* const* p, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_packets_host<F61>(c, p, N, n, a, x, o); }
+extern "C" int sclgpu_fp127_recover_p_packets(sclgpu_ctx* c, const uint8_t* const* p, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return recover_p_packets_host<F127>(c, p, N, n, a, x, o); }
+extern "C" uint64_t sclgpu_packet_bytes(uint32_t element_bytes, uint64_t n_elements) { return kPacketHeader + (uint64_t)element_bytes * n_elements; }
 extern "C" int sclgpu_fp61_recover_p(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_host<F61>(c, s, N, n, a, x, o); }
 extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return recover_p_host<F127>(c, s, N, n, a, x, o); }
 extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }

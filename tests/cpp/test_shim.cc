@@ -142,6 +142,29 @@ int main() {
                         "not enough shares provided to detect errors"));
   }
 
+  // ---- per-party packets: what the dealer would build with Packet::write(Vector) on the CPU
+  {
+    const std::size_t N = 2500, t = 3, n = 7;
+    PRG sprg = PRG::create("secrets");
+    const auto secrets = math::Vector<Fp61>::random(N, sprg);
+    PRG cpu = PRG::create("packets"), gpu = PRG::create("packets");
+    auto packets = sclgpu::shamirSharePackets(ctx, secrets, t, n, gpu);
+    REQUIRE(packets.size() == n);
+    std::vector<std::vector<Fp61>> cols(n, std::vector<Fp61>(N));
+    for (std::size_t j = 0; j < N; ++j) {
+      const auto sh = ss::shamirSecretShare(secrets[j], t, n, cpu);
+      for (std::size_t i = 0; i < n; ++i) cols[i][j] = sh[i];
+    }
+    REQUIRE(cpu.next(16) == gpu.next(16));
+    for (std::size_t i = 0; i < n; ++i) {
+      scl::net::Packet want;
+      want.write(math::Vector<Fp61>(cols[i]));                 // SCL's own serializer
+      REQUIRE(want == packets[i]);                             // byte-identical packet
+    }
+    REQUIRE(sclgpu::shamirRecoverP<Fp61>(ctx, packets).equals(secrets));
+    REQUIRE(packets[2].read<math::Vector<Fp61>>().equals(math::Vector<Fp61>(cols[2])));  // and SCL can read it
+  }
+
   // ---- additiveShare (test/scl/ss/test_additive.cc: shares sum to the secret), both fields, PRG state
   {
     for (std::size_t n : {1, 2, 5, 33}) {

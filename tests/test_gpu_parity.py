@@ -387,6 +387,30 @@ def test_full_size_c2_properties(ctx, pkg, orc):
     assert torch.equal(d_sum, d_want)
 
 
+# ------------------------------------------------------------------ per-party packets
+@pytest.mark.parametrize("field,t,n,N", [(61, 15, 32, 5000), (61, 2, 5, 1), (61, 3, 7, 4097), (127, 7, 16, 3001),
+                                         (61, 20, 40, 300), (61, 1, 3, (1 << 21) + 7)])
+def test_share_packets_wire_layout(ctx, pkg, orc, field, t, n, N):
+    """packet i == Serializer<Vector<FF>>::write(column i of SCL's share matrix): u32 count, then
+    FF::write bytes (vector.h:596-629, serializer.h:160-176); recover_p_packets inverts it."""
+    import struct
+
+    secrets = orc.vector_random(field, "secrets", 0, N)
+    want = orc.shamir_share(field, secrets, t, n, "packets", 9)          # [N][n](,2)
+    packets = ctx.shamir_share_packets(field, secrets, t, n, "packets", 9)
+    assert len(packets) == n
+    for i, p in enumerate(packets):
+        col = np.ascontiguousarray(want[:, i])
+        assert bytes(p[:4]) == struct.pack("<I", N)
+        assert p[4:].tobytes() == col.tobytes(), (field, i)
+    rec = ctx.recover_p_packets(field, packets, N)
+    assert np.array_equal(rec, secrets)
+    bad = [p.copy() for p in packets]
+    bad[n - 1][:4] = np.frombuffer(struct.pack("<I", N + 1), dtype=np.uint8)
+    with pytest.raises(pkg.InvalidArgument, match="Vec sizes mismatch"):
+        ctx.recover_p_packets(field, bad, N)
+
+
 # ------------------------------------------------------------------ additive sharing (SURVEY 8f.2)
 def test_additive_golden(ctx, port, golden):
     for c in golden["additive"]:
