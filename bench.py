@@ -246,10 +246,20 @@ def run_b200(args):
     # ---- e2e: host buffers through the reference-facing C ABI
     e2e = None
     if not args.no_e2e:
+        # host footprint guard: every rank pins 8*N*(n+2) bytes; keep the sum below half of MemAvailable
+        N_full, lg_e = N, args.log2_secrets
+        try:
+            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+        except (OSError, StopIteration):
+            avail = 1 << 40
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        while lg_e > 16 and local_world * 8 * (1 << lg_e) * (n + 2) > avail // 2:
+            lg_e -= 1
+        N = 1 << lg_e
         h_sec = ctx.host_alloc(8 * N).view(np.uint64)
         h_sh = ctx.host_alloc(8 * N * n).view(np.uint64)
         h_out = ctx.host_alloc(8 * N).view(np.uint64)
-        h_sec[:] = d_sec.cpu().numpy().view(np.uint64)
+        h_sec[:] = d_sec[:N].cpu().numpy().view(np.uint64)
         import ctypes as C
 
         def p(a):
@@ -277,6 +287,7 @@ def run_b200(args):
         verified = verified and bool(np.array_equal(h_out, h_sec))
         e2e = {"value": world * N / e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N + 8 * N * n,
                "d2h_bytes_per_step": 8 * N * n + 8 * N, "ms_per_step": 1e3 * e_s, "steps": args.e2e_steps,
+               "secrets_per_gpu": N,
                "api": "sclgpu_fp61_shamir_share + sclgpu_fp61_recover_p, pinned host buffers, SCL [N][n] layout"}
         for a in (h_sh,):
             ctx.host_free(a.view(np.uint8))
@@ -307,6 +318,7 @@ def run_b200(args):
                           "api": "sclgpu_fp61_shamir_share_packets + sclgpu_fp61_recover_p_packets (n pinned packet buffers)"}
         for a in [h_sec, h_out] + h_pk:
             ctx.host_free(a.view(np.uint8))
+        N = N_full
 
     if rank == 0:
         peaks = {}
