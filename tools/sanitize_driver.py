@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Small workload that touches every hot kernel once or twice (for compute-sanitizer)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import __graft_entry__ as entry
+
+pkg = entry.load_package()
+o = entry.load_oracle(); port = o.PortOracle()
+ctx = pkg.Context(0)
+for field, t, n, N in [(61, 15, 32, 700), (61, 2, 5, 130), (127, 7, 16, 300), (61, 16, 40, 64)]:
+    sec = port.vector_random(field, "secrets", 0, N)
+    sh = ctx.shamir_share(field, sec, t, n, "shamir bench", 5)
+    assert np.array_equal(sh, port.shamir_share(field, sec, t, n, "shamir bench", 5))
+    assert np.array_equal(ctx.recover_p(field, sh), sec)
+    if n >= 2 * t + 1:
+        out, err, nd = ctx.recover_d(field, sh, t)
+        assert nd == 0 and np.array_equal(out, sec)
+    pk = ctx.shamir_share_packets(field, sec, t, n, "shamir bench", 5)
+    assert np.array_equal(ctx.recover_p_packets(field, pk, N), sec)
+    ad = ctx.additive_share(field, sec, 4, "additive", 1)
+    assert np.array_equal(ctx.additive_recover(field, ad), sec)
+assert np.array_equal(ctx.prg_expand("k", 250, 5000), port.prg_next("k", 250, 5000))
+assert np.array_equal(ctx.vector_random(61, "v", 3, 1001), port.vector_random(61, "v", 3, 1001))
+A = port.vector_random(61, "mat A", 0, 64 * 512).reshape(64, 512); x = port.vector_random(61, "vec x", 0, 512)
+assert np.array_equal(ctx.matvec(61, A, x), port.matvec(61, A, x))
+a = port.vector_random(61, "a", 0, 1001); b = port.vector_random(61, "b", 0, 1001)
+assert np.array_equal(ctx.beaver(61, a, b, a, b, a), port.beaver(61, a, b, a, b, a))
+ctx.close()
+print("SANITIZE_DRIVER_OK")
