@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-staged"
 # every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/ncu_launches_${TAG}.log 2>&1

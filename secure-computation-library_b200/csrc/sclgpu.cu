@@ -454,6 +454,20 @@ template <class F>
 static int share_coeffs_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_coeffs, uint64_t N,
                            uint32_t t, uint32_t n, typename F::E* d_out, uint64_t si, uint64_t sj) {
   if (N == 0 || n == 0) return SCLGPU_OK;
+  const bool fits = F::BYTES == 8 ? (t <= kTcMaxT && n <= kTcMaxParties) : (t <= kTcMaxT127 && n <= kTcMaxParties127);
+  if (fits && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr) {
+    const void* d_bmat = nullptr;
+    RET(share_tc_bmat<F>(ctx, st, t, n, &d_bmat));
+    ctx->launches++;
+    cudaError_t e;
+    if constexpr (F::BYTES == 8) {
+      e = share61_coeffs_tc_launch(st, ctx->sm_count, d_bmat, d_coeffs, N, t, n, d_out, si, sj);
+    } else {
+      e = share127_coeffs_tc_launch(st, ctx->sm_count, d_bmat, d_coeffs, N, t, n, d_out, si, sj);
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
+    return SCLGPU_OK;
+  }
   k_share_coeffs<F><<<grid_for(ctx, N, 256, 8), 256, 0, st>>>(d_coeffs, N, t, n, d_out, si, sj);
   CKL();
   return SCLGPU_OK;

@@ -294,7 +294,10 @@ __device__ __forceinline__ E127 tc_combine127(const uint32_t* v) {
 // GROUPS x 128 threads; NBUF accumulators of PCOLS columns (PCOLS / F::BYTES parties per MMA pass) per
 // group.  F = F61: K = 8(t+1) bytes, t <= 15, n <= 32.  F = F127: K = 16(t+1) bytes, t <= 7, n <= 16;
 // coefficient k is keystream block k of the secret's draw (vector.h:508-519 with 16-byte elements).
-template <class F, int GROUPS, int NBUF, int PCOLS>
+// COEFFS = false: coefficients drawn from the PRG (shamirSecretShare).  COEFFS = true: coefficient planes
+// supplied by the caller (Polynomial::create + evaluate, poly.h:56-64,179-198): `secrets` is then the
+// [t+1][N] array (coefficient k of secret j at k*N + j), no AES tables, and the kernel is HBM-bound.
+template <class F, int GROUPS, int NBUF, int PCOLS, bool COEFFS>
 __global__ void __launch_bounds__(128 * GROUPS, 1)
 k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
             const uint4* __restrict__ g_bmat, uint64_t first_block, const typename F::E* __restrict__ secrets,
@@ -310,13 +313,13 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
   static_assert(PCOLS == 32 || PCOLS == 64, "pass width");
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const uint32_t dyn = smem_u32(dyn_smem);
-  const uint32_t tbase = aes_table_base(dyn_smem);
-  const uint32_t b_base = tbase + kAesTableBytes;
+  const uint32_t tbase = COEFFS ? ((dyn + 1023u) & ~1023u) : aes_table_base(dyn_smem);
+  const uint32_t b_base = COEFFS ? tbase : tbase + kAesTableBytes;
   const uint32_t ctl = b_base + kTcBmatBytes;             // 2*GROUPS mbarriers + the TMEM base address
-  if (ctl + 128u > dyn + kTcmDynSmem) __trap();
+  if (ctl + 128u > dyn + (COEFFS ? kTcCoeffDynSmem : kTcmDynSmem)) __trap();
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
-  aes_fill_tables(tbase, g_t0);
+  if (!COEFFS) aes_fill_tables(tbase, g_t0);
   for (uint32_t e = tid; e < kTcBmatBytes / 16; e += kThreads) {
     const uint4 w = __ldg(g_bmat + e);
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
@@ -375,6 +378,31 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
     const uint64_t j = tile * 128u + gt;
     const bool valid = j < N;
     const uint64_t jj = valid ? j : N - 1;                 // tail lanes recompute the last secret (never stored)
+    const uint32_t a_lane = a_tm + lane_off;
+    if constexpr (COEFFS) {
+      // (t+1) coalesced plane loads, all requested before the first is consumed, then 16 bytes per tcgen05.st
+      constexpr uint32_t kMaxC = 128u / EB;
+      E c[kMaxC];
+#pragma unroll
+      for (uint32_t k = 0; k < kMaxC; ++k) c[k] = (k <= t) ? secrets[(uint64_t)k * N + jj] : F::zero();
+      if constexpr (EB == 8) {
+#pragma unroll
+        for (uint32_t q = 0; q < kMaxC / 2; ++q)
+          if (2 * q <= t)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * q),
+                         "r"((uint32_t)c[2 * q]), "r"((uint32_t)(c[2 * q] >> 32)), "r"((uint32_t)c[2 * q + 1]),
+                         "r"((uint32_t)(c[2 * q + 1] >> 32))
+                         : "memory");
+      } else {
+#pragma unroll
+        for (uint32_t q = 0; q < kMaxC; ++q)
+          if (q <= t)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * q),
+                         "r"((uint32_t)c[q].lo), "r"((uint32_t)(c[q].lo >> 32)), "r"((uint32_t)c[q].hi),
+                         "r"((uint32_t)(c[q].hi >> 32))
+                         : "memory");
+      }
+    } else {
     uint32_t s0, s1, s2 = 0, s3 = 0;                       // the secret = coefficient 0 (shamir.h:56-57)
     if constexpr (EB == 8) {
       const uint64_t sec = secrets[jj];
@@ -388,7 +416,6 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
       s3 = (uint32_t)(sec.hi >> 32);
     }
     const uint64_t ctr0 = first_block + jj * nblk;
-    const uint32_t a_lane = a_tm + lane_off;
     if (t == 0 || EB == 16) {
       // Fp61, t = 0: one block is consumed, none of it is used.  Fp127: block 0 is slot 0 of the draw,
       // consumed and replaced by the secret.
@@ -416,6 +443,7 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
         // keystream block b = K bytes [16b, 16b+16) of the row = TMEM columns 4b..4b+3 of this lane
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
       }
+    }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -662,8 +690,8 @@ cudaError_t recover_d127_tc_launch(cudaStream_t st, int sm_count, const void* d_
 cudaError_t share_tc_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
 #define X(V, G, NB, PC)                                                                                                                       \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
   SCLGPU_TCM_VARIANTS(X)
 #undef X
   return e;
@@ -684,7 +712,7 @@ cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesK
   bool done = false;
 #define X(V, G, NB, PC)                                                                                               \
   if (variant == V) {                                                                                                 \
-    k_share_tcm<F61, G, NB, PC><<<grid, 128 * G, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
+    k_share_tcm<F61, G, NB, PC, false><<<grid, 128 * G, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
                                                                   d_out, stride_i, stride_j);                         \
     done = true;                                                                                                      \
   }
@@ -700,11 +728,35 @@ cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const Aes
                                uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j) {
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
   if (variant == 2) {
-    k_share_tcm<F127, 4, 1, 64><<<grid, 512, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    k_share_tcm<F127, 4, 1, 64, false><<<grid, 512, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
   } else {
-    k_share_tcm<F127, 5, 1, 64><<<grid, 640, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    k_share_tcm<F127, 5, 1, 64, false><<<grid, 640, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
   }
   return cudaGetLastError();
+}
+
+// Polynomial evaluation from caller-supplied coefficient planes on the tensor cores (no PRG)
+template <class F>
+static cudaError_t share_coeffs_tc_launch_t(cudaStream_t st, int sm_count, const void* d_bmat, const typename F::E* d_coeffs,
+                                            uint64_t N, uint32_t t, uint32_t n, typename F::E* d_out, uint64_t stride_i,
+                                            uint64_t stride_j) {
+  auto kern = k_share_tcm<F, 5, 1, 64, true>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcCoeffDynSmem);
+  if (e != cudaSuccess) return e;
+  const uint64_t tiles = (N + 127) / 128;
+  const int grid = (int)std::min<uint64_t>((tiles + 4) / 5, (uint64_t)sm_count);
+  AesKey unused{};
+  kern<<<grid, 640, kTcCoeffDynSmem, st>>>(unused, nullptr, reinterpret_cast<const uint4*>(d_bmat), 0, d_coeffs, N, t, n, d_out,
+                                          stride_i, stride_j);
+  return cudaGetLastError();
+}
+cudaError_t share61_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const uint64_t* d_coeffs, uint64_t N,
+                                     uint32_t t, uint32_t n, uint64_t* d_out, uint64_t stride_i, uint64_t stride_j) {
+  return share_coeffs_tc_launch_t<F61>(st, sm_count, d_bmat, d_coeffs, N, t, n, d_out, stride_i, stride_j);
+}
+cudaError_t share127_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_coeffs, uint64_t N,
+                                      uint32_t t, uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j) {
+  return share_coeffs_tc_launch_t<F127>(st, sm_count, d_bmat, d_coeffs, N, t, n, d_out, stride_i, stride_j);
 }
 
 }  // namespace sclgpu

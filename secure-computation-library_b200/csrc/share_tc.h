@@ -18,6 +18,8 @@ static constexpr uint32_t kTcDynSmem = 232448;        // 227 KiB: A tiles | AES 
 // what is addressed leaves ~4 KiB of the SM's shared memory for a small co-resident CTA (e.g. the HBM-bound
 // reconstruction kernel of another stream).
 static constexpr uint32_t kTcmDynSmem = (65536u - 1024u) + 131072u + kTcBmatBytes + 128u;
+// coefficient-plane variant: B limbs + barriers only; > half an SM so that one CTA owns the tensor memory
+static constexpr uint32_t kTcCoeffDynSmem = 120u * 1024u;
 static constexpr uint32_t kTcMaxT = 15, kTcMaxParties = 32;        // Fp61:  K = 8(t+1)  <= 128 bytes, 8 limbs per party
 static constexpr uint32_t kTcMaxT127 = 7, kTcMaxParties127 = 16;   // Fp127: K = 16(t+1) <= 128 bytes, 16 limbs per party
 
@@ -51,5 +53,10 @@ cudaError_t recover_d61_tc_launch(cudaStream_t st, int sm_count, const void* d_b
 cudaError_t recover_d127_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_in, uint64_t N,
                                    uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks, E127* d_out, uint8_t* d_err,
                                    unsigned long long* d_count);
+
+cudaError_t share61_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const uint64_t* d_coeffs, uint64_t N,
+                                     uint32_t t, uint32_t n, uint64_t* d_out, uint64_t stride_i, uint64_t stride_j);
+cudaError_t share127_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_coeffs, uint64_t N,
+                                      uint32_t t, uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j);
 
 }  // namespace sclgpu

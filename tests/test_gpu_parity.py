@@ -387,6 +387,35 @@ def test_full_size_c2_properties(ctx, pkg, orc):
     assert torch.equal(d_sum, d_want)
 
 
+# ------------------------------------------------------------------ Polynomial::evaluate from coefficient planes
+@pytest.mark.parametrize("field,t,n,N", [(61, 15, 32, 5000), (61, 2, 5, 129), (61, 0, 3, 7), (61, 9, 20, 1 << 16),
+                                         (127, 7, 16, 3001), (127, 3, 9, 640), (61, 20, 40, 300), (127, 9, 20, 100)])
+def test_share_from_coefficient_planes(ctx, pkg, orc, field, t, n, N):
+    """shamir_share_coeffs_dev (poly.h:56-64): coefficients supplied by the caller as [t+1][N] planes
+    (arbitrary residues, plane 0 = the secrets).  Oracle: the same polynomial written as a Vandermonde
+    product, shares[j] = V(n, t+1) * c_j (the reference's test_matrix.cc:342-365 identity), through
+    Matrix::multiply(Vector) of the oracle."""
+    import torch
+
+    ctx.use_torch_stream()
+    w = 1 if field == 61 else 2
+    coeffs = orc.vector_random(field, "coeff planes", 3, (t + 1) * N).reshape((t + 1, N) + (() if w == 1 else (2,)))
+    d_c = torch.from_numpy(coeffs.view(np.int64)).cuda()
+    d_pm = torch.empty((n, N, w), dtype=torch.int64, device="cuda")
+    d_sm = torch.empty((N, n, w), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_coeffs_dev(field, d_c, N, t, n, d_pm, pkg.binding.PARTY_MAJOR)
+    ctx.shamir_share_coeffs_dev(field, d_c, N, t, n, d_sm, pkg.binding.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    pm = d_pm.cpu().numpy().view(np.uint64)
+    sm = d_sm.cpu().numpy().view(np.uint64)
+    assert np.array_equal(np.swapaxes(pm, 0, 1), sm)
+    V = orc.vandermonde(field, n, t + 1)
+    K = min(N, 64)
+    for j in list(range(K)) + [N - 1]:
+        cj = np.ascontiguousarray(coeffs[:, j])
+        assert np.array_equal(sm[j].reshape(V.shape[:1] + V.shape[2:]), orc.matvec(field, V, cj)), (field, j)
+
+
 # ------------------------------------------------------------------ per-party packets (SURVEY 8f.1)
 @pytest.mark.parametrize("field,t,n,N", [(61, 15, 32, 5000), (61, 2, 5, 1), (61, 3, 7, 4097), (127, 7, 16, 3001),
                                          (61, 20, 40, 300), (61, 1, 3, (1 << 21) + 7)])

@@ -41,6 +41,13 @@ def shamir(tag, field, n, t, N, detect):
         r["recover_p_ms"] = timeit(lambda: ctx.recover_p_dev(field, sh, N, n, out, B.PARTY_MAJOR))
         rec = r["recover_p_ms"]
     r["ok"] = bool(torch.equal(out, sec))
+    if not detect and N * (t + 1) * eb <= (12 << 30):
+        # staged form: coefficient planes resident in HBM (plane 0 = secrets), Polynomial::evaluate only
+        planes = i64(t + 1, N, w)
+        ctx.random_dev(field, "coefficient planes", 0, (t + 1) * N, planes)
+        r["share_from_coeffs_ms"] = timeit(lambda: ctx.shamir_share_coeffs_dev(field, planes, N, t, n, sh, B.PARTY_MAJOR))
+        r["share_from_coeffs_GBps"] = ((t + 1) * eb + n * eb) * N / r["share_from_coeffs_ms"] / 1e6
+        del planes
     r["secrets_per_s"] = N / ((r["share_ms"] + rec) * 1e-3)
     r["share_GBps"] = (eb + n * eb) * N / r["share_ms"] / 1e6
     r["recover_GBps"] = ((min(n, 2 * t) if detect else n) * eb + eb) * N / rec / 1e6
