@@ -42,6 +42,10 @@ struct sclgpu_ctx {
   std::map<uint32_t, void*> tc_bmat_cache;   // (t, n) -> Vandermonde limb image of k_share61_tc
   std::map<const void*, void*> rd_bmat_cache;  // Lagrange check matrix (device) -> its limb image for k_recover_d_tc
   bool tc_prepared = false;
+  // device scratch of the host-pointer entry points (chunk buffers), kept across calls: a cudaMalloc /
+  // cudaFree pair per buffer per call costs milliseconds and a device synchronisation
+  std::vector<std::pair<void*, size_t>> pool;
+  size_t pool_next = 0;
 };
 
 static constexpr int kMaxPartials = 2048;
@@ -184,6 +188,7 @@ extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
   for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
   for (auto& kv : ctx->tc_bmat_cache) cudaFree(kv.second);
   for (auto& kv : ctx->rd_bmat_cache) cudaFree(kv.second);
+  for (auto& pb : ctx->pool) cudaFree(pb.first);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
     if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
@@ -280,6 +285,40 @@ struct DevBuf {
     if (p) cudaFree(p);
   }
   cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// Scratch from the context's pool: same interface as DevBuf, nothing freed on return.  A host entry
+// point opens a PoolScope (calls on one context are serialised and end synchronised, so buffers handed
+// out in one call are free again in the next).
+static thread_local sclgpu_ctx* g_pool_ctx = nullptr;
+struct PoolScope {
+  explicit PoolScope(sclgpu_ctx* ctx) {
+    g_pool_ctx = ctx;
+    if (ctx) ctx->pool_next = 0;
+  }
+  ~PoolScope() { g_pool_ctx = nullptr; }
+};
+struct PoolBuf {
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) {
+    sclgpu_ctx* ctx = g_pool_ctx;
+    if (!ctx) return cudaErrorInvalidValue;
+    if (bytes == 0) bytes = 1;
+    if (ctx->pool_next == ctx->pool.size()) ctx->pool.emplace_back(nullptr, 0);
+    auto& slot = ctx->pool[ctx->pool_next++];
+    if (slot.second < bytes) {
+      if (slot.first) cudaFree(slot.first);
+      slot = {nullptr, 0};
+      void* q = nullptr;
+      cudaError_t e = cudaMalloc(&q, bytes);
+      if (e != cudaSuccess) return e;
+      slot = {q, bytes};
+    }
+    p = slot.first;
+    return cudaSuccess;
+  }
   template <class T>
   T* as() { return reinterpret_cast<T*>(p); }
 };
@@ -737,7 +776,8 @@ extern "C" int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64
   CK(cudaSetDevice(ctx->device));
   if (n_bytes == 0) return SCLGPU_OK;
   const uint64_t chunk = 256ull << 20;  // bytes, multiple of 16
-  DevBuf buf[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf buf[2];
   CK(buf[0].alloc(std::min(chunk, n_bytes)));
   if (n_bytes > chunk) CK(buf[1].alloc(std::min(chunk, n_bytes - chunk)));
   int k = 0;
@@ -793,7 +833,8 @@ static int random_host(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_b
   if (n == 0) return SCLGPU_OK;
   const uint64_t chunk = 1ull << 25;  // elements; even, so Fp61 chunks start on a block boundary
   const uint64_t per_block = (F::BYTES == 16 || ONE) ? 1 : 2;
-  DevBuf buf[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf buf[2];
   CK(buf[0].alloc(std::min(chunk, n) * sizeof(E)));
   if (n > chunk) CK(buf[1].alloc(std::min(chunk, n - chunk) * sizeof(E)));
   int k = 0;
@@ -896,7 +937,8 @@ static int share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t
   const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
   uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
-  DevBuf dsec[2], dpm[2], dsm[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsec[2], dpm[2], dsm[2];
   const int nbuf = N > chunk ? 2 : 1;
   for (int k = 0; k < nbuf; ++k) {
     CK(dsec[k].alloc(chunk * sizeof(E)));
@@ -963,7 +1005,8 @@ static int share_packets_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, 
   const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
   uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
-  DevBuf dsec[2], dpm[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsec[2], dpm[2];
   const int nbuf = N > chunk ? 2 : 1;
   for (int k = 0; k < nbuf; ++k) {
     CK(dsec[k].alloc(chunk * sizeof(E)));
@@ -1027,7 +1070,8 @@ static int additive_share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N,
   if (N == 0) return SCLGPU_OK;
   uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
-  DevBuf dsec[2], dpm[2], dsm[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsec[2], dpm[2], dsm[2];
   const int nbuf = N > chunk ? 2 : 1;
   for (int k = 0; k < nbuf; ++k) {
     CK(dsec[k].alloc(chunk * sizeof(E)));
@@ -1073,7 +1117,8 @@ static int additive_recover_host(sclgpu_ctx* ctx, const void* shares, uint64_t N
   uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n, 1) * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
   const int nbuf = N > chunk ? 2 : 1;
-  DevBuf dsh[2], dout[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsh[2], dout[2];
   for (int k = 0; k < nbuf; ++k) {
     CK(dsh[k].alloc(chunk * n * sizeof(E)));
     CK(dout[k].alloc(chunk * sizeof(E)));
@@ -1160,7 +1205,8 @@ static int recover_p_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   chunk &= ~1ull;  // even chunks: 128-bit loads in the plane kernel
   if (chunk == 0) chunk = N;
   const int nbuf = N > chunk ? 2 : 1;
-  DevBuf dsh[2], dpm[2], dout[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsh[2], dpm[2], dout[2];
   for (int k = 0; k < nbuf; ++k) {
     CK(dsh[k].alloc(chunk * n * sizeof(E)));
     CK(dpm[k].alloc(chunk * n * sizeof(E)));
@@ -1205,7 +1251,8 @@ static int recover_p_packets_host(sclgpu_ctx* ctx, const uint8_t* const* packets
   chunk = std::min(chunk, std::min(N, kHostChunk)) & ~1ull;  // even: 128-bit loads in the plane kernel
   if (chunk == 0) chunk = N;
   const int nbuf = N > chunk ? 2 : 1;
-  DevBuf dsh[2], dout[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsh[2], dout[2];
   for (int k = 0; k < nbuf; ++k) {
     CK(dsh[k].alloc(chunk * std::max<uint64_t>(n, 1) * sizeof(E)));
     CK(dout[k].alloc(chunk * sizeof(E)));
@@ -1285,7 +1332,8 @@ static int recover_d_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n_given * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
   const int nbuf = N > chunk ? 2 : 1;
-  DevBuf dsh[2], dout[2], derr[2];
+  PoolScope pool_scope(ctx);
+  PoolBuf dsh[2], dout[2], derr[2];
   for (int k = 0; k < nbuf; ++k) {
     CK(dsh[k].alloc(chunk * n_given * sizeof(E)));
     CK(dout[k].alloc(chunk * sizeof(E)));
