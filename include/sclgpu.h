@@ -50,6 +50,8 @@ extern "C" {
                                for at least one secret of the batch; see err[] */
 #define SCLGPU_ECUDA (-4)   /* CUDA runtime failure / no usable device */
 #define SCLGPU_ENOMEM (-5)  /* device or pinned-host allocation failed */
+#define SCLGPU_ECORRECT (-6) /* std::logic_error("could not correct shares") (shamir.h:243-245) for at
+                                least one sharing of the batch; see status[] */
 
 /* Layout of a batch of N sharings of n shares each. */
 #define SCLGPU_SECRET_MAJOR 0 /* [N][n]: row j = the Vector SCL returns for secret j (shamir.h:60-67) */
@@ -140,6 +142,29 @@ int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const uint64_t* d_coeff
                                         uint32_t t, uint32_t n, uint64_t* d_shares, int layout);
 int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N,
                                          uint32_t t, uint32_t n, void* d_shares, int layout);
+
+/* ---- ss::shamirRecoverC (shamir.h:203-258, Berlekamp-Welch) on N sharings ---------
+ * t = (n-1)/3 and the first np = 3t+1 shares of each sharing are used, as in the
+ * reference; alphas == NULL means 1..n (shamir.h:256-258).  Per sharing j:
+ *   f[j][0..np)    coefficients of ErrorCorrectedSecret::f (the recovered polynomial;
+ *                  the secret is f[j][0]), zero padded to np entries;
+ *   err[j][0..t]   coefficients of ErrorCorrectedSecret::err (monic, its roots are the
+ *                  nodes of the corrupted shares), zero padded;
+ *   status[j]      1 where the reference throws "could not correct shares" (f, err = 0).
+ * Returns SCLGPU_ECORRECT if any status[j] is set (everything is still written),
+ * *n_failed (nullable) = how many.  np <= 32, i.e. 1 <= n <= 33 (SCLGPU_EINVAL otherwise).
+ * Up to t corrupted shares per sharing are corrected. */
+int sclgpu_fp61_recover_c(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t n,
+                          const uint64_t* alphas, uint64_t* f, uint64_t* err, uint8_t* status,
+                          uint64_t* n_failed);
+int sclgpu_fp127_recover_c(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n, const void* alphas,
+                           void* f, void* err, uint8_t* status, uint64_t* n_failed);
+int sclgpu_fp61_recover_c_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N, uint32_t n, int layout,
+                              const uint64_t* alphas, uint64_t* d_f, uint64_t* d_err, uint8_t* d_status,
+                              uint64_t* n_failed);
+int sclgpu_fp127_recover_c_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n, int layout,
+                               const void* alphas, void* d_f, void* d_err, uint8_t* d_status,
+                               uint64_t* n_failed);
 
 /* ---- per-party packets: Serializer<math::Vector<FF>> wire layout ------------------
  * What a dealer sends to party i after sharing N secrets is a net::Packet holding the

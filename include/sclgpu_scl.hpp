@@ -15,6 +15,8 @@
 //     -> sclgpu::shamirRecoverP(ctx, shares[, alphas, x])   : Vector (N)
 //   scl::ss::shamirRecoverD(shares, t)                   shamir.h:117-155
 //     -> sclgpu::shamirRecoverD(ctx, shares, t[, flags])    : Vector (N); throws as SCL unless flags != nullptr
+//   scl::ss::shamirRecoverC(shares[, alphas])            shamir.h:203-258
+//     -> sclgpu::shamirRecoverC(ctx, shares[, alphas][, status]) : std::vector<ErrorCorrectedSecret<FF>>
 //   packet.write(Vector of party i's shares)             net/packet.h:145-149, vector.h:596-629
 //     -> sclgpu::shamirSharePackets(ctx, secrets, t, n, prg) : n net::Packet, ready for channel->send
 //        sclgpu::shamirRecoverP(ctx, packets)                : Vector (N) from the n packets received
@@ -39,7 +41,9 @@
 #include "scl/math/fp.h"
 #include "scl/math/matrix.h"
 #include "scl/math/vector.h"
+#include "scl/math/poly.h"
 #include "scl/net/packet.h"
+#include "scl/ss/shamir.h"
 #include "scl/util/prg.h"
 #include "sclgpu.h"
 
@@ -68,6 +72,7 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto random = &sclgpu_##SUF##_random;                                                    \
     static constexpr auto share = &sclgpu_##SUF##_shamir_share;                                               \
     static constexpr auto recover_p = &sclgpu_##SUF##_recover_p;                                              \
+    static constexpr auto recover_c = &sclgpu_##SUF##_recover_c;                                              \
     static constexpr auto share_packets = &sclgpu_##SUF##_shamir_share_packets;                               \
     static constexpr auto recover_p_packets = &sclgpu_##SUF##_recover_p_packets;                              \
     static constexpr auto additive_share = &sclgpu_##SUF##_additive_share;                                    \
@@ -119,13 +124,13 @@ class Context {
   sclgpu_ctx* get() const { return m_ctx; }
   std::uint64_t launches() const { return sclgpu_launch_count(m_ctx); }
 
-  // SCLGPU_EINVAL -> std::invalid_argument, ELOGIC/EDETECT -> std::logic_error,
+  // SCLGPU_EINVAL -> std::invalid_argument, ELOGIC/EDETECT/ECORRECT -> std::logic_error,
   // with the reference's own message (sclgpu_last_error).
   void check(int rc) const {
     if (rc == SCLGPU_OK) return;
     const std::string msg = sclgpu_last_error(m_ctx);
     if (rc == SCLGPU_EINVAL) throw std::invalid_argument(msg);
-    if (rc == SCLGPU_ELOGIC || rc == SCLGPU_EDETECT) throw std::logic_error(msg);
+    if (rc == SCLGPU_ELOGIC || rc == SCLGPU_EDETECT || rc == SCLGPU_ECORRECT) throw std::logic_error(msg);
     throw std::runtime_error(std::string("sclgpu: ") + sclgpu_strerror(rc) + ": " + msg);
   }
 
@@ -284,6 +289,37 @@ scl::math::Vector<FF> shamirRecoverD(Context& ctx, const scl::math::Matrix<FF>& 
   ctx.check(rc);
   if (flags != nullptr) *flags = std::move(err);
   return scl::math::Vector<FF>(std::move(out));
+}
+
+// ---- shamirRecoverC(shares[, alphas]), shamir.h:203-258, on every row of `shares`.  With status ==
+// nullptr the call throws std::logic_error("could not correct shares") if ANY sharing cannot be
+// corrected (what the loop over SCL's function does at the first one); otherwise (*status)[j] = 1 marks
+// those rows and their result holds zero polynomials.
+template <class FF>
+std::vector<scl::ss::ErrorCorrectedSecret<FF>> shamirRecoverC(Context& ctx, const scl::math::Matrix<FF>& shares,
+                                                              const scl::math::Vector<FF>* alphas = nullptr,
+                                                              std::vector<std::uint8_t>* status = nullptr) {
+  using A = detail::Abi<FF>;
+  const std::size_t N = shares.rows(), n = shares.cols();
+  if (N == 0) return {};
+  if (alphas != nullptr && alphas->size() != n) throw std::invalid_argument("Vec sizes mismatch");
+  const std::size_t t = (n - 1) / 3, np = 3 * t + 1;
+  std::vector<FF> f(N * np), e(N * (t + 1));
+  std::vector<std::uint8_t> st(N);
+  std::uint64_t n_failed = 0;
+  const int rc = A::recover_c(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(shares)(0, 0)), N,
+                              (std::uint32_t)n, alphas ? detail::raw<FF>(alphas->toStlVector().data()) : nullptr,
+                              detail::raw<FF>(f.data()), detail::raw<FF>(e.data()), st.data(), &n_failed);
+  if (!(rc == SCLGPU_ECORRECT && status != nullptr)) ctx.check(rc);
+  std::vector<scl::ss::ErrorCorrectedSecret<FF>> out;
+  out.reserve(N);
+  for (std::size_t j = 0; j < N; ++j) {
+    using Vec = scl::math::Vector<FF>;
+    out.push_back({scl::math::Polynomial<FF>::create(Vec(f.begin() + j * np, f.begin() + (j + 1) * np)),
+                   scl::math::Polynomial<FF>::create(Vec(e.begin() + j * (t + 1), e.begin() + (j + 1) * (t + 1)))});
+  }
+  if (status != nullptr) *status = std::move(st);
+  return out;
 }
 
 // ---- Vector entrywise operations, vector.h:192-301 ("Vec sizes mismatch", :481-485)

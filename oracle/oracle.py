@@ -143,6 +143,8 @@ class PortOracle(_Base):
                 g(n).restype = None
             g("shamir_share").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
             g("shamir_share").restype = None
+            g("recover_c").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]
+            g("recover_c").restype = C.c_int64
             g("additive_share").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
             g("additive_share").restype = None
             g("additive_recover").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
@@ -217,6 +219,18 @@ class PortOracle(_Base):
         out = empty(field, N)
         self._f(field, "additive_recover")(_p(shares), N, n, _p(out))
         return out
+
+    def recover_c(self, field, shares, alphas=None):
+        """shamirRecoverC per sharing -> (f [N][3t+1], err [N][t+1], status [N] uint8, n_failed)"""
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        t = (n - 1) // 3
+        f = empty(field, N, 3 * t + 1)
+        e = empty(field, N, t + 1)
+        st = np.zeros(N, dtype=np.uint8)
+        A = None if alphas is None else _c(alphas)
+        nf = self._f(field, "recover_c")(_p(shares), N, n, _p(A), _p(f), _p(e), _p(st))
+        return f, e, st, int(nf)
 
     def lagrange(self, field, nodes, x: int):
         nodes = _c(nodes)
@@ -305,6 +319,8 @@ class RefOracle(_Base):
                 g(n).restype = None
             g("shamir_share").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
             g("shamir_share").restype = None
+            g("recover_c").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]
+            g("recover_c").restype = C.c_int64
             g("additive_share").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
             g("additive_share").restype = None
             g("additive_recover").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
@@ -394,6 +410,18 @@ class RefOracle(_Base):
         out = empty(field, N)
         self._f(field, "additive_recover")(_p(shares), N, n, _p(out))
         return out
+
+    def recover_c(self, field, shares, alphas=None):
+        """shamirRecoverC per sharing -> (f [N][3t+1], err [N][t+1], status [N] uint8, n_failed)"""
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        t = (n - 1) // 3
+        f = empty(field, N, 3 * t + 1)
+        e = empty(field, N, t + 1)
+        st = np.zeros(N, dtype=np.uint8)
+        A = None if alphas is None else _c(alphas)
+        nf = self._f(field, "recover_c")(_p(shares), N, n, _p(A), _p(f), _p(e), _p(st))
+        return f, e, st, int(nf)
 
     def lagrange(self, field, nodes, x: int):
         nodes = _c(nodes)

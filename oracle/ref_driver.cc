@@ -14,6 +14,7 @@
 //     ss::shamirSecretShare              (include/scl/ss/shamir.h:52-68)
 //     ss::shamirRecoverP / shamirRecoverD(include/scl/ss/shamir.h:82-155)
 //     ss::additiveShare                  (include/scl/ss/additive.h:42-53)
+//     ss::shamirRecoverC                 (include/scl/ss/shamir.h:203-258)
 //     math::computeLagrangeBasis         (include/scl/math/lagrange.h:55-71)
 //     math::Matrix<T>::multiply(Vector)  (include/scl/math/matrix.h:498-513)
 //     Vector add/subtract/multiplyEntryWise/scalarMultiply/dot/sum
@@ -137,6 +138,40 @@ void additiveRecover(const unsigned char* shares, uint64_t N, uint64_t n,
   for (uint64_t j = 0; j < N; ++j) {
     readVec<T>(shares + j * n * bs, n).sum().write(out + j * bs);
   }
+}
+
+// ss::shamirRecoverC(shares[, alphas]) per sharing (Berlekamp-Welch, shamir.h:203-258).
+// t = (n-1)/3, np = 3t+1.  f_out: [N][np] coefficients of the recovered polynomial, zero padded;
+// e_out: [N][t+1] coefficients of the (monic) error polynomial, zero padded; status[j] = 1 where the
+// reference throws std::logic_error("could not correct shares").  Returns the number of such j.
+template <typename T>
+int64_t recoverC(const unsigned char* shares, uint64_t N, uint64_t n,
+                 const unsigned char* alphas, unsigned char* f_out,
+                 unsigned char* e_out, unsigned char* status) {
+  const std::size_t bs = T::byteSize();
+  const std::size_t t = (n - 1) / 3, np = 3 * t + 1;
+  int64_t failed = 0;
+  for (uint64_t j = 0; j < N; ++j) {
+    const auto sh = readVec<T>(shares + j * n * bs, n);
+    std::memset(f_out + j * np * bs, 0, np * bs);
+    std::memset(e_out + j * (t + 1) * bs, 0, (t + 1) * bs);
+    try {
+      const auto r = alphas == nullptr
+                         ? scl::ss::shamirRecoverC(sh)
+                         : scl::ss::shamirRecoverC(sh, readVec<T>(alphas, n));
+      for (std::size_t k = 0; k <= r.f.degree() && k < np; ++k) {
+        r.f[k].write(f_out + (j * np + k) * bs);
+      }
+      for (std::size_t k = 0; k <= r.err.degree() && k <= t; ++k) {
+        r.err[k].write(e_out + (j * (t + 1) + k) * bs);
+      }
+      status[j] = 0;
+    } catch (const std::logic_error&) {
+      status[j] = 1;
+      ++failed;
+    }
+  }
+  return failed;
 }
 
 template <typename T>
@@ -351,6 +386,12 @@ double benchShareRecover(uint64_t N, uint64_t t, uint64_t n, int detect,
       const unsigned char* seed, uint64_t seed_len, uint64_t skip,             \
       unsigned char* shares) {                                                 \
     shamirShare<T>(secrets, N, t, n, seed, seed_len, skip, shares);            \
+  }                                                                            \
+  int64_t sclref_##SUF##_recover_c(const unsigned char* shares, uint64_t N,    \
+                                   uint64_t n, const unsigned char* alphas,    \
+                                   unsigned char* f_out, unsigned char* e_out, \
+                                   unsigned char* status) {                    \
+    return recoverC<T>(shares, N, n, alphas, f_out, e_out, status);            \
   }                                                                            \
   void sclref_##SUF##_additive_share(                                          \
       const unsigned char* secrets, uint64_t N, uint64_t n,                    \

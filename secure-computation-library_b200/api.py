@@ -129,7 +129,7 @@ class Context:
         msg = self.lib.sclgpu_last_error(self._ctx).decode(errors="replace")
         if rc == B.EINVAL:
             raise InvalidArgument(msg)
-        if rc in (B.ELOGIC, B.EDETECT):
+        if rc in (B.ELOGIC, B.EDETECT, B.ECORRECT):
             raise LogicError(msg)
         raise CudaError(f"{self.lib.sclgpu_strerror(rc).decode()}: {msg}")
 
@@ -223,6 +223,32 @@ class Context:
 
     def shamir_share_coeffs_dev(self, field: int, coeffs, N: int, t: int, n: int, shares, layout: int = B.PARTY_MAJOR):
         self._check(self._f(field, "shamir_share_coeffs_dev")(self._ctx, _dp(coeffs), N, t, n, _dp(shares), layout))
+
+    def recover_c(self, field: int, shares, alphas=None):
+        """ss::shamirRecoverC (shamir.h:203-258) per sharing ->
+        (f [N][3t+1], err [N][t+1], status [N] uint8, n_failed); the secrets are f[:, 0]."""
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        if n < 1:
+            raise InvalidArgument("shamirRecoverC needs at least one share")
+        t = (n - 1) // 3
+        f = empty(field, N, 3 * t + 1)
+        e = empty(field, N, t + 1)
+        st = np.zeros(N, dtype=np.uint8)
+        nf = C.c_uint64(0)
+        A = None if alphas is None else _c(alphas)
+        rc = self._f(field, "recover_c")(self._ctx, _p(shares), N, n, _p(A), _p(f), _p(e), _p(st), C.byref(nf))
+        self._check(rc, allow=(B.ECORRECT,))
+        return f, e, st, int(nf.value)
+
+    def recover_c_dev(self, field: int, shares, N: int, n: int, f, err, status, layout: int = B.PARTY_MAJOR,
+                      alphas=None) -> int:
+        nf = C.c_uint64(0)
+        A = None if alphas is None else _c(alphas)
+        rc = self._f(field, "recover_c_dev")(self._ctx, _dp(shares), N, n, layout, _p(A), _dp(f), _dp(err), _dp(status),
+                                              C.byref(nf))
+        self._check(rc, allow=(B.ECORRECT,))
+        return int(nf.value)
 
     # ------------------------------------------------------------ per-party packets
     def shamir_share_packets(self, field: int, secrets, t: int, n: int, seed, first_block: int = 0) -> list:

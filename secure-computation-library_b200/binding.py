@@ -16,7 +16,7 @@ REPO = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libsclgpu.so")
 HEADER_PATH = os.path.join(REPO, "include", "sclgpu.h")
 
-OK, EINVAL, ELOGIC, EDETECT, ECUDA, ENOMEM = 0, -1, -2, -3, -4, -5
+OK, EINVAL, ELOGIC, EDETECT, ECUDA, ENOMEM, ECORRECT = 0, -1, -2, -3, -4, -5, -6
 SECRET_MAJOR, PARTY_MAJOR = 0, 1
 
 _vp = C.c_void_p
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_shamir_share", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_shamir_share_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _int)
         _sig(lib, f"sclgpu_{f}_shamir_share_coeffs_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _int)
+        _sig(lib, f"sclgpu_{f}_recover_c", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, C.POINTER(_u64))
+        _sig(lib, f"sclgpu_{f}_recover_c_dev", _int, _vp, _vp, _u64, _u32, _int, _vp, _vp, _vp, _vp, C.POINTER(_u64))
         _sig(lib, f"sclgpu_{f}_shamir_share_packets", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_recover_p_packets", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp)
         _sig(lib, f"sclgpu_{f}_additive_share", _int, _vp, _vp, _u64, _u32, _vp, _u64, _vp)

@@ -364,6 +364,141 @@ k_share61(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
   }
 }
 
+// ================================================================ shamirRecoverC
+// include/scl/ss/shamir.h:203-258 (Berlekamp-Welch) + solveLinearSystem (matrix.h:812-828) +
+// Polynomial::divide (poly.h:262-278).  One WARP per sharing, lane i owns row i of the
+// np x (np+1) augmented system in shared memory (np = 3t+1 <= 32).  For e = t..0:
+//   A(i,j) = s_i a_i^j (j<e), A(i,e) = -1, A(i,j) = A(i,j-1) a_i (j>e), b_i = -s_i a_i^e
+// The reference accepts a system only when its solution is unique (hasSolution(aug, true),
+// matrix.h:741-764), so any exact elimination yields the same x.  Here: fraction-free
+// Gauss-Jordan (row_k <- p*row_k - f*row_c: no inversion per pivot), then one inversion per
+// lane, all lanes in parallel.  Then Q / E by long division, lanes over the divisor terms.
+// Outputs per sharing: f (np coefficients, zero padded), err (t+1, monic, zero padded),
+// status 1 where the reference throws "could not correct shares" (f, err zeroed).
+template <class F>
+__global__ void __launch_bounds__(256)
+k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i, uint64_t stride_j,
+            uint32_t t, const typename F::E* __restrict__ alphas, typename F::E* __restrict__ f_out,
+            typename F::E* __restrict__ e_out, uint8_t* __restrict__ status,
+            unsigned long long* __restrict__ n_failed) {
+  typedef typename F::E E;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t np = 3u * t + 1u, cols = np + 1u;
+  const uint32_t per_warp = np * cols + 2u * np;            // matrix, x, division remainder
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  E* M = reinterpret_cast<E*>(dyn_smem) + (size_t)wib * per_warp;
+  E* X = M + np * cols;
+  E* R = X + np;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const E minus1 = F::neg(F::one());
+  const bool row = lane < np;
+  const E a_i = row ? alphas[lane] : F::zero();
+  unsigned long long local_failed = 0;
+
+  for (uint64_t j = warp; j < N; j += warps) {
+    const E s_i = row ? in[(uint64_t)lane * stride_i + j * stride_j] : F::zero();
+    int e = (int)t;
+    for (;; --e) {
+      if (row) {
+        E* mr = M + lane * cols;
+        E v = s_i;
+        for (int c = 0; c < e; ++c) {
+          mr[c] = v;
+          v = F::mul(v, a_i);
+        }
+        mr[np] = F::neg(v);
+        E u = minus1;
+        for (uint32_t c = (uint32_t)e; c < np; ++c) {
+          mr[c] = u;
+          u = F::mul(u, a_i);
+        }
+      }
+      __syncwarp();
+      bool singular = false;
+      for (uint32_t c = 0; c < np; ++c) {
+        const bool nz = row && lane >= c && !F::is_zero(M[lane * cols + c]);
+        const unsigned mask = __ballot_sync(0xffffffffu, nz);
+        if (mask == 0) {
+          singular = true;
+          break;
+        }
+        const uint32_t piv = (uint32_t)__ffs(mask) - 1u;
+        if (piv != c) {
+          for (uint32_t q = lane; q < cols; q += 32u) {
+            const E tmp = M[piv * cols + q];
+            M[piv * cols + q] = M[c * cols + q];
+            M[c * cols + q] = tmp;
+          }
+          __syncwarp();
+        }
+        const E p = M[c * cols + c];
+        if (row && lane != c) {
+          E* mr = M + lane * cols;
+          const E f = mr[c];
+          if (!F::is_zero(f)) {
+            for (uint32_t q = c + 1; q < cols; ++q) mr[q] = F::sub(F::mul(mr[q], p), F::mul(f, M[c * cols + q]));
+            mr[c] = F::zero();
+            if (lane < c) mr[lane] = F::mul(mr[lane], p);  // keep the diagonal of finished rows consistent
+          }
+        }
+        __syncwarp();
+      }
+      if (!singular) break;
+      if (e == 0) {  // only with coinciding nodes: the reference then proceeds with x = 0 (shamir.h:213,238-240)
+        e = -1;
+        break;
+      }
+      __syncwarp();
+    }
+    // x_i = b_i / d_i
+    if (row) X[lane] = e < 0 ? F::zero() : F::mul(M[lane * cols + np], F::inv(M[lane * cols + lane]));
+    if (e < 0) e = 0;
+    __syncwarp();
+    // Q = x[e..np-1] (trailing zeros stripped), E = (x_0..x_{e-1}, 1); f = Q / E
+    const uint32_t ue = (uint32_t)e, qn = np - ue;
+    if (lane < qn) R[lane] = X[ue + lane];
+    __syncwarp();
+    const unsigned nzq = __ballot_sync(0xffffffffu, lane < qn && !F::is_zero(R[lane]));
+    const uint32_t deg = nzq ? 31u - (uint32_t)__clz(nzq) : 0u;
+    E* fo = f_out + j * np;
+    E* eo = e_out + j * (uint64_t)(t + 1);
+    if (lane < np) fo[lane] = F::zero();
+    if (lane <= t) eo[lane] = F::zero();
+    __syncwarp();
+    bool ok;
+    if (deg >= ue) {
+      for (int d = (int)deg; d >= (int)ue; --d) {
+        const E c = R[d];
+        __syncwarp();
+        if (lane < ue) R[d - ue + lane] = F::sub(R[d - ue + lane], F::mul(c, X[lane]));
+        if (lane == 0) {
+          fo[d - ue] = c;
+          R[d] = F::zero();
+        }
+        __syncwarp();
+      }
+      ok = __ballot_sync(0xffffffffu, lane < ue && !F::is_zero(R[lane])) == 0;
+    } else {
+      ok = nzq == 0;  // Q == 0: quotient and remainder are zero
+    }
+    if (ok) {
+      if (lane < ue) eo[lane] = X[lane];
+      if (lane == ue) eo[lane] = F::one();
+      if (lane == 0) status[j] = 0;
+    } else {
+      __syncwarp();
+      if (lane < np) fo[lane] = F::zero();
+      if (lane == 0) {
+        status[j] = 1;
+        ++local_failed;
+      }
+    }
+    __syncwarp();
+  }
+  if (local_failed) atomicAdd(n_failed, local_failed);
+}
+
 // ================================================================ additiveShare
 // include/scl/ss/additive.h:42-53, N calls on one PRG: n-1 x FF::random (ff.h:72-76: ONE
 // whole keystream block per element, bytes beyond byteSize dropped), last share =

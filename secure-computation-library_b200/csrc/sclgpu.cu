@@ -222,6 +222,7 @@ extern "C" const char* sclgpu_strerror(int code) {
     case SCLGPU_EDETECT: return "error detected during recovery";
     case SCLGPU_ECUDA: return "CUDA failure or no usable device";
     case SCLGPU_ENOMEM: return "out of memory";
+    case SCLGPU_ECORRECT: return "could not correct shares";
     default: return "unknown";
   }
 }
@@ -1360,6 +1361,83 @@ extern "C" int sclgpu_fp61_recover_d(sclgpu_ctx* c, const uint64_t* s, uint64_t 
 extern "C" int sclgpu_fp127_recover_d(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F127>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
 extern "C" int sclgpu_fp61_recover_d_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return recover_d_dev<F61>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }
 extern "C" int sclgpu_fp127_recover_d_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_dev<F127>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }
+
+// ------------------------------------------------------------------ recover C
+// alphas stay HOST pointers (n values); d_* are device pointers
+template <class F>
+static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_shares, uint64_t N, uint32_t n,
+                        uint64_t si, uint64_t sj, const typename F::E* alphas, typename F::E* d_f,
+                        typename F::E* d_e, uint8_t* d_status, uint64_t* n_failed) {
+  typedef typename F::E E;
+  if (n == 0) return fail(ctx, SCLGPU_EINVAL, "shamirRecoverC needs at least one share");
+  const uint32_t t = (n - 1) / 3, np = 3 * t + 1;
+  if (np > 32) return fail(ctx, SCLGPU_EINVAL, "recover_c supports n <= 33 (3t+1 <= 32 rows per warp)");
+  if (n_failed) *n_failed = 0;
+  if (N == 0) return SCLGPU_OK;
+  std::vector<E> al(np);
+  for (uint32_t i = 0; i < np; ++i) al[i] = alphas ? alphas[i] : F::from_u32(i + 1);
+  DevBuf dal;
+  CK(dal.alloc(np * sizeof(E)));
+  CK(cudaMemcpyAsync(dal.p, al.data(), np * sizeof(E), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
+  const int warps_per_cta = 8;
+  const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 2 * np) * sizeof(E);
+  CK(cudaFuncSetAttribute(k_recover_c<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<uint64_t>((N + warps_per_cta - 1) / warps_per_cta, (uint64_t)ctx->sm_count * 4);
+  k_recover_c<F><<<grid, 32 * warps_per_cta, smem, st>>>(d_shares, N, si, sj, t, dal.as<E>(), d_f, d_e, d_status,
+                                                         ctx->d_count);
+  CKL();
+  unsigned long long bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->d_count, sizeof(bad), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));  // also keeps `dal` alive until the kernel is done
+  if (n_failed) *n_failed = bad;
+  if (bad) return fail(ctx, SCLGPU_ECORRECT, "could not correct shares");
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int recover_c_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t n, int layout, const void* alphas,
+                         void* d_f, void* d_e, uint8_t* d_status, uint64_t* n_failed) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (N && (!d_shares || !d_f || !d_e || !d_status)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  uint64_t si, sj;
+  strides_for(layout, N, n, si, sj);
+  return recover_c_on<F>(ctx, ctx->stream, (const E*)d_shares, N, n, si, sj, (const E*)alphas, (E*)d_f, (E*)d_e, d_status,
+                         n_failed);
+}
+
+template <class F>
+static int recover_c_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n, const void* alphas, void* f,
+                          void* e, uint8_t* status, uint64_t* n_failed) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (N && (!shares || !f || !e || !status)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n == 0) return fail(ctx, SCLGPU_EINVAL, "shamirRecoverC needs at least one share");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t t = (n - 1) / 3, np = 3 * t + 1;
+  HostOp hop(ctx);
+  void *dsh, *df, *de, *dst;
+  RET(hop.up(shares, (size_t)N * n * sizeof(E), &dsh));
+  RET(hop.dev((size_t)N * np * sizeof(E), &df));
+  RET(hop.dev((size_t)N * (t + 1) * sizeof(E), &de));
+  RET(hop.dev((size_t)N, &dst));
+  const int rc = recover_c_on<F>(ctx, hop.st, (const E*)dsh, N, n, 1, n, (const E*)alphas, (E*)df, (E*)de, (uint8_t*)dst,
+                                 n_failed);
+  if (rc != SCLGPU_OK && rc != SCLGPU_ECORRECT) return rc;
+  if (N) {
+    CK(cudaMemcpyAsync(f, df, (size_t)N * np * sizeof(E), cudaMemcpyDeviceToHost, hop.st));
+    CK(cudaMemcpyAsync(e, de, (size_t)N * (t + 1) * sizeof(E), cudaMemcpyDeviceToHost, hop.st));
+    RET(hop.down(status, dst, (size_t)N));
+  }
+  return rc;
+}
+extern "C" int sclgpu_fp61_recover_c(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, uint64_t* f, uint64_t* e, uint8_t* st, uint64_t* nf) { return recover_c_host<F61>(c, s, N, n, a, f, e, st, nf); }
+extern "C" int sclgpu_fp127_recover_c(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, void* f, void* e, uint8_t* st, uint64_t* nf) { return recover_c_host<F127>(c, s, N, n, a, f, e, st, nf); }
+extern "C" int sclgpu_fp61_recover_c_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, uint64_t* f, uint64_t* e, uint8_t* st, uint64_t* nf) { return recover_c_dev<F61>(c, s, N, n, layout, a, f, e, st, nf); }
+extern "C" int sclgpu_fp127_recover_c_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, void* f, void* e, uint8_t* st, uint64_t* nf) { return recover_c_dev<F127>(c, s, N, n, layout, a, f, e, st, nf); }
 
 // ------------------------------------------------------------------ vector ops
 template <class F, int OP>

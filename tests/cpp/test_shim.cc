@@ -142,6 +142,40 @@ int main() {
                         "not enough shares provided to detect errors"));
   }
 
+  // ---- test_shamir.cc:111-142: shamirRecoverC corrects <= t errors; beyond that it throws
+  {
+    const std::size_t N = 300, n = 10, t = 3;
+    PRG sprg = PRG::create("secrets");
+    const auto secrets = math::Vector<Fp61>::random(N, sprg);
+    PRG gpu = PRG::create("rc");
+    auto shares = sclgpu::shamirSecretShare(ctx, secrets, t, n, gpu);
+    for (std::size_t j = 0; j < N; ++j)
+      for (std::size_t k = 0; k < j % (t + 2); ++k) shares(j, (3 * k + j) % n) = shares(j, (3 * k + j) % n) + Fp61(j + 1);
+    std::vector<std::uint8_t> status;
+    const auto got = sclgpu::shamirRecoverC(ctx, shares, (const math::Vector<Fp61>*)nullptr, &status);
+    bool any_failed = false;
+    for (std::size_t j = 0; j < N; ++j) {
+      std::vector<Fp61> row(n);
+      for (std::size_t i = 0; i < n; ++i) row[i] = shares(j, i);
+      bool threw = false;
+      ss::ErrorCorrectedSecret<Fp61> want;
+      try {
+        want = ss::shamirRecoverC(math::Vector<Fp61>(row));
+      } catch (const std::logic_error& e) {
+        threw = std::string(e.what()) == "could not correct shares";
+      }
+      REQUIRE(threw == (status[j] != 0));
+      any_failed = any_failed || threw;
+      if (!threw) {
+        REQUIRE(got[j].f.coefficients().equals(want.f.coefficients()));
+        REQUIRE(got[j].err.coefficients().equals(want.err.coefficients()));
+        if (j % (t + 2) <= t) REQUIRE(got[j].f.evaluate(Fp61(0)) == secrets[j]);
+      }
+    }
+    REQUIRE(any_failed);
+    REQUIRE(throwsLogic([&] { (void)sclgpu::shamirRecoverC(ctx, shares); }, "could not correct shares"));
+  }
+
   // ---- per-party packets: what the dealer would build with Packet::write(Vector) on the CPU
   {
     const std::size_t N = 2500, t = 3, n = 7;

@@ -85,6 +85,21 @@ def main():
         g["shamir"].append({"field": field, "t": t, "n": n, "N": N, "seed": seed, "first_block": first,
                             "secrets": hx(secrets, field), "shares": hx(sh, field), "recover_p": hx(rec, field)})
 
+    # --- shamirRecoverC (shamir.h:203-258): 0..t+1 corrupted shares per sharing
+    g["recover_c"] = []
+    for field, n, seed in [(61, 4, "rc4"), (61, 7, "rc7"), (61, 16, "rc16"), (61, 5, "rc5"), (127, 7, "rc127"), (127, 10, "rc10")]:
+        t = (n - 1) // 3
+        N = t + 3
+        secrets = from_ints([1000 + j for j in range(N)], field)
+        sh = r.shamir_share(field, secrets, t, n, seed, 0).copy()
+        flat = sh.reshape(N, n, -1)
+        for j in range(N):                      # sharing j gets j corrupted shares (j = t+1, t+2: beyond the radius)
+            for i in range(min(j, 3 * t + 1)):
+                flat[j, (2 * i + j) % (3 * t + 1), 0] ^= np.uint64(0x10001 + i)
+        f, e, st, nf = r.recover_c(field, sh)
+        g["recover_c"].append({"field": field, "n": n, "N": N, "shares": hx(sh, field), "f": hx(f, field),
+                               "err": hx(e, field), "status": [int(v) for v in st], "n_failed": nf})
+
     # --- additiveShare (additive.h:42-53): n-1 FF::random (one block each) + secret - sum
     g["additive"] = []
     for field, n, N, seed, first in [(61, 3, 4, "additive", 0), (61, 1, 2, "additive", 3), (61, 5, 3, "shamir bench", 1 << 20),

@@ -387,6 +387,67 @@ def test_full_size_c2_properties(ctx, pkg, orc):
     assert torch.equal(d_sum, d_want)
 
 
+# ------------------------------------------------------------------ shamirRecoverC
+def test_recover_c_golden(ctx, port, golden):
+    for c in golden["recover_c"]:
+        f, n, N = c["field"], c["n"], c["N"]
+        sh = unhex(port, c["shares"], f, (N, n))
+        pf, pe, st, nf = ctx.recover_c(f, sh)
+        assert [int(v) for v in st] == c["status"] and nf == c["n_failed"]
+        assert ints(port, pf, f) == [int(h, 16) for h in c["f"]]
+        assert ints(port, pe, f) == [int(h, 16) for h in c["err"]]
+
+
+@pytest.mark.parametrize("field,n,N", [(61, 1, 50), (61, 4, 3000), (61, 7, 2000), (61, 16, 4097), (61, 22, 600), (61, 31, 300),
+                                       (61, 33, 200), (127, 4, 1000), (127, 16, 1500), (127, 31, 150)])
+def test_recover_c_vs_oracle(ctx, pkg, orc, field, n, N):
+    """0..t+1 corrupted shares per sharing; f, err, status and the count against shamirRecoverC of the
+    oracle; default and custom nodes; device-pointer path in both layouts."""
+    import torch
+
+    rng = np.random.default_rng(n)
+    t = (n - 1) // 3
+    sec = orc.vector_random(field, "secrets", 0, N)
+    sh = orc.shamir_share(field, sec, t, n, "rc", 3).copy()
+    flat = sh.reshape(N, n, -1)
+    for j in range(N):
+        k = j % (t + 2)
+        for i in (rng.choice(3 * t + 1, size=min(k, 3 * t + 1), replace=False) if k else []):
+            flat[j, i, rng.integers(flat.shape[2])] ^= np.uint64(1 + j)
+    K = N if orc.kind == "port" or n <= 16 else min(N, 64)
+    want = orc.recover_c(field, sh[:K])
+    got = ctx.recover_c(field, sh)
+    for g, w, name in zip(got[:3], want[:3], ("f", "err", "status")):
+        assert np.array_equal(g[:K], w), (field, n, name)
+    ok = np.array([j % (t + 2) <= t for j in range(N)])   # at most t corrupted shares: must be corrected
+    assert not got[2][ok].any()                            # (beyond the radius the outcome depends on the data)
+    f0 = got[0][:, 0]
+    assert np.array_equal(f0[ok], sec[ok])
+    assert got[3] == int((got[2] != 0).sum())
+    alphas = orc.from_ints([7 * i + 2 for i in range(n)], field)
+    w2, g2 = orc.recover_c(field, sh[:min(K, 256)], alphas), ctx.recover_c(field, sh[:min(K, 256)], alphas)
+    assert all(np.array_equal(a, b) for a, b in zip(g2[:3], w2[:3])) and g2[3] == w2[3]
+    # device pointers
+    ctx.use_torch_stream()
+    w = 1 if field == 61 else 2
+    d_sm = torch.from_numpy(sh.view(np.int64)).cuda()
+    d_pm = torch.from_numpy(np.ascontiguousarray(np.swapaxes(sh.reshape(N, n, w), 0, 1)).view(np.int64)).cuda()
+    for layout, buf in ((pkg.binding.SECRET_MAJOR, d_sm), (pkg.binding.PARTY_MAJOR, d_pm)):
+        d_f = torch.empty((N, 3 * t + 1, w), dtype=torch.int64, device="cuda")
+        d_e = torch.empty((N, t + 1, w), dtype=torch.int64, device="cuda")
+        d_st = torch.empty(N, dtype=torch.uint8, device="cuda")
+        nf = ctx.recover_c_dev(field, buf, N, n, d_f, d_e, d_st, layout)
+        assert nf == got[3]
+        assert np.array_equal(d_f.cpu().numpy().view(np.uint64).reshape(got[0].shape), got[0])
+        assert np.array_equal(d_e.cpu().numpy().view(np.uint64).reshape(got[1].shape), got[1])
+        assert np.array_equal(d_st.cpu().numpy(), got[2])
+
+
+def test_recover_c_errors(ctx, pkg, port):
+    with pytest.raises(pkg.InvalidArgument):
+        ctx.recover_c(61, port.from_ints(list(range(34)), 61).reshape(1, 34))     # 3t+1 = 34 rows > one warp
+
+
 # ------------------------------------------------------------------ Polynomial::evaluate from coefficient planes
 @pytest.mark.parametrize("field,t,n,N", [(61, 15, 32, 5000), (61, 2, 5, 129), (61, 0, 3, 7), (61, 9, 20, 1 << 16),
                                          (127, 7, 16, 3001), (127, 3, 9, 640), (61, 20, 40, 300), (127, 9, 20, 100)])

@@ -121,6 +121,41 @@ def test_golden_shamir(port, golden):
     assert golden["survey_sum_1023"] == "44672d90dd13206"
 
 
+def test_golden_recover_c(port, golden):
+    """shamirRecoverC (Berlekamp-Welch, shamir.h:203-258): vectors recorded from the reference with
+    0..t+2 corrupted shares per sharing (the last two beyond the correction radius)."""
+    for c in golden["recover_c"]:
+        f, n, N = c["field"], c["n"], c["N"]
+        sh = unhex(port, c["shares"], f, (N, n))
+        pf, pe, st, nf = port.recover_c(f, sh)
+        assert [int(v) for v in st] == c["status"] and nf == c["n_failed"], c["n"]
+        assert ints(port, pf, f) == [int(h, 16) for h in c["f"]]
+        assert ints(port, pe, f) == [int(h, 16) for h in c["err"]]
+        t = (n - 1) // 3
+        for j in range(min(N, t + 1)):               # within the radius: the secret is f(0)
+            assert ints(port, pf[j], f)[0] == 1000 + j
+
+
+def test_port_vs_reference_recover_c(port, ref):
+    rng = np.random.default_rng(7)
+    for field in (61, 127):
+        for n in (1, 4, 6, 10, 16, 22, 31):
+            t, N = (n - 1) // 3, 40
+            sec = port.vector_random(field, "secrets", 0, N)
+            sh = port.shamir_share(field, sec, t, n, "rc", 3).copy()
+            flat = sh.reshape(N, n, -1)
+            for j in range(N):
+                k = j % (t + 2)
+                for i in (rng.choice(3 * t + 1, size=min(k, 3 * t + 1), replace=False) if k else []):
+                    flat[j, i, 0] ^= np.uint64(1 + j)
+            a, b = port.recover_c(field, sh), ref.recover_c(field, sh)
+            assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3], (field, n)
+            alphas = port.from_ints([5 * i + 3 for i in range(n)], field)
+            sh2 = sh.copy()                                   # custom nodes: garbage in, same answer out
+            a, b = port.recover_c(field, sh2, alphas), ref.recover_c(field, sh2, alphas)
+            assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3], (field, n, "alphas")
+
+
 def test_golden_additive(port, golden):
     """additiveShare (additive.h:42-53): vectors recorded from the reference; reconstruction = sum."""
     for c in golden["additive"]:
