@@ -60,6 +60,21 @@ shamir("C3_fp127_n16_t7_2^24_recoverD", 127, 16, 7, 1 << 24, True)
 shamir("C3b_fp61_n16_t7_2^24_recoverD", 61, 16, 7, 1 << 24, True)
 torch.cuda.empty_cache()
 
+# shamirRecoverC (Berlekamp-Welch): Fp61 n=16 (t=5), one corrupted share in every second sharing
+Nc, nc_, tc_ = 1 << 20, 16, 5
+sec = i64(Nc); shc = i64(nc_, Nc)
+ctx.random_dev(61, "secrets", 0, Nc, sec)
+ctx.shamir_share_dev(61, sec, Nc, tc_, nc_, "rc", 0, shc, B.PARTY_MAJOR)
+shc[3, ::2] ^= 5
+fo, eo = i64(Nc, 3 * tc_ + 1), i64(Nc, tc_ + 1)
+sto = torch.empty(Nc, dtype=torch.uint8, device=dev)
+r = {"field": 61, "n": nc_, "t": tc_, "N": Nc}
+r["recover_c_ms"] = timeit(lambda: ctx.recover_c_dev(61, shc, Nc, nc_, fo, eo, sto, B.PARTY_MAJOR))
+r["ok"] = bool(torch.equal(fo[:, 0], sec)) and int(sto.sum().item()) == 0
+r["sharings_per_s"] = Nc / (r["recover_c_ms"] * 1e-3)
+res["recoverC_fp61_n16_t5_2^20"] = r
+del sec, shc, fo, eo, sto; torch.cuda.empty_cache()
+
 # C4: PRG -> 2^28 Fp61 elements (2 GiB keystream)
 n4 = 1 << 28
 buf = i64(n4)
