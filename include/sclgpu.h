@@ -317,6 +317,17 @@ int sclgpu_fp61_matvec_dev(sclgpu_ctx* ctx, const uint64_t* d_A, uint32_t rows, 
                            const uint64_t* d_x, uint64_t* d_y);
 int sclgpu_fp127_matvec_dev(sclgpu_ctx* ctx, const void* d_A, uint32_t rows, uint32_t cols,
                             const void* d_x, void* d_y);
+/* matmul: Matrix::multiply(Matrix) (matrix.h:476-495): C (rows x cols) = A (rows x inner) * B (inner x cols),
+ *   all row-major; the host mirror raises "matmul: this->cols() != that->rows()" (matrix.h:480) itself, a zero
+ *   dimension is SCLGPU_EINVAL ("n or m cannot be 0", matrix.h:165). */
+int sclgpu_fp61_matmul(sclgpu_ctx* ctx, const uint64_t* A, uint32_t rows, uint32_t inner, const uint64_t* B,
+                       uint32_t cols, uint64_t* C);
+int sclgpu_fp127_matmul(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t inner, const void* B, uint32_t cols,
+                        void* C);
+int sclgpu_fp61_matmul_dev(sclgpu_ctx* ctx, const uint64_t* d_A, uint32_t rows, uint32_t inner, const uint64_t* d_B,
+                           uint32_t cols, uint64_t* d_C);
+int sclgpu_fp127_matmul_dev(sclgpu_ctx* ctx, const void* d_A, uint32_t rows, uint32_t inner, const void* d_B,
+                            uint32_t cols, void* d_C);
 int sclgpu_fp61_vandermonde(sclgpu_ctx* ctx, uint32_t n, uint32_t m, uint64_t* out);
 int sclgpu_fp127_vandermonde(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out);
 

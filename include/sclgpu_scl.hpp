@@ -26,6 +26,7 @@
 //     -> sclgpu::randomVector<FF>(ctx, n, prg)
 //   Vector add / subtract / multiplyEntryWise / scalarMultiply / dot / sum   vector.h:192-301
 //   Matrix::multiply(Vector)                             matrix.h:498-513
+//   Matrix::multiply(Matrix)                             matrix.h:476-495
 //   Beaver combination e*b + d*a + c + e*d               test/scl/protocol/beaver.h:57-61
 //
 // There is no CPU fallback: Context's constructor throws when no B200 is usable.
@@ -86,6 +87,7 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto dot = &sclgpu_##SUF##_dot;                                                          \
     static constexpr auto sum = &sclgpu_##SUF##_sum;                                                          \
     static constexpr auto matvec = &sclgpu_##SUF##_matvec;                                                    \
+    static constexpr auto matmul = &sclgpu_##SUF##_matmul;                                                    \
   }
 SCLGPU_SCL_ABI(scl::math::ff::Mersenne61, fp61, 8);
 SCLGPU_SCL_ABI(scl::math::ff::Mersenne127, fp127, 16);
@@ -395,6 +397,18 @@ scl::math::Vector<FF> multiply(Context& ctx, const scl::math::Matrix<FF>& A, con
                                     (std::uint32_t)A.rows(), (std::uint32_t)A.cols(),
                                     detail::raw<FF>(x.toStlVector().data()), detail::raw<FF>(y.data())));
   return scl::math::Vector<FF>(std::move(y));
+}
+
+// ---- Matrix::multiply(Matrix), matrix.h:476-495
+template <class FF>
+scl::math::Matrix<FF> multiply(Context& ctx, const scl::math::Matrix<FF>& A, const scl::math::Matrix<FF>& B) {
+  if (A.cols() != B.rows()) throw std::invalid_argument("matmul: this->cols() != that->rows()");  // matrix.h:480
+  scl::math::Matrix<FF> C(A.rows(), B.cols());
+  ctx.check(detail::Abi<FF>::matmul(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(A)(0, 0)),
+                                    (std::uint32_t)A.rows(), (std::uint32_t)A.cols(),
+                                    detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(B)(0, 0)),
+                                    (std::uint32_t)B.cols(), detail::raw<FF>(&C(0, 0))));
+  return C;
 }
 
 }  // namespace sclgpu

@@ -161,6 +161,8 @@ class PortOracle(_Base):
             g("beaver").restype = None
             g("matvec").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp]
             g("matvec").restype = None
+            g("matmul").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
+            g("matmul").restype = None
             g("vandermonde").argtypes = [C.c_uint64, C.c_uint64, _vp]
             g("vandermonde").restype = None
             g("bench_share_recover").argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
@@ -290,6 +292,13 @@ class PortOracle(_Base):
         self._f(field, "matvec")(_p(A), rows, cols, _p(x), _p(y))
         return y
 
+    def matmul(self, field, A, Bm):
+        A, Bm = _c(A), _c(Bm)
+        rows, inner, cols = A.shape[0], A.shape[1], Bm.shape[1]
+        out = empty(field, rows, cols)
+        self._f(field, "matmul")(_p(A), rows, inner, _p(Bm), cols, _p(out))
+        return out
+
     def vandermonde(self, field, n, m):
         out = empty(field, n, m)
         self._f(field, "vandermonde")(n, m, _p(out))
@@ -337,6 +346,8 @@ class RefOracle(_Base):
             g("beaver").restype = None
             g("matvec").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp]
             g("matvec").restype = None
+            g("matmul").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
+            g("matmul").restype = None
             g("vandermonde").argtypes = [C.c_uint64, C.c_uint64, _vp]
             g("vandermonde").restype = None
             g("scalar_op").argtypes = [C.c_int, _vp, _vp, _vp]
@@ -476,6 +487,13 @@ class RefOracle(_Base):
         y = empty(field, rows)
         self._f(field, "matvec")(_p(A), rows, cols, _p(x), _p(y))
         return y
+
+    def matmul(self, field, A, Bm):
+        A, Bm = _c(A), _c(Bm)
+        rows, inner, cols = A.shape[0], A.shape[1], Bm.shape[1]
+        out = empty(field, rows, cols)
+        self._f(field, "matmul")(_p(A), rows, inner, _p(Bm), cols, _p(out))
+        return out
 
     def vandermonde(self, field, n, m):
         out = empty(field, n, m)

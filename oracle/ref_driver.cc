@@ -17,6 +17,7 @@
 //     ss::shamirRecoverC                 (include/scl/ss/shamir.h:203-258)
 //     math::computeLagrangeBasis         (include/scl/math/lagrange.h:55-71)
 //     math::Matrix<T>::multiply(Vector)  (include/scl/math/matrix.h:498-513)
+//     math::Matrix<T>::multiply(Matrix)  (include/scl/math/matrix.h:476-495)
 //     Vector add/subtract/multiplyEntryWise/scalarMultiply/dot/sum
 // All element buffers are the reference's FF::write bytes (little-endian
 // canonical residues, 8 B for Fp<61>, 16 B for Fp<127>).
@@ -287,6 +288,22 @@ void matvec(const unsigned char* A, uint64_t rows, uint64_t cols,
   writeVec(m.multiply(readVec<T>(x, cols)), y);
 }
 
+// Matrix::multiply(Matrix), matrix.h:476-495
+template <typename T>
+void matmul(const unsigned char* A, uint64_t rows, uint64_t inner,
+            const unsigned char* B, uint64_t cols, unsigned char* C) {
+  const auto a = scl::math::Matrix<T>::fromVector(
+      rows, inner, readVec<T>(A, rows * inner).toStlVector());
+  const auto b = scl::math::Matrix<T>::fromVector(
+      inner, cols, readVec<T>(B, inner * cols).toStlVector());
+  const auto c = a.multiply(b);
+  for (uint64_t i = 0; i < rows; ++i) {
+    for (uint64_t j = 0; j < cols; ++j) {
+      c(i, j).write(C + (i * cols + j) * T::byteSize());
+    }
+  }
+}
+
 template <typename T>
 void vandermonde(uint64_t n, uint64_t m, unsigned char* out) {
   const auto v = scl::math::Matrix<T>::vandermonde(n, m);
@@ -436,6 +453,11 @@ double benchShareRecover(uint64_t N, uint64_t t, uint64_t n, int detect,
                              uint64_t cols, const unsigned char* x,            \
                              unsigned char* y) {                               \
     matvec<T>(A, rows, cols, x, y);                                            \
+  }                                                                            \
+  void sclref_##SUF##_matmul(const unsigned char* A, uint64_t rows,            \
+                             uint64_t inner, const unsigned char* B,           \
+                             uint64_t cols, unsigned char* C) {                \
+    matmul<T>(A, rows, inner, B, cols, C);                                     \
   }                                                                            \
   void sclref_##SUF##_vandermonde(uint64_t n, uint64_t m,                      \
                                   unsigned char* out) {                        \

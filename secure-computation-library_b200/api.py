@@ -390,6 +390,19 @@ class Context:
         self._check(self._f(field, "matvec")(self._ctx, _p(A), rows, cols, _p(x), _p(y)))
         return y
 
+    def matmul(self, field: int, A, Bm) -> np.ndarray:
+        """Matrix::multiply(Matrix) (matrix.h:476-495)."""
+        A, Bm = _c(A), _c(Bm)
+        if A.shape[1] != Bm.shape[0]:
+            raise InvalidArgument("matmul: this->cols() != that->rows()")
+        rows, inner, cols = A.shape[0], A.shape[1], Bm.shape[1]
+        out = empty(field, rows, cols)
+        self._check(self._f(field, "matmul")(self._ctx, _p(A), rows, inner, _p(Bm), cols, _p(out)))
+        return out
+
+    def matmul_dev(self, field: int, A, rows: int, inner: int, Bm, cols: int, out):
+        self._check(self._f(field, "matmul_dev")(self._ctx, _dp(A), rows, inner, _dp(Bm), cols, _dp(out)))
+
     def matvec_dev(self, field: int, A, rows: int, cols: int, x, y):
         self._check(self._f(field, "matvec_dev")(self._ctx, _dp(A), rows, cols, _dp(x), _dp(y)))
 

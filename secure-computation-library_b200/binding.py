@@ -83,6 +83,7 @@ def load() -> C.CDLL:
             _sig(lib, f"sclgpu_{f}_dot{suf}", _int, _vp, _vp, _vp, _u64, _vp)
             _sig(lib, f"sclgpu_{f}_sum{suf}", _int, _vp, _vp, _u64, _vp)
             _sig(lib, f"sclgpu_{f}_matvec{suf}", _int, _vp, _vp, _u32, _u32, _vp, _vp)
+            _sig(lib, f"sclgpu_{f}_matmul{suf}", _int, _vp, _vp, _u32, _u32, _vp, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_shamir_share", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_shamir_share_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _int)
         _sig(lib, f"sclgpu_{f}_shamir_share_coeffs_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _int)

@@ -1,0 +1,295 @@
+// matmul_tc.cu -- Matrix<Fp61>::multiply(Matrix) (include/scl/math/matrix.h:476-495) on the
+// 5th-generation tensor cores, and a generic integer-pipe kernel for every other case.
+//
+// Same byte-limb identity as the Shamir kernels (share_tc.cu): with a_{ik} = sum_a a_{ik,a} 2^(8a)
+// (the eight bytes of the canonical residue) and C_{kj,a} = b_{kj} 2^(8a) mod p = sum_s C_{kj,a,s} 2^(8s)
+//     (A B)_{ij} = sum_s 2^(8s) * acc_{ij,s},    acc_{ij,s} = sum_{k,a} a_{ik,a} * C_{kj,a,s}
+// which is a u8 x u8 -> s32 GEMM with inner dimension 8K (exact while 8K * 255^2 < 2^31, i.e. up to
+// 4096 elements of K per accumulation round).  B is expanded ONCE into that limb image
+// (k_matmul61_prep: 64 bytes per element, stored tile by tile in the canonical 128B-swizzled
+// K-major layout tcgen05 reads), A is used as it lies in memory: a row-major row of A is already a
+// K-major operand row.
+//
+// k_matmul61_tc: one CTA per 128 x 32 tile of the result.  Per 16-element chunk of K (128 bytes of
+// an A row): cp.async brings the A chunk (16 KiB, swizzled on the fly) and the matching 32 KiB of
+// the limb image into a 4-stage shared-memory ring; one thread issues four
+// tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32 bytes) accumulating in 256 TMEM columns;
+// tcgen05.commit frees the stage.  Epilogue: each of 128 threads drains its TMEM lane, recombines
+// 32 x 8 limbs mod 2^61 - 1 and writes its 32 outputs (one 256-byte row segment).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "field.cuh"
+#include "matmul_tc.h"
+
+namespace sclgpu {
+
+static constexpr uint32_t kMmThreads = 256;
+static constexpr uint32_t kMmStages = 4;
+static constexpr uint32_t kMmATile = 128u * 128u;                    // 128 rows x 16 elements
+static constexpr uint32_t kMmStage = kMmATile + kMmBTileBytes;        // 48 KiB
+static constexpr uint32_t kMmDynSmem = kMmStages * kMmStage + 1024u + 256u;
+static constexpr uint32_t kMmRoundChunks = 4096u / kMmKChunk;         // accumulation round: 4096 elements of K
+
+__device__ __forceinline__ uint32_t mm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t mm_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B, SBO = 1024 B, sm_100 version
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// D = s32, A = B = u8, K-major, M = 128, N = 256
+static constexpr uint32_t kMmIdesc = (2u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void mm_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(kMmIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mm_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mm_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mm_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {  // src_bytes 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mm_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// sum_s v[s] * 2^(8s) mod p for v[s] < 2^31 (a full 4096-element round): 64-bit pieces, 2^61 = 1
+__device__ __forceinline__ uint64_t mm_combine(const uint32_t* v) {
+  uint64_t lo = 0, hi = 0;  // value = lo + hi * 2^32, each a sum of four terms < 2^55
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    lo += (uint64_t)v[s] << (8 * s);
+    hi += (uint64_t)v[4 + s] << (8 * s);
+  }
+  // hi * 2^32: (hi mod 2^29) * 2^32 + (hi >> 29) * 2^61
+  const uint64_t R = lo + ((hi & 0x1FFFFFFFull) << 32) + (hi >> 29);  // < 2^56 + 2^61 + 2^27
+  const uint64_t r = (R & F61::P) + (R >> 61);
+  return r >= F61::P ? r - F61::P : r;
+}
+
+// ---- limb image of B: tile (jt, kc) = 32 columns x 16 rows of B -> 256 x 128 bytes, stored at
+// ((jt * KC) + kc) * 32 KiB in the canonical swizzled layout.  Thread = one element of the padded B.
+__global__ void __launch_bounds__(256)
+k_matmul61_prep(const uint64_t* __restrict__ B, uint32_t K, uint32_t N, uint32_t KC, uint32_t NT, uint8_t* __restrict__ img) {
+  const uint64_t total = (uint64_t)KC * kMmKChunk * NT * kMmNTile;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const uint32_t j = (uint32_t)(idx % ((uint64_t)NT * kMmNTile));
+    const uint32_t k = (uint32_t)(idx / ((uint64_t)NT * kMmNTile));
+    uint64_t c = (k < K && j < N) ? B[(uint64_t)k * N + j] : 0;
+    uint64_t ca[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      ca[a] = c;
+      c = F61::mul(c, 256);
+    }
+    uint8_t* tile = img + ((uint64_t)(j / kMmNTile) * KC + k / kMmKChunk) * kMmBTileBytes;
+    const uint32_t jl = j % kMmNTile, kl = k % kMmKChunk;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      uint64_t w = 0;  // bytes a = 0..7 of row (jl, s): byte_s(C_a)
+#pragma unroll
+      for (int a = 0; a < 8; ++a) w |= ((ca[a] >> (8 * s)) & 0xFFull) << (8 * a);
+      const uint32_t r = jl * 8 + s, kk = kl * 8;
+      *reinterpret_cast<uint64_t*>(tile + (r >> 3) * 1024u + (r & 7u) * 128u + (((kk >> 4) ^ (r & 7u)) << 4) + (kk & 15u)) = w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMmThreads, 1)
+k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint8_t* __restrict__ img, uint32_t KC,
+              uint32_t N, uint64_t* __restrict__ C) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t base = (mm_smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t ctl = base + kMmStages * kMmStage;  // empty[stage] mbarriers, done mbarrier, TMEM address
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t m0 = blockIdx.y * 128u, jt = blockIdx.x;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(ctl + 64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint32_t i = 0; i <= kMmStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctl + 8u * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(ctl + 64u) : "memory");
+  const uint32_t done_bar = ctl + 8u * kMmStages;
+
+  const uint8_t* img_row = img + (uint64_t)jt * KC * kMmBTileBytes;
+  auto load_chunk = [&](uint32_t kc) {
+    const uint32_t st = base + (kc % kMmStages) * kMmStage;
+    // A: 128 rows x 8 sixteen-byte pieces
+#pragma unroll
+    for (uint32_t q = tid; q < 1024u; q += kMmThreads) {
+      const uint32_t row = q >> 3, piece = q & 7u;
+      const uint32_t k = kc * kMmKChunk + piece * 2u;
+      const bool in = (m0 + row < M) && (k < K);  // K is even: a piece is inside or outside as a whole
+      const uint64_t* src = A + (uint64_t)(in ? m0 + row : 0) * K + (in ? k : 0);
+      mm_cp16(st + (row >> 3) * 1024u + (row & 7u) * 128u + ((piece ^ (row & 7u)) << 4), src, in ? 16u : 0u);
+    }
+    // limb image tile: already in shared-memory layout
+    const uint8_t* bsrc = img_row + (uint64_t)kc * kMmBTileBytes;
+#pragma unroll
+    for (uint32_t q = tid; q < kMmBTileBytes / 16u; q += kMmThreads) mm_cp16(st + kMmATile + q * 16u, bsrc + q * 16u, 16u);
+  };
+
+  uint64_t acc[kMmNTile];
+#pragma unroll
+  for (uint32_t j = 0; j < kMmNTile; ++j) acc[j] = 0;
+  uint32_t done_phase = 0;
+  // empty[s] completes once per chunk that used stage s (tcgen05.commit after its MMAs), in chunk order:
+  // before chunk kc (>= stages) may overwrite its stage, completion number kc/stages - 1 must have happened
+  auto wait_stage_free = [&](uint32_t kc) {
+    if (kc >= kMmStages) mm_wait(ctl + 8u * (kc % kMmStages), ((kc / kMmStages) - 1u) & 1u);
+  };
+
+  for (uint32_t r0 = 0; r0 < KC; r0 += kMmRoundChunks) {
+    const uint32_t r1 = min(r0 + kMmRoundChunks, KC);
+    // prologue: stages - 1 chunks in flight
+    for (uint32_t p = 0; p < kMmStages - 1; ++p) {
+      const uint32_t kc = r0 + p;
+      if (kc < r1) {
+        wait_stage_free(kc);
+        load_chunk(kc);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (uint32_t kc = r0; kc < r1; ++kc) {
+      const uint32_t nx = kc + kMmStages - 1;
+      if (nx < r1) {
+        wait_stage_free(nx);
+        load_chunk(nx);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kMmStages - 1) : "memory");  // this thread's pieces of chunk kc landed
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = base + (kc % kMmStages) * kMmStage;
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) mm_mma(tmem, mm_desc(st + ks * 32u), mm_desc(st + kMmATile + ks * 32u), (kc > r0) | ks);
+        mm_commit(ctl + 8u * (kc % kMmStages));
+        if (kc + 1 == r1) mm_commit(done_bar);
+      }
+    }
+    // drain this accumulation round (at most 4096 elements of K: the s32 accumulators are exact)
+    mm_wait(done_bar, done_phase);
+    done_phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+      const uint32_t lane_off = (warp * 32u) << 16;
+#pragma unroll
+      for (uint32_t g = 0; g < 8; ++g) {
+        uint32_t v[32];
+        mm_tmem_ld32(tmem + lane_off + g * 32u, v);
+#pragma unroll
+        for (uint32_t jj = 0; jj < 4; ++jj) acc[g * 4 + jj] = F61::add(acc[g * 4 + jj], mm_combine(v + 8 * jj));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // TMEM drained before the next round overwrites it
+  }
+  if (warp < 4) {
+    const uint32_t row = m0 + tid;
+    if (row < M) {
+      uint64_t* dst = C + (uint64_t)row * N + (uint64_t)jt * kMmNTile;
+#pragma unroll
+      for (uint32_t j = 0; j < kMmNTile; ++j)
+        if (jt * kMmNTile + j < N) dst[j] = acc[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---- generic kernel (any field, any shape): thread = one output element, lazy accumulation
+template <class F>
+__global__ void __launch_bounds__(256)
+k_matmul_generic(const typename F::E* __restrict__ A, uint32_t M, uint32_t K, const typename F::E* __restrict__ B, uint32_t N,
+                 typename F::E* __restrict__ C) {
+  const uint64_t total = (uint64_t)M * N;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const uint32_t i = (uint32_t)(idx / N), j = (uint32_t)(idx % N);
+    typename F::Acc acc = F::acc_zero();
+    int terms = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+      F::mac(acc, A[(uint64_t)i * K + k], B[(uint64_t)k * N + j]);
+      if (++terms == F::ACC_TERMS - 1) {
+        F::acc_fold(acc);
+        terms = 0;
+      }
+    }
+    C[idx] = F::acc_reduce(acc);
+  }
+}
+
+size_t matmul61_image_bytes(uint32_t K, uint32_t N) {
+  const uint64_t KC = (K + kMmKChunk - 1) / kMmKChunk, NT = (N + kMmNTile - 1) / kMmNTile;
+  return (size_t)(KC * NT * kMmBTileBytes);
+}
+
+cudaError_t matmul61_tc_launch(cudaStream_t st, int sm_count, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B,
+                               uint32_t N, uint8_t* d_img, uint64_t* d_C) {
+  const uint32_t KC = (K + kMmKChunk - 1) / kMmKChunk, NT = (N + kMmNTile - 1) / kMmNTile;
+  const uint64_t total = (uint64_t)KC * kMmKChunk * NT * kMmNTile;
+  const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sm_count * 8);
+  k_matmul61_prep<<<pgrid, 256, 0, st>>>(d_B, K, N, KC, NT, d_img);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_matmul61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmDynSmem);
+  if (e != cudaSuccess) return e;
+  const dim3 grid(NT, (M + 127) / 128);
+  k_matmul61_tc<<<grid, kMmThreads, kMmDynSmem, st>>>(d_A, M, K, d_img, KC, N, d_C);
+  return cudaGetLastError();
+}
+
+cudaError_t matmul61_generic_launch(cudaStream_t st, int sm_count, const uint64_t* A, uint32_t M, uint32_t K, const uint64_t* B,
+                                    uint32_t N, uint64_t* C) {
+  const uint64_t total = (uint64_t)M * N;
+  k_matmul_generic<F61><<<(int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sm_count * 8), 256, 0, st>>>(A, M, K, B, N, C);
+  return cudaGetLastError();
+}
+cudaError_t matmul127_generic_launch(cudaStream_t st, int sm_count, const E127* A, uint32_t M, uint32_t K, const E127* B, uint32_t N,
+                                     E127* C) {
+  const uint64_t total = (uint64_t)M * N;
+  k_matmul_generic<F127><<<(int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sm_count * 8), 256, 0, st>>>(A, M, K, B, N, C);
+  return cudaGetLastError();
+}
+
+}  // namespace sclgpu

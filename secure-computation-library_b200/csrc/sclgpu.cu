@@ -19,6 +19,7 @@
 
 #include "../../include/sclgpu.h"
 #include "kernels.cuh"
+#include "matmul_tc.h"
 #include "share_tc.h"
 
 using namespace sclgpu;
@@ -164,6 +165,13 @@ extern "C" int sclgpu_init(int device, sclgpu_ctx** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   aes_host_init();
+  {  // stream-ordered scratch (cudaMallocAsync in matmul_on) stays cached in the device's pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   bool ok = cudaMalloc(&ctx->d_t0, sizeof(g_t0)) == cudaSuccess &&
             cudaMemcpy(ctx->d_t0, g_t0, sizeof(g_t0), cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMalloc(&ctx->d_flag, sizeof(int)) == cudaSuccess &&
@@ -1612,6 +1620,61 @@ static int matvec_host(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t c
   RET(matvec_on<F>(ctx, hop.st, (const E*)dA, rows, cols, (const E*)dx, (E*)dy));
   return hop.down(y, dy, (size_t)rows * sizeof(E));
 }
+// Matrix::multiply(Matrix), matrix.h:476-495: C (rows x cols) = A (rows x inner) * B (inner x cols), row-major
+template <class F>
+static int matmul_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, uint32_t rows, uint32_t inner,
+                     const typename F::E* B, uint32_t cols, typename F::E* C) {
+  ctx->launches++;
+  cudaError_t e;
+  if constexpr (F::BYTES == 8) {
+    const bool tc = (inner % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (uint64_t)rows * cols * inner >= (1ull << 18) &&
+                    getenv("SCLGPU_MATMUL_GENERIC") == nullptr;
+    if (tc) {
+      void* img = nullptr;
+      CK(cudaMallocAsync(&img, matmul61_image_bytes(inner, cols), st));
+      ctx->launches++;
+      e = matmul61_tc_launch(st, ctx->sm_count, A, rows, inner, B, cols, (uint8_t*)img, C);
+      cudaFreeAsync(img, st);
+    } else {
+      e = matmul61_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
+    }
+  } else {
+    e = matmul127_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
+  }
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int matmul_dev(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t inner, const void* B, uint32_t cols, void* C) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (rows == 0 || inner == 0 || cols == 0) return fail(ctx, SCLGPU_EINVAL, "n or m cannot be 0");
+  if (!A || !B || !C) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return matmul_on<F>(ctx, ctx->stream, (const E*)A, rows, inner, (const E*)B, cols, (E*)C);
+}
+
+template <class F>
+static int matmul_host(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t inner, const void* B, uint32_t cols, void* C) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (rows == 0 || inner == 0 || cols == 0) return fail(ctx, SCLGPU_EINVAL, "n or m cannot be 0");
+  if (!A || !B || !C) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  HostOp hop(ctx);
+  void *dA, *dB, *dC;
+  RET(hop.up(A, (size_t)rows * inner * sizeof(E), &dA));
+  RET(hop.up(B, (size_t)inner * cols * sizeof(E), &dB));
+  RET(hop.dev((size_t)rows * cols * sizeof(E), &dC));
+  RET(matmul_on<F>(ctx, hop.st, (const E*)dA, rows, inner, (const E*)dB, cols, (E*)dC));
+  return hop.down(C, dC, (size_t)rows * cols * sizeof(E));
+}
+extern "C" int sclgpu_fp61_matmul(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* B, uint32_t n, uint64_t* C) { return matmul_host<F61>(c, A, r, k, B, n, C); }
+extern "C" int sclgpu_fp127_matmul(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* B, uint32_t n, void* C) { return matmul_host<F127>(c, A, r, k, B, n, C); }
+extern "C" int sclgpu_fp61_matmul_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* B, uint32_t n, uint64_t* C) { return matmul_dev<F61>(c, A, r, k, B, n, C); }
+extern "C" int sclgpu_fp127_matmul_dev(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* B, uint32_t n, void* C) { return matmul_dev<F127>(c, A, r, k, B, n, C); }
+
 extern "C" int sclgpu_fp61_matvec(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return matvec_host<F61>(c, A, r, k, x, y); }
 extern "C" int sclgpu_fp127_matvec(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return matvec_host<F127>(c, A, r, k, x, y); }
 extern "C" int sclgpu_fp61_matvec_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return matvec_dev<F61>(c, A, r, k, x, y); }

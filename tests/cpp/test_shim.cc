@@ -258,6 +258,15 @@ int main() {
     REQUIRE(y.equals(A.multiply(x)));
     REQUIRE(y[0].toString() == "1172bf06cc5d2e8b");  // SURVEY 8c golden vector
     REQUIRE(throwsInvalid([&] { (void)sclgpu::multiply(ctx, A, v); }, "matmul: this->cols() != vec.size()"));
+    // test_matrix.cc:175-222 (mat-mul) on a size that takes the tensor-core path, and a small Fp127 one
+    PRG mb = PRG::create("mat B");
+    const auto A2 = math::Matrix<Fp61>::random(130, 96, ma);
+    const auto B2 = math::Matrix<Fp61>::random(96, 70, mb);
+    REQUIRE(sclgpu::multiply(ctx, A2, B2).equals(A2.multiply(B2)));
+    const auto A3 = math::Matrix<Fp127>::random(9, 5, ma);
+    const auto B3 = math::Matrix<Fp127>::random(5, 11, mb);
+    REQUIRE(sclgpu::multiply(ctx, A3, B3).equals(A3.multiply(B3)));
+    REQUIRE(throwsInvalid([&] { (void)sclgpu::multiply(ctx, A2, A2); }, "matmul: this->cols() != that->rows()"));
   }
   std::printf("SHIM_OK checks=%d launches=%llu\n", g_checks, (unsigned long long)ctx.launches());
   return 0;

@@ -258,6 +258,43 @@ def test_matvec_golden_and_vs_oracle(ctx, orc, port, golden):
         assert np.array_equal(ctx.matvec(field, A, x), orc.matvec(field, A, x)), (field, rows, cols)
 
 
+@pytest.mark.parametrize("field,rows,inner,cols", [
+    (61, 128, 16, 32), (61, 1, 2, 1), (61, 300, 520, 70), (61, 129, 4100, 33), (61, 64, 8200, 40), (61, 257, 130, 257),
+    (61, 5, 7, 3), (61, 200, 333, 100), (127, 40, 50, 30), (127, 3, 1, 2)])
+def test_matmul_vs_oracle(ctx, pkg, port, field, rows, inner, cols):
+    """Matrix::multiply(Matrix) (matrix.h:476-495).  Fp61 with even inner dimension runs on the tensor cores
+    (inner > 4096: more than one accumulation round; ragged tiles in every dimension), everything else on the
+    integer pipe; edge residues 0, 1, p-1 planted in both operands."""
+    sh = () if field == 61 else (2,)
+    A = port.vector_random(field, "mat A", 0, rows * inner).reshape((rows, inner) + sh).copy()
+    Bm = port.vector_random(field, "mat B", 7, inner * cols).reshape((inner, cols) + sh).copy()
+    pm1 = port.from_ints([P[field] - 1, 0, 1], field)
+    A[0, 0], Bm[0, 0] = pm1[0], pm1[0]
+    A[rows - 1, inner - 1], Bm[inner - 1, cols - 1] = pm1[0], pm1[2]
+    A[rows // 2, inner // 2] = pm1[1]
+    got = ctx.matmul(field, A, Bm)
+    assert np.array_equal(got, port.matmul(field, A, Bm)), (field, rows, inner, cols)
+
+
+def test_matmul_all_max_residues(ctx, port):
+    """every product is (p-1)^2 = 1: the limb accumulators run at their maximum (255 * 255 per byte pair)"""
+    rows, inner, cols = 128, 4096, 32
+    A = np.full((rows, inner), P[61] - 1, dtype=np.uint64)
+    Bm = np.full((inner, cols), P[61] - 1, dtype=np.uint64)
+    got = ctx.matmul(61, A, Bm)
+    assert np.all(got == np.uint64(inner % P[61]))
+
+
+def test_matmul_errors_and_golden_identity(ctx, pkg, port):
+    with pytest.raises(pkg.InvalidArgument, match="this->cols\\(\\) != that->rows\\(\\)"):
+        ctx.matmul(61, np.zeros((2, 3), dtype=np.uint64), np.zeros((4, 2), dtype=np.uint64))
+    # test_matrix.cc:342-365: Vandermonde * coefficients = polynomial evaluations = the shares
+    V = ctx.vandermonde(61, 32, 16)                                   # 32 x 16
+    coeffs = port.vector_random(61, "coeffs", 0, 16 * 40).reshape(16, 40)
+    sh = ctx.matmul(61, V, coeffs)                                   # 32 x 40: column j = shares of polynomial j
+    assert np.array_equal(sh, port.matmul(61, V, coeffs))
+
+
 def test_matvec_and_vandermonde_errors(ctx, pkg, port, golden):
     with pytest.raises(pkg.InvalidArgument, match="n or m cannot be 0"):
         ctx.vandermonde(61, 0, 3)

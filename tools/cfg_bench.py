@@ -104,4 +104,12 @@ r["vec_mul_GBps"] = 24 * n5 / r["vec_mul_ms"] / 1e6
 r["dot_ms"] = timeit(lambda: ctx.vec_op_dev(61, 4, vs[0], vs[1], n5, vs[5]))
 r["dot_GBps"] = 16 * n5 / r["dot_ms"] / 1e6
 res["C5_fp61_matvec_muladd"] = r
+# Matrix::multiply(Matrix), Fp61, square
+del vs; torch.cuda.empty_cache()
+for dim in (2048, 4096, 8192):
+    A, Bm, Cm = i64(dim, dim), i64(dim, dim), i64(dim, dim)
+    ctx.random_dev(61, "mat A", 0, dim * dim, A); ctx.random_dev(61, "mat B", 0, dim * dim, Bm)
+    ms = timeit(lambda: ctx.matmul_dev(61, A, dim, dim, Bm, dim, Cm))
+    res[f"matmul_fp61_{dim}"] = {"ms": ms, "field_mults_per_s": dim ** 3 / (ms * 1e-3), "int8_TOPS": 128 * dim ** 3 / (ms * 1e-3) / 1e12}
+    del A, Bm, Cm; torch.cuda.empty_cache()
 print(json.dumps(res, indent=1))
