@@ -383,7 +383,7 @@ def test_sharded_gpu_engine(ctx, pkg, orc):
 
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_c2_properties(ctx, pkg, orc):
-    """BASELINE config C2 at a large size (2^24 secrets per pass here; bench.py runs 2^26):
+    """BASELINE config C2 at its full size (2^26 secrets, n=32, t=15: 16 GiB of shares per pass):
     (i) share -> recoverP round trip returns every secret, (ii) a prefix and strided
     samples equal the oracle bit for bit, (iii) linearity: share(a)+share(b) over the
     same coefficients... is checked through sum of shares == share of sums at x (party) level
@@ -392,7 +392,7 @@ def test_full_size_c2_properties(ctx, pkg, orc):
 
     ctx.use_torch_stream()
     B = pkg.binding
-    field, t, n, N = 61, 15, 32, 1 << 24
+    field, t, n, N = 61, 15, 32, 1 << 26
     d_sec = torch.empty(N, dtype=torch.int64, device="cuda")
     ctx.random_dev(61, "secrets", 0, N, d_sec)
     d_sh = torch.empty((n, N), dtype=torch.int64, device="cuda")
@@ -596,3 +596,110 @@ def test_share_kernel_paths_vs_oracle(tc):
     r = subprocess.run([sys.executable, os.path.join(repo, "tools", "tc_check.py")], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "TC_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ------------------------------------------------------------------ full-size properties, configs C3 / C4 / C5
+def test_full_size_c3_fp127_recover_d_tamper_set(ctx, pkg, orc, port):
+    """BASELINE config C3 at its full size: Fp127 n=16 t=7, 2^24 secrets, share -> recoverD with the tamper
+    set of SURVEY 8d (one flipped share at idx in {0, 8, 13, 14, 15} for 1/1024 of the secrets): idx 14 and 15
+    are never checked by the reference (shamir.h:129) and must stay undetected, the others must be flagged."""
+    import torch
+
+    ctx.use_torch_stream()
+    B = pkg.binding
+    N, n, t = 1 << 24, 16, 7
+    d_sec = torch.empty((N, 2), dtype=torch.int64, device="cuda")
+    ctx.random_dev(127, "secrets127", 0, N, d_sec)
+    d_sh = torch.empty((n, N, 2), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_dev(127, d_sec, N, t, n, "shamir bench", 0, d_sh, B.PARTY_MAJOR)
+    # prefix + far slice against the oracle
+    K = 512
+    sec_h = d_sec[:K].cpu().numpy().view(np.uint64)
+    want = orc.shamir_share(127, sec_h, t, n, "shamir bench", 0)
+    assert np.array_equal(d_sh[:, :K].permute(1, 0, 2).contiguous().cpu().numpy().view(np.uint64), want)
+    lo = N - K
+    sec_h = d_sec[lo:].cpu().numpy().view(np.uint64)
+    want = port.shamir_share(127, sec_h, t, n, "shamir bench", lo * 8)
+    assert np.array_equal(d_sh[:, lo:].permute(1, 0, 2).contiguous().cpu().numpy().view(np.uint64), want)
+    # tamper: secret j = 1024*k gets share idxs[k % 5] flipped
+    idxs = [0, 8, 13, 14, 15]
+    js = torch.arange(0, N, 1024, device="cuda")
+    which = torch.tensor(idxs, device="cuda")[torch.arange(js.numel(), device="cuda") % 5]
+    d_sh[which, js, 0] ^= 1
+    d_out = torch.empty((N, 2), dtype=torch.int64, device="cuda")
+    d_err = torch.empty(N, dtype=torch.uint8, device="cuda")
+    nd = ctx.recover_d_dev(127, d_sh, N, n, t, d_out, d_err, B.PARTY_MAJOR)
+    detected = which < 14                                   # idx 0, 8, 13 are read and checked
+    assert nd == int(detected.sum())
+    flags = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    flags[js[detected]] = 1
+    assert torch.equal(d_err, flags)
+    good = flags == 0
+    assert torch.equal(d_out[good], d_sec[good])            # untouched and UNDETECTED-tampered sharings recover
+    assert int(d_out[~good].abs().sum()) == 0               # flagged ones are zeroed
+    # the same 64 tampered sharings through the oracle
+    pick = js[:64].cpu().numpy()
+    sm = d_sh[:, js[:64]].permute(1, 0, 2).contiguous().cpu().numpy().view(np.uint64)
+    o_out, o_err, o_nd = orc.recover_d(127, sm, t)
+    assert np.array_equal(o_err, d_err[js[:64]].cpu().numpy()) and np.array_equal(o_out, d_out[js[:64]].cpu().numpy().view(np.uint64))
+
+
+def test_full_size_c4_prg_expansion(ctx, pkg, orc, port):
+    """C4: Vector<Fp61>::random of 2^28 elements (2 GiB of keystream): prefix against the real oracle, far
+    slices against the seekable port, and the raw-keystream kernel against the element kernel on every element
+    (from_bytes of the former must equal the latter)."""
+    import torch
+
+    ctx.use_torch_stream()
+    n = 1 << 28
+    d_el = torch.empty(n, dtype=torch.int64, device="cuda")
+    ctx.random_dev(61, "prg bench", 0, n, d_el)
+    K = 1 << 16
+    assert np.array_equal(d_el[:K].cpu().numpy().view(np.uint64), orc.vector_random(61, "prg bench", 0, K))
+    for lo in (n // 2 - 6, n - K):
+        lo -= lo % 2
+        assert np.array_equal(d_el[lo:lo + K].cpu().numpy().view(np.uint64), port.vector_random(61, "prg bench", lo // 2, K))
+    d_raw = torch.empty(n, dtype=torch.int64, device="cuda")
+    ctx.prg_expand_dev("prg bench", 0, 8 * n, d_raw)
+    d_chk = torch.empty(n, dtype=torch.int64, device="cuda")
+    ctx.lib.sclgpu_fp61_from_bytes_dev(ctx._ctx, d_raw.data_ptr(), n, d_chk.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(d_chk, d_el)
+
+
+def test_full_size_c5_matvec_and_muladd(ctx, pkg, port):
+    """C5: Fp61 mat-vec 8192 x 8192 against the oracle on every row, and the Beaver combination on 2^26
+    elements against the oracle on a prefix / far slice plus an algebraic identity on everything:
+    z - c = e*(b+d) + d*a."""
+    import torch
+
+    ctx.use_torch_stream()
+    rows = cols = 8192
+    d_A = torch.empty((rows, cols), dtype=torch.int64, device="cuda")
+    d_x = torch.empty(cols, dtype=torch.int64, device="cuda")
+    d_y = torch.empty(rows, dtype=torch.int64, device="cuda")
+    ctx.random_dev(61, "mat A", 0, rows * cols, d_A)
+    ctx.random_dev(61, "vec x", 0, cols, d_x)
+    ctx.matvec_dev(61, d_A, rows, cols, d_x, d_y)
+    torch.cuda.synchronize()
+    want = port.matvec(61, d_A.cpu().numpy().view(np.uint64), d_x.cpu().numpy().view(np.uint64))
+    assert np.array_equal(d_y.cpu().numpy().view(np.uint64), want)
+    del d_A
+    n = 1 << 26
+    v = {k: torch.empty(n, dtype=torch.int64, device="cuda") for k in "ebdacz"}
+    for k in "ebdac":
+        ctx.random_dev(61, k, 0, n, v[k])
+    ctx.beaver_dev(61, v["e"], v["b"], v["d"], v["a"], v["c"], n, v["z"])
+    torch.cuda.synchronize()
+    K = 1 << 16
+    for lo in (0, n - K):
+        h = {k: v[k][lo:lo + K].cpu().numpy().view(np.uint64) for k in "ebdacz"}
+        assert np.array_equal(h["z"], port.beaver(61, h["e"], h["b"], h["d"], h["a"], h["c"]))
+    t1, t2, lhs = (torch.empty(n, dtype=torch.int64, device="cuda") for _ in range(3))
+    ctx.vec_op_dev(61, 0, v["b"], v["d"], n, t1)        # b + d
+    ctx.vec_op_dev(61, 2, v["e"], t1, n, t1)            # e * (b + d)
+    ctx.vec_op_dev(61, 2, v["d"], v["a"], n, t2)        # d * a
+    ctx.vec_op_dev(61, 0, t1, t2, n, t1)
+    ctx.vec_op_dev(61, 1, v["z"], v["c"], n, lhs)       # z - c
+    torch.cuda.synchronize()
+    assert torch.equal(lhs, t1)
