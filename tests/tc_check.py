@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Development check of the active Fp61 share kernel against the plain-C oracle on a
+"""TEST HELPER (run by tests/test_gpu_parity.py in a subprocess): the active share kernels against the plain-C oracle on a
 sweep of (t, n, N), device-pointer path, both layouts.  Usage: tc_check.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

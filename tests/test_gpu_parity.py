@@ -583,7 +583,7 @@ def test_additive_errors(ctx, pkg, port):
 # ------------------------------------------------------------------ both Fp61 share kernels
 @pytest.mark.parametrize("tc", ["3", "2", "1", "0"])
 def test_share_kernel_paths_vs_oracle(tc):
-    """tools/tc_check.py sweeps (t, n, N) on the device-pointer path against the plain-C oracle;
+    """tests/tc_check.py sweeps (t, n, N) on the device-pointer path against the plain-C oracle;
     SCLGPU_SHARE_TC selects the tcgen05 kernels (3 = default: A operand in tensor memory, 5 groups;
     2 = 4 groups; 1 = A operand in shared memory) or the integer-pipe kernel (0).
     A separate process because the library reads the knob once."""
@@ -593,7 +593,7 @@ def test_share_kernel_paths_vs_oracle(tc):
 
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, SCLGPU_SHARE_TC=tc)
-    r = subprocess.run([sys.executable, os.path.join(repo, "tools", "tc_check.py")], env=env, capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(repo, "tests", "tc_check.py")], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "TC_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
