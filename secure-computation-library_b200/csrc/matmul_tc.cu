@@ -27,11 +27,15 @@
 namespace sclgpu {
 
 static constexpr uint32_t kMmThreads = 256;
-static constexpr uint32_t kMmStages = 4;
 static constexpr uint32_t kMmATile = 128u * 128u;                    // 128 rows x 16 elements
-static constexpr uint32_t kMmStage = kMmATile + kMmBTileBytes;        // 48 KiB
-static constexpr uint32_t kMmDynSmem = kMmStages * kMmStage + 1024u + 256u;
+// RT = row tiles (of 128) per CTA: 1 -> 4 stages of 48 KiB, 2 -> 3 stages of 64 KiB (the image chunk is shared)
+template <int RT> struct MmCfg {
+  static constexpr uint32_t kStages = RT == 1 ? 4u : 3u;
+  static constexpr uint32_t kStage = RT * kMmATile + kMmBTileBytes;
+  static constexpr uint32_t kDynSmem = kStages * kStage + 1024u + 256u;
+};
 static constexpr uint32_t kMmRoundChunks = 4096u / kMmKChunk;         // accumulation round: 4096 elements of K
+static constexpr uint32_t kMmRaster = 8;                              // CTA row tiles per rasterisation band
 
 __device__ __forceinline__ uint32_t mm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,45 +96,61 @@ __device__ __forceinline__ uint64_t mm_combine(const uint32_t* v) {
 }
 
 // ---- limb image of B: tile (jt, kc) = 32 columns x 16 rows of B -> 256 x 128 bytes, stored at
-// ((jt * KC) + kc) * 32 KiB in the canonical swizzled layout.  Thread = one element of the padded B.
+// ((jt * KC) + kc) * 32 KiB in the canonical swizzled layout.  One CTA per tile; thread (jl, q) takes the
+// two elements B[kc*16 + 2q .. +1][jt*32 + jl] and writes, for every limb s, the 16-byte chunk q of row
+// (jl, s): the eight threads q = 0..7 of a row together write its whole 128-byte line.
 __global__ void __launch_bounds__(256)
-k_matmul61_prep(const uint64_t* __restrict__ B, uint32_t K, uint32_t N, uint32_t KC, uint32_t NT, uint8_t* __restrict__ img) {
-  const uint64_t total = (uint64_t)KC * kMmKChunk * NT * kMmNTile;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const uint32_t j = (uint32_t)(idx % ((uint64_t)NT * kMmNTile));
-    const uint32_t k = (uint32_t)(idx / ((uint64_t)NT * kMmNTile));
-    uint64_t c = (k < K && j < N) ? B[(uint64_t)k * N + j] : 0;
-    uint64_t ca[8];
+k_matmul61_prep(const uint64_t* __restrict__ B, uint32_t K, uint32_t N, uint32_t KC, uint8_t* __restrict__ img) {
+  const uint32_t kc = blockIdx.x % KC, jt = blockIdx.x / KC;
+  const uint32_t q = threadIdx.x & 7u, jl = threadIdx.x >> 3;
+  const uint32_t j = jt * kMmNTile + jl, k0 = kc * kMmKChunk + 2u * q;
+  uint64_t c0 = (j < N && k0 < K) ? B[(uint64_t)k0 * N + j] : 0;
+  uint64_t c1 = (j < N && k0 + 1 < K) ? B[(uint64_t)(k0 + 1) * N + j] : 0;
+  uint64_t ca[16];  // c * 2^(8a), a = 0..7, for both elements
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    ca[a] = c0;
+    ca[8 + a] = c1;
+    c0 = F61::mul(c0, 256);
+    c1 = F61::mul(c1, 256);
+  }
+  uint8_t* tile = img + (uint64_t)blockIdx.x * kMmBTileBytes;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    uint64_t w0 = 0, w1 = 0;  // bytes a = 0..7: byte_s(C_a) of element k0 and of element k0 + 1
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-      ca[a] = c;
-      c = F61::mul(c, 256);
+      w0 |= ((ca[a] >> (8 * s)) & 0xFFull) << (8 * a);
+      w1 |= ((ca[8 + a] >> (8 * s)) & 0xFFull) << (8 * a);
     }
-    uint8_t* tile = img + ((uint64_t)(j / kMmNTile) * KC + k / kMmKChunk) * kMmBTileBytes;
-    const uint32_t jl = j % kMmNTile, kl = k % kMmKChunk;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      uint64_t w = 0;  // bytes a = 0..7 of row (jl, s): byte_s(C_a)
-#pragma unroll
-      for (int a = 0; a < 8; ++a) w |= ((ca[a] >> (8 * s)) & 0xFFull) << (8 * a);
-      const uint32_t r = jl * 8 + s, kk = kl * 8;
-      *reinterpret_cast<uint64_t*>(tile + (r >> 3) * 1024u + (r & 7u) * 128u + (((kk >> 4) ^ (r & 7u)) << 4) + (kk & 15u)) = w;
-    }
+    const uint32_t r = jl * 8u + s;
+    *reinterpret_cast<ulonglong2*>(tile + (r >> 3) * 1024u + (r & 7u) * 128u + ((q ^ (r & 7u)) << 4)) = make_ulonglong2(w0, w1);
   }
 }
 
+template <int RT>
 __global__ void __launch_bounds__(kMmThreads, 1)
 k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint8_t* __restrict__ img, uint32_t KC,
-              uint32_t N, uint64_t* __restrict__ C) {
+              uint32_t N, uint32_t NT, uint64_t* __restrict__ C) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+  constexpr uint32_t kMmStages = MmCfg<RT>::kStages, kMmStage = MmCfg<RT>::kStage;
+  constexpr uint32_t kRows = 128u * RT;               // result rows per CTA
   const uint32_t base = (mm_smem_u32(dyn_smem) + 1023u) & ~1023u;
   const uint32_t ctl = base + kMmStages * kMmStage;  // empty[stage] mbarriers, done mbarrier, TMEM address
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t m0 = blockIdx.y * 128u, jt = blockIdx.x;
+  // rasterisation: consecutive CTAs walk kMmRaster row tiles of one column tile, then the next column tile,
+  // so the ~148 resident CTAs share 16 A row-tiles and ~9 image column-tiles through L2 while they advance
+  // along K in step (otherwise the 64-byte-per-element image is re-read from HBM once per row tile)
+  const uint32_t MT = (M + kRows - 1u) / kRows;
+  const uint32_t per_band = kMmRaster * NT;
+  const uint32_t band = blockIdx.x / per_band, in_band = blockIdx.x % per_band;
+  const uint32_t band_rows = min(kMmRaster, MT - band * kMmRaster);
+  const uint32_t mt = band * kMmRaster + in_band % band_rows, jt = in_band / band_rows;
+  if (jt >= NT) return;  // only in the last, shorter band (uniform per CTA: nothing allocated yet)
+  const uint32_t m0 = mt * kRows;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(ctl + 64u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ctl + 64u), "n"(256 * RT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
@@ -148,9 +168,9 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
   const uint8_t* img_row = img + (uint64_t)jt * KC * kMmBTileBytes;
   auto load_chunk = [&](uint32_t kc) {
     const uint32_t st = base + (kc % kMmStages) * kMmStage;
-    // A: 128 rows x 8 sixteen-byte pieces
+    // A: RT tiles of 128 rows x 8 sixteen-byte pieces (row r of the CTA lives in tile r / 128)
 #pragma unroll
-    for (uint32_t q = tid; q < 1024u; q += kMmThreads) {
+    for (uint32_t q = tid; q < 1024u * RT; q += kMmThreads) {
       const uint32_t row = q >> 3, piece = q & 7u;
       const uint32_t k = kc * kMmKChunk + piece * 2u;
       const bool in = (m0 + row < M) && (k < K);  // K is even: a piece is inside or outside as a whole
@@ -160,7 +180,7 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
     // limb image tile: already in shared-memory layout
     const uint8_t* bsrc = img_row + (uint64_t)kc * kMmBTileBytes;
 #pragma unroll
-    for (uint32_t q = tid; q < kMmBTileBytes / 16u; q += kMmThreads) mm_cp16(st + kMmATile + q * 16u, bsrc + q * 16u, 16u);
+    for (uint32_t q = tid; q < kMmBTileBytes / 16u; q += kMmThreads) mm_cp16(st + RT * kMmATile + q * 16u, bsrc + q * 16u, 16u);
   };
 
   uint64_t acc[kMmNTile];
@@ -198,7 +218,10 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + (kc % kMmStages) * kMmStage;
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) mm_mma(tmem, mm_desc(st + ks * 32u), mm_desc(st + kMmATile + ks * 32u), (kc > r0) | ks);
+        for (uint32_t rt = 0; rt < (uint32_t)RT; ++rt)
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            mm_mma(tmem + rt * 256u, mm_desc(st + rt * kMmATile + ks * 32u), mm_desc(st + RT * kMmATile + ks * 32u), (kc > r0) | ks);
         mm_commit(ctl + 8u * (kc % kMmStages));
         if (kc + 1 == r1) mm_commit(done_bar);
       }
@@ -207,12 +230,12 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
     mm_wait(done_bar, done_phase);
     done_phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp < 4) {
-      const uint32_t lane_off = (warp * 32u) << 16;
+    if (warp < 4u * RT) {  // warps 0-3 drain row tile 0, warps 4-7 row tile 1; a warp reads TMEM lanes 32 * (warp % 4) ...
+      const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
 #pragma unroll
       for (uint32_t g = 0; g < 8; ++g) {
         uint32_t v[32];
-        mm_tmem_ld32(tmem + lane_off + g * 32u, v);
+        mm_tmem_ld32(tmem + (warp >> 2) * 256u + lane_off + g * 32u, v);
 #pragma unroll
         for (uint32_t jj = 0; jj < 4; ++jj) acc[g * 4 + jj] = F61::add(acc[g * 4 + jj], mm_combine(v + 8 * jj));
       }
@@ -220,7 +243,7 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // TMEM drained before the next round overwrites it
   }
-  if (warp < 4) {
+  if (warp < 4u * RT) {
     const uint32_t row = m0 + tid;
     if (row < M) {
       uint64_t* dst = C + (uint64_t)row * N + (uint64_t)jt * kMmNTile;
@@ -233,7 +256,7 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256 * RT) : "memory");
   }
 }
 
@@ -267,15 +290,21 @@ size_t matmul61_image_bytes(uint32_t K, uint32_t N) {
 cudaError_t matmul61_tc_launch(cudaStream_t st, int sm_count, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B,
                                uint32_t N, uint8_t* d_img, uint64_t* d_C) {
   const uint32_t KC = (K + kMmKChunk - 1) / kMmKChunk, NT = (N + kMmNTile - 1) / kMmNTile;
-  const uint64_t total = (uint64_t)KC * kMmKChunk * NT * kMmNTile;
-  const int pgrid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sm_count * 8);
-  k_matmul61_prep<<<pgrid, 256, 0, st>>>(d_B, K, N, KC, NT, d_img);
+  (void)sm_count;
+  k_matmul61_prep<<<KC * NT, 256, 0, st>>>(d_B, K, N, KC, d_img);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_matmul61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmDynSmem);
-  if (e != cudaSuccess) return e;
-  const dim3 grid(NT, (M + 127) / 128);
-  k_matmul61_tc<<<grid, kMmThreads, kMmDynSmem, st>>>(d_A, M, K, d_img, KC, N, d_C);
+  if (M > 128) {  // two row tiles per CTA: every image chunk feeds twice the MMAs
+    e = cudaFuncSetAttribute(k_matmul61_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmCfg<2>::kDynSmem);
+    if (e != cudaSuccess) return e;
+    const uint32_t MT = (M + 255) / 256, bands = (MT + kMmRaster - 1) / kMmRaster;
+    k_matmul61_tc<2><<<bands * kMmRaster * NT, kMmThreads, MmCfg<2>::kDynSmem, st>>>(d_A, M, K, d_img, KC, N, NT, d_C);
+  } else {
+    e = cudaFuncSetAttribute(k_matmul61_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmCfg<1>::kDynSmem);
+    if (e != cudaSuccess) return e;
+    const uint32_t MT = (M + 127) / 128, bands = (MT + kMmRaster - 1) / kMmRaster;
+    k_matmul61_tc<1><<<bands * kMmRaster * NT, kMmThreads, MmCfg<1>::kDynSmem, st>>>(d_A, M, K, d_img, KC, N, NT, d_C);
+  }
   return cudaGetLastError();
 }
 
