@@ -650,6 +650,11 @@ static int basis_rows(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* nod
 }
 
 template <class F>
+static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_shares, uint64_t N,
+                        uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
+                        const typename F::E* d_mat, typename F::E* d_out, uint8_t* d_err);
+
+template <class F>
 static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_shares, uint64_t N,
                         uint32_t n, uint64_t si, uint64_t sj, const typename F::E* d_basis,
                         typename F::E* d_out) {
@@ -668,6 +673,11 @@ static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
       CKL();
       return SCLGPU_OK;
     }
+  }
+  if constexpr (F::BYTES == 16) {
+    // Fp127: the inner product as a one-row limb product on the tensor cores (k_recover_d_tc without checks)
+    if (recover_d_tc_fits<F>(n, 0) && getenv("SCLGPU_RECOVER_GENERIC") == nullptr)
+      return recover_d_on<F>(ctx, st, d_shares, N, si, sj, n, 0, d_basis, d_out, nullptr);
   }
   const size_t smem = (size_t)n * sizeof(typename F::E);
   if (smem > 48 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_p: more than 48 KiB of basis");
@@ -729,7 +739,7 @@ static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
           for (uint32_t a = 0; a < EB; ++a) {
             uint8_t bytes[16];
             std::memcpy(bytes, &c, EB);
-            for (uint32_t s = 0; s < EB; ++s) img[tc_bmat_offset(r * EB + s, k * EB + a)] = bytes[s];
+            for (uint32_t s = 0; s < EB; ++s) img[tc_rd_offset(r * EB + s, k * EB + a)] = bytes[s];
             c = F::mul(c, F::from_u32(256));
           }
         }
@@ -745,9 +755,9 @@ static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     ctx->launches++;
     cudaError_t e;
     if constexpr (EB == 8) {
-      e = recover_d61_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, ctx->d_count);
+      e = recover_d61_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, d_err ? ctx->d_count : nullptr);
     } else {
-      e = recover_d127_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, ctx->d_count);
+      e = recover_d127_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, d_err ? ctx->d_count : nullptr);
     }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
     return SCLGPU_OK;

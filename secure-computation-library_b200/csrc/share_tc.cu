@@ -520,8 +520,9 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
   constexpr uint32_t EB = F::BYTES;
   constexpr uint32_t kThreads = 128 * GROUPS;
   constexpr uint32_t PCOLS = 64;
-  constexpr uint32_t kColsPerGroup = 32u + PCOLS;
-  constexpr uint32_t kMaxM = 128u / EB;                    // shares in one 128-byte A row
+  constexpr uint32_t kACols = 64u;                         // A rows of up to 256 bytes: two K tiles of 128
+  constexpr uint32_t kColsPerGroup = kACols + PCOLS;
+  constexpr uint32_t kMaxM = 256u / EB;                    // shares in one A row
   constexpr uint32_t kLdRows = 32u / EB;                   // output rows per 32-column TMEM load
   static_assert(GROUPS * kColsPerGroup <= 512, "tensor memory has 512 columns");
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -551,7 +552,7 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
 
   const uint32_t g = tid >> 7, gt = tid & 127u;
   const uint32_t a_tm = tmem + g * kColsPerGroup;
-  const uint32_t acc0 = a_tm + 32u;
+  const uint32_t acc0 = a_tm + kACols;
   const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
   const uint32_t a_lane = a_tm + lane_off;
   const uint32_t mbar = ctl + 8u * g;
@@ -564,7 +565,8 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
 
   auto issue_pass = [&](uint32_t p) {
     for (uint32_t ks = 0; ks < ksteps; ++ks)
-      tc_mma_ts(acc0, a_tm + ks * 8u, tc_desc(b_base + p * (PCOLS * 128u) + ks * 32u), tc_idesc(PCOLS), ks);
+      tc_mma_ts(acc0, a_tm + ks * 8u, tc_desc(b_base + (ks >> 2) * kTcRdKTileBytes + p * (PCOLS * 128u) + (ks & 3u) * 32u),
+                tc_idesc(PCOLS), ks);
     tc_commit(mbar);
   };
 
@@ -642,11 +644,11 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
     }
     if (valid) {
       out[j] = bad ? F::zero() : result;
-      err[j] = bad ? 1 : 0;
+      if (err != nullptr) err[j] = bad ? 1 : 0;
       local_bad += bad;
     }
   }
-  if (local_bad) atomicAdd(n_bad, local_bad);
+  if (local_bad && n_bad != nullptr) atomicAdd(n_bad, local_bad);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -42,10 +42,14 @@ cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const Aes
                                const void* d_bmat, uint64_t first_block, const E127* d_secrets, uint64_t N, uint32_t t,
                                uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j);
 
-// shamirRecoverD on tensor cores: m*BYTES <= 128 and (n_checks+1)*BYTES <= 128 (two 64-column passes)
+// shamirRecoverD / shamirRecoverP on tensor cores: m*BYTES <= 256 (two K tiles of 128 bytes) and
+// (n_checks+1)*BYTES <= 128 (two 64-column passes).  Image: K tile kt at kt * kTcRdKTileBytes, inside it the
+// canonical layout of up to 128 rows.
+static constexpr uint32_t kTcRdKTileBytes = 16384;
+static inline uint32_t tc_rd_offset(uint32_t r, uint32_t kk) { return (kk >> 7) * kTcRdKTileBytes + tc_bmat_offset(r, kk & 127u); }
 template <class F>
 static inline bool recover_d_tc_fits(uint32_t m, uint32_t n_checks) {
-  return m >= 1 && m * F::BYTES <= 128u && (n_checks + 1u) * F::BYTES <= 128u;
+  return m >= 1 && m * F::BYTES <= 256u && (n_checks + 1u) * F::BYTES <= 128u;
 }
 cudaError_t recover_d61_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const uint64_t* d_in, uint64_t N,
                                   uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks, uint64_t* d_out, uint8_t* d_err,
