@@ -1,4 +1,5 @@
-// kernels.cuh -- the sm_100a kernels behind libsclgpu.so.
+// kernels.cuh -- the integer-pipe / HBM-bound sm_100a kernels behind libsclgpu.so (the tensor-core
+// kernels are in share_tc.cu and matmul_tc.cu).
 //
 // One kernel per hot loop of the reference ("Kernels the new
 // build must write"); each cites the reference loop it replaces.  All kernels are

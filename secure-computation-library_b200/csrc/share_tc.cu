@@ -1,32 +1,38 @@
-// share_tc.cu -- shamirSecretShare for Fp61 on the 5th-generation tensor cores.
+// share_tc.cu -- the tcgen05 (5th-generation tensor core) kernels of the Shamir path:
+//   k_share_tcm<F, ...>      shamirSecretShare, both fields, PRG fused or coefficient planes (the default)
+//   k_share61_tc             first variant, A operand staged in shared memory (kept as a measured comparison)
+//   k_recover_d_tc<F, ...>   shamirRecoverD, and shamirRecoverP for Fp127
 //
 // Reference path replaced: ss::shamirSecretShare (include/scl/ss/shamir.h:52-68) =
 // Vector::random(t+1, prg) (vector.h:508-519, prg.cc:124-146), c[0] = secret,
-// n Horner evaluations at x = 1..n (poly.h:56-64) -- N calls on one PRG.
+// n Horner evaluations at x = 1..n (poly.h:56-64) -- N calls on one PRG; and
+// ss::shamirRecoverD / shamirRecoverP (shamir.h:82-155).
 //
-// Formulation (DESIGN.md "tensor-core share kernel").  The shares of one secret are
-// the Vandermonde product  share_i = sum_k c_k * (i+1)^k  (the reference's own
+// Formulation.  The shares of one secret are the Vandermonde
+// product  share_i = sum_k c_k * (i+1)^k  (the reference's own
 // test/scl/math/test_matrix.cc:342-365 states this identity).  A coefficient is
-// used through its eight BYTES c_k = sum_a c_{k,a} 2^(8a) -- the raw little-endian
+// used through its BYTES c_k = sum_a c_{k,a} 2^(8a) -- the raw little-endian
 // keystream word, no reduction needed because the map is linear -- and the constant
-//     C_{i,k,a} = (i+1)^k * 2^(8a) mod p       (61 bits)
-// through its eight bytes C_{i,k,a} = sum_s C_{i,k,a,s} 2^(8s).  Then
+//     C_{i,k,a} = (i+1)^k * 2^(8a) mod p
+// through its bytes C_{i,k,a} = sum_s C_{i,k,a,s} 2^(8s).  Then
 //     share_i = sum_s 2^(8s) * acc_{i,s},   acc_{i,s} = sum_{k,a} c_{k,a} * C_{i,k,a,s}
-// and acc is a u8 x u8 -> s32 matrix product with K = 8(t+1) <= 128 (acc < 2^23):
-//     D[128 secrets][8 parties x 8 limbs] += A[128 secrets][K] * B[K][64]
+// and acc is a u8 x u8 -> s32 matrix product with K = BYTES*(t+1) <= 128 (acc < 2^23):
+//     D[128 secrets][parties x limbs] += A[128 secrets][K] * B[K][64 per pass]
 // issued as tcgen05.mma.kind::i8 (M=128, N=64, K=32 per instruction), A = the
-// coefficient bytes exactly as the PRG emits them (one 128-byte row per secret,
-// K-major, 128B-swizzled), B = the constant limbs (32 KiB, built on the host once per
-// (t, n), resident in shared memory), D in tensor memory.  The epilogue reads the
-// eight 23-bit limbs of a share with tcgen05.ld and recombines them mod 2^61 - 1.
+// coefficient bytes exactly as the PRG emits them (one 128-byte row per secret),
+// B = the constant limbs (32 KiB, K-major, 128B-swizzled, built on the host once per
+// (field, t, n), resident in shared memory), D in tensor memory.  The epilogue reads the
+// 23-bit limbs of a share with tcgen05.ld and recombines them mod p.
 //
-// One CTA per SM, 384 threads = 3 groups of 4 warps; a group owns one 128-secret
-// tile at a time: every thread draws its secret's keystream (T-table AES-CTR,
-// aes_ctr.cuh) straight into its A row, one elected thread issues the MMAs for the
-// group, each warp drains its own 32 TMEM lanes.  Groups run unsynchronised with
-// respect to each other, so one group's AES (LSU + ALU pipes) overlaps another's
-// MMA and epilogue.  Two 64-column accumulators per group: the MMA of pass p+1 runs
-// under the epilogue of pass p.
+// Default schedule (k_share_tcm<F, 5, 1, 64>): one CTA per SM, 640 threads = 5 groups
+// of 4 warps; a group owns one 128-secret tile at a time: every thread draws its
+// secret's keystream (T-table AES-CTR, aes_ctr.cuh) and writes it straight into its own
+// TENSOR-MEMORY lane (tcgen05.st; the A operand never touches shared memory), one
+// elected thread issues the `.ts` MMAs for the group, each warp drains its own 32 TMEM
+// lanes.  Groups run unsynchronised with respect to each other (named barriers and one
+// mbarrier per group), so one group's AES (LSU + ALU pipes) overlaps another's MMA and
+// epilogue.  The reconstruction kernels use the same structure with the A rows loaded
+// from the share planes instead of drawn from the PRG.
 #include <cuda_runtime.h>
 
 #include <algorithm>
