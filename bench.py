@@ -35,6 +35,7 @@ METRIC = "fp61_shamir_share_reconstruct_secrets_per_s"
 UNIT = "secrets/s"
 FIELD, T, NPARTIES = 61, 15, 32
 ALGO_IMADS_PER_SECRET = 2048       # 512 field muls x 4 32-bit IMADs
+AES_LDS_PER_SECRET = 1083          # 8 blocks x 133 T-table lookups + 27 per-group lookups / ... (ncu op mix, profiles/)
 ALGO_BYTES_SHARE = 8 + 8 * NPARTIES    # secret in, n shares out
 ALGO_BYTES_RECOVER = 8 * NPARTIES + 8  # n shares in, secret out
 
@@ -214,6 +215,7 @@ def run_b200(args):
     # integer-pipe peak at the clocks of this box (denominator of the int-mul roofline)
     imad_peak = ctx.pipe_microbench(0, 1 << 14)
     imadw_peak = ctx.pipe_microbench(1, 1 << 14)
+    lds_peak = ctx.pipe_microbench(4, 1 << 14)      # conflict-free LDS.32 lane-operations per second
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -387,7 +389,12 @@ def run_b200(args):
                          "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_secret": ALGO_BYTES_SHARE if share_ms >= rec_ms else ALGO_BYTES_RECOVER,
                          "note": "the share kernel's limiter is the shared-memory (LSU) pipe of the fused T-table AES-CTR, "
-                                 "not HBM; see profiles/ and DESIGN.md section 3"},
+                                 "not HBM; see profiles/ and DESIGN.md section 3",
+                         "limiter": {"pipe": "lsu (shared-memory lookups of the fused AES-128-CTR)",
+                                     "lookups_per_secret": AES_LDS_PER_SECRET,
+                                     "achieved": AES_LDS_PER_SECRET * N / (share_ms * 1e-3), "peak": lds_peak,
+                                     "unit": "LDS.32 lane-ops/s", "frac": AES_LDS_PER_SECRET * N / (share_ms * 1e-3) / lds_peak,
+                                     "peak_source": "sclgpu_pipe_microbench(kind=4) on this GPU"}},
             "int_roofline": {"unit": "IMAD/s", "algorithmic_imads_per_secret": ALGO_IMADS_PER_SECRET,
                              "achieved": ALGO_IMADS_PER_SECRET * N / (ms_per_step * 1e-3),
                              "peak_imad32": imad_peak, "peak_imad_wide": imadw_peak,
