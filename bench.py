@@ -369,8 +369,8 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         share_gbs = ALGO_BYTES_SHARE * N / (share_ms * 1e-3) / 1e9
         rec_gbs = ALGO_BYTES_RECOVER * N / (rec_ms * 1e-3) / 1e9
-        share_kernel = {"0": "k_share61<15>", "1": "k_share61_tc", "2": "k_share61_tcm<4,1,64>"}.get(
-            os.environ.get("SCLGPU_SHARE_TC", "3"), "k_share61_tcm<5,1,64>")
+        share_kernel = {"0": "k_share61<15>", "1": "k_share61_tc", "2": "k_share_tcm<F61,4,1,64>"}.get(
+            os.environ.get("SCLGPU_SHARE_TC", "3"), "k_share_tcm<F61,5,1,64>")
         dominant = share_kernel if share_ms >= rec_ms else "k_recover61_pm<2>"
         dom_gbs = share_gbs if share_ms >= rec_ms else rec_gbs
         traffic = None
