@@ -76,15 +76,16 @@ def dist_env():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
-def gather_shards(local, shard: Shard, n_units: int, group=None):
+def gather_shards(local, shard: Shard, n_units: int, group=None, align: int = 1):
     """all_gather the per-rank result slices (torch tensors, dim 0 = units) into the
-    full [n_units, ...] tensor on every rank.  Uneven slices are padded."""
+    full [n_units, ...] tensor on every rank.  Uneven slices are padded.  `align` must be the
+    value the slices were cut with (shard_range)."""
     import torch
     import torch.distributed as dist
 
     if shard.world == 1:
         return local
-    counts = [shard_range(n_units, shard.world, r).count for r in range(shard.world)]
+    counts = [shard_range(n_units, shard.world, r, align).count for r in range(shard.world)]
     pad = max(counts)
     buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     buf[: local.shape[0]] = local
@@ -103,3 +104,20 @@ def sum_over_ranks(value: int, device=None, group=None) -> int:
     t = torch.tensor([int(value)], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t.item())
+
+
+def matvec_row_sharded(ctx, field: int, d_A_local, cols: int, d_x, shard: Shard, n_rows: int, group=None):
+    """y = A x (Matrix::multiply(Vector), matrix.h:498-513) with the ROWS of A sharded over the ranks
+    (BASELINE config C5): every rank multiplies its contiguous row slice on its own GPU
+    (`d_A_local` = rows [shard.lo, shard.hi) of A, row-major, `d_x` replicated), then the y slices are
+    all-gathered -- the one real exchange step of the path (8 KiB per GPU at 8192 rows over 8 GPUs).
+    Returns the full y (n_rows elements) as a device tensor on every rank."""
+    import torch
+
+    w = 1 if field == 61 else 2
+    y_local = torch.empty((shard.count, w), dtype=torch.int64, device=d_x.device)
+    if shard.count:
+        ctx.matvec_dev(field, d_A_local, shard.count, cols, d_x, y_local)
+    torch.cuda.current_stream().synchronize() if d_x.is_cuda else None
+    y = gather_shards(y_local, shard, n_rows, group=group)
+    return y.reshape(n_rows) if w == 1 else y

@@ -1,0 +1,79 @@
+"""torchrun worker for the multi-GPU path on real GPUs (NCCL; one process per GPU).  Checks, against the
+oracle on rank 0:
+  * batch-sharded shamirSecretShare / shamirRecoverP with the PRG counter offset per rank, secrets gathered;
+  * recoverD error counts summed over ranks;
+  * C5: row-sharded Fp61 mat-vec with the all-gather of the y slices (sharding.matvec_row_sharded).
+Run by tests/test_gpu_parity.py::test_multi_gpu_nccl when at least two GPUs are visible."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def main():
+    pkg = entry.load_package()
+    o = entry.load_oracle()
+    port = o.PortOracle()
+    sh = pkg.sharding
+    B = pkg.binding
+    rank, world, local_rank = sh.dist_env()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    ctx.use_torch_stream()
+    dev = torch.device("cuda", local_rank)
+
+    # ---- batch-sharded share / reconstruct
+    field, t, n, N = 61, 15, 32, 100003
+    s = sh.shard_range(N, world, rank, align=2)
+    d_sec = torch.empty(s.count, dtype=torch.int64, device=dev)
+    ctx.random_dev(field, "secrets", sh.random_first_block(field, 0, s), s.count, d_sec)
+    d_shr = torch.empty((n, s.count), dtype=torch.int64, device=dev)
+    ctx.shamir_share_dev(field, d_sec, s.count, t, n, "shamir bench", sh.share_first_block(field, t, 3, s), d_shr, B.PARTY_MAJOR)
+    if rank == world - 1:
+        d_shr[20, 5] ^= 1                                        # one tampered (and checked) share on the last rank
+    d_out = torch.empty(s.count, dtype=torch.int64, device=dev)
+    d_err = torch.empty(s.count, dtype=torch.uint8, device=dev)
+    nd = ctx.recover_d_dev(field, d_shr, s.count, n, t, d_out, d_err, B.PARTY_MAJOR)
+    total_bad = sh.sum_over_ranks(nd, device=dev)
+    ctx.recover_p_dev(field, d_shr[:, :], s.count, n, d_out, B.PARTY_MAJOR)
+    torch.cuda.synchronize()
+    g_sec = sh.gather_shards(d_sec.reshape(-1, 1), s, N, align=2).reshape(-1)
+    g_shr = sh.gather_shards(d_shr.t().contiguous(), s, N, align=2)       # [N][n]
+    if rank == 0:
+        secrets = port.vector_random(field, "secrets", 0, N)
+        assert np.array_equal(g_sec.cpu().numpy().view(np.uint64), secrets), "gathered secrets differ"
+        want = port.shamir_share(field, secrets, t, n, "shamir bench", 3)
+        got = g_shr.cpu().numpy().view(np.uint64)
+        last = sh.shard_range(N, world, world - 1, align=2)
+        want[last.lo + 5, 20] ^= np.uint64(1)
+        assert np.array_equal(got, want), "gathered shares differ from the one-PRG batch"
+        assert total_bad == 1, total_bad
+
+    # ---- C5: row-sharded mat-vec + all-gather
+    rows, cols = 2048, 1024
+    rs = sh.shard_range(rows, world, rank)
+    d_A = torch.empty((rs.count, cols), dtype=torch.int64, device=dev)
+    ctx.random_dev(61, "mat A", (rs.lo * cols) // 2, rs.count * cols, d_A)   # rows [lo, hi) of Matrix::random(rows, cols)
+    d_x = torch.empty(cols, dtype=torch.int64, device=dev)
+    ctx.random_dev(61, "vec x", 0, cols, d_x)
+    y = sh.matvec_row_sharded(ctx, 61, d_A, cols, d_x, rs, rows)
+    if rank == 0:
+        A = port.vector_random(61, "mat A", 0, rows * cols).reshape(rows, cols)
+        x = port.vector_random(61, "vec x", 0, cols)
+        assert np.array_equal(y.cpu().numpy().view(np.uint64), port.matvec(61, A, x)), "row-sharded mat-vec differs"
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST_GPU_OK world={world}")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,14 @@ def main():
         assert np.array_equal(g_sh, full), "gathered shares differ from the unsharded batch"
         assert np.array_equal(g_rec, secrets), "gathered secrets differ"
         assert total_bad == 1, total_bad
+    # C5: rows of A sharded, x replicated, all-gather of the y slices (the path's one exchange step)
+    rows, cols = 37, 20
+    A = engine.vector_random(61, "mat A", 0, rows * cols).reshape(rows, cols)
+    x = engine.vector_random(61, "vec x", 0, cols)
+    s = sh.shard_range(rows, world, rank)
+    y_local = engine.matvec(61, A[s.lo:s.hi], x) if s.count else np.zeros(0, dtype=np.uint64)
+    y = sh.gather_shards(torch.from_numpy(y_local.view(np.int64)), s, rows).numpy().view(np.uint64)
+    assert np.array_equal(y, engine.matvec(61, A, x)), "row-sharded mat-vec differs"
     dist.barrier()
     if rank == 0:
         print(f"DIST_OK world={world}")

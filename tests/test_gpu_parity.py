@@ -703,3 +703,24 @@ def test_full_size_c5_matvec_and_muladd(ctx, pkg, port):
     ctx.vec_op_dev(61, 1, v["z"], v["c"], n, lhs)       # z - c
     torch.cuda.synchronize()
     assert torch.equal(lhs, t1)
+
+
+# ------------------------------------------------------------------ several GPUs, NCCL
+def test_multi_gpu_nccl():
+    """tests/dist_gpu_worker.py under torchrun, one process per visible GPU (needs >= 2): batch-sharded
+    share / reconstruct with per-rank PRG offsets, error counts summed over ranks, and C5's row-sharded
+    mat-vec with its all-gather, all against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("one GPU visible")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(g, 8)}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(repo, "tests", "dist_gpu_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
