@@ -43,3 +43,15 @@ def test_cpp_shim_against_scl_in_process():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SHIM_OK" in r.stdout
+
+
+C_BIN = os.path.join(REPO, "tests", "cpp", "_build", "c_example")
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_of_the_abi():
+    """examples/share_reconstruct.c: the C ABI from plain C (gcc, no CUDA / C++ headers)."""
+    assert os.path.exists(C_BIN), "tests/cpp/_build/c_example must travel to the GPU box"
+    r = subprocess.run([C_BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "C_EXAMPLE_OK" in r.stdout, r.stdout + r.stderr
+    assert "error detected during recovery" in r.stdout
