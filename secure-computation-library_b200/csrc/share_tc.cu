@@ -281,20 +281,46 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 
-// Fp127 (mersenne127.cc:60-97 semantics): sixteen 23-bit limbs at 2^(8s) -> canonical residue mod 2^127 - 1
+// Fp127 (mersenne127.cc:60-97 semantics): sixteen 23-bit limbs at 2^(8s) -> canonical residue mod 2^127 - 1.
+// Word-level: pairs q_m = v_2m + v_2m+1 * 2^8 (< 2^32, weight 2^(16m)); the even pairs concatenate into a
+// 128-bit number E, the odd ones into O with weight 2^16; X = E + (O << 16) is formed in five 32-bit words
+// with one carry chain, folded once at bit 127 (2^127 = 1), once more for the single possible carry, and
+// p itself is mapped to 0.
 __device__ __forceinline__ E127 tc_combine127(const uint32_t* v) {
   uint32_t q[8];
 #pragma unroll
-  for (int m = 0; m < 8; ++m) q[m] = v[2 * m] + (v[2 * m + 1] << 8);  // < 2^32, weight 2^(16m)
-  // even pairs are word-aligned: E = q0 | q2<<32 | q4<<64 | q6<<96; odd pairs form O, weight 2^16
-  const E127 e{(uint64_t)q[0] | ((uint64_t)q[2] << 32), (uint64_t)q[4] | ((uint64_t)q[6] << 32)};
-  const uint64_t olo = (uint64_t)q[1] | ((uint64_t)q[3] << 32), ohi = (uint64_t)q[5] | ((uint64_t)q[7] << 32);
-  // O * 2^16 = (O mod 2^111) * 2^16 + (O >> 111) * 2^127, and 2^127 = 1
-  E127 x{olo << 16, ((ohi << 16) | (olo >> 48)) & F127::PHI};
-  const uint64_t wrap = ohi >> 47;
-  x.lo += wrap;
-  x.hi += (x.lo < wrap);  // < 2^127 + 2^17
-  return F127::add(F127::from_raw(e), F127::from_raw(x));
+  for (int m = 0; m < 8; ++m) q[m] = v[2 * m] + (v[2 * m + 1] << 8);
+  // W = O << 16 as words w0..w4 (O = q1 | q3<<32 | q5<<64 | q7<<96)
+  const uint32_t w0 = q[1] << 16;
+  const uint32_t w1 = __funnelshift_l(q[1], q[3], 16);
+  const uint32_t w2 = __funnelshift_l(q[3], q[5], 16);
+  const uint32_t w3 = __funnelshift_l(q[5], q[7], 16);
+  const uint32_t w4 = q[7] >> 16;
+  uint32_t s0, s1, s2, s3, s4;  // X = E + W, E = q0 | q2<<32 | q4<<64 | q6<<96
+  asm("add.cc.u32 %0, %5, %9;\n\t"
+      "addc.cc.u32 %1, %6, %10;\n\t"
+      "addc.cc.u32 %2, %7, %11;\n\t"
+      "addc.cc.u32 %3, %8, %12;\n\t"
+      "addc.u32 %4, %13, 0;"
+      : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4)
+      : "r"(q[0]), "r"(q[2]), "r"(q[4]), "r"(q[6]), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4));
+  // fold bits >= 127: hi = X >> 127 (< 2^18)
+  const uint32_t hi = __funnelshift_l(s3, s4, 1);
+  s3 &= 0x7FFFFFFFu;
+  asm("add.cc.u32 %0, %0, %4;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.u32 %3, %3, 0;"
+      : "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3)
+      : "r"(hi));
+  // now < 2^127 + 2^18: if bit 127 is set the rest is < 2^18, so adding the carry cannot ripple
+  s0 += s3 >> 31;
+  s3 &= 0x7FFFFFFFu;
+  const bool is_p = (s0 & s1 & s2 & (s3 | 0x80000000u)) == 0xFFFFFFFFu;
+  E127 r;
+  r.lo = is_p ? 0 : ((uint64_t)s0 | ((uint64_t)s1 << 32));
+  r.hi = is_p ? 0 : ((uint64_t)s2 | ((uint64_t)s3 << 32));
+  return r;
 }
 
 // GROUPS x 128 threads; NBUF accumulators of PCOLS columns (PCOLS / F::BYTES parties per MMA pass) per

@@ -514,6 +514,36 @@ def test_share_from_coefficient_planes(ctx, pkg, orc, field, t, n, N):
         assert np.array_equal(sm[j].reshape(V.shape[:1] + V.shape[2:]), orc.matvec(field, V, cj)), (field, j)
 
 
+@pytest.mark.parametrize("field,t,n", [(61, 15, 32), (61, 1, 5), (127, 7, 16), (127, 1, 4)])
+def test_share_limb_recombination_edges(ctx, pkg, port, field, t, n):
+    """Crafted coefficient planes that drive the tensor-core epilogue through its corner cases: every
+    coefficient p-1 (largest limb sums), c0 = p-1 and c1 = 1 (the share at x = 1 is exactly p before
+    canonicalisation and must come out as 0), all zero, and single-bit coefficients."""
+    import torch
+
+    ctx.use_torch_stream()
+    w = 1 if field == 61 else 2
+    p = P[field]
+    cols = []
+    cols.append([p - 1] * (t + 1))
+    cols.append([p - 1, 1] + [0] * (t - 1))
+    cols.append([0] * (t + 1))
+    cols.append([1] * (t + 1))
+    for b in (0, 7, 8, 60, field - 1):
+        cols.append([(1 << b) % p] * (t + 1))
+        cols.append([(p - (1 << b)) % p] + [(1 << b) % p] * t)
+    N = len(cols)
+    planes = port.from_ints([cols[j][k] for k in range(t + 1) for j in range(N)], field).reshape((t + 1, N) + (() if w == 1 else (2,)))
+    d_c = torch.from_numpy(planes.view(np.int64)).cuda()
+    d_sm = torch.empty((N, n, w), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_coeffs_dev(field, d_c, N, t, n, d_sm, pkg.binding.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    got = d_sm.cpu().numpy().view(np.uint64)
+    for j in range(N):
+        want = [sum(c * pow(i, k, p) for k, c in enumerate(cols[j])) % p for i in range(1, n + 1)]
+        assert ints(port, got[j], field) == want, (field, j)
+
+
 # ------------------------------------------------------------------ per-party packets (SURVEY 8f.1)
 @pytest.mark.parametrize("field,t,n,N", [(61, 15, 32, 5000), (61, 2, 5, 1), (61, 3, 7, 4097), (127, 7, 16, 3001),
                                          (61, 20, 40, 300), (61, 1, 3, (1 << 21) + 7)])
