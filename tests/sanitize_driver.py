@@ -26,5 +26,14 @@ A = port.vector_random(61, "mat A", 0, 64 * 512).reshape(64, 512); x = port.vect
 assert np.array_equal(ctx.matvec(61, A, x), port.matvec(61, A, x))
 a = port.vector_random(61, "a", 0, 1001); b = port.vector_random(61, "b", 0, 1001)
 assert np.array_equal(ctx.beaver(61, a, b, a, b, a), port.beaver(61, a, b, a, b, a))
+# error-correcting reconstruction, GEMM on tensor cores (two accumulation rounds, ragged tiles), Fp127 GEMM
+sec = port.vector_random(61, "secrets", 0, 200)
+sh = ctx.shamir_share(61, sec, 3, 10, "rc", 0).copy(); sh[::3, 4] ^= np.uint64(9)
+f, e, st, nf = ctx.recover_c(61, sh)
+assert nf == 0 and np.array_equal(f[:, 0], sec)
+A = port.vector_random(61, "mat A", 0, 130 * 4100).reshape(130, 4100); Bm = port.vector_random(61, "mat B", 0, 4100 * 33).reshape(4100, 33)
+assert np.array_equal(ctx.matmul(61, A, Bm), port.matmul(61, A, Bm))
+A7 = port.vector_random(127, "mat A", 0, 9 * 6).reshape(9, 6, 2); B7 = port.vector_random(127, "mat B", 0, 6 * 5).reshape(6, 5, 2)
+assert np.array_equal(ctx.matmul(127, A7, B7), port.matmul(127, A7, B7))
 ctx.close()
 print("SANITIZE_DRIVER_OK")
