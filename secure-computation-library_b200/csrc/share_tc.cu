@@ -697,12 +697,9 @@ template <class F>
 static cudaError_t recover_d_tc_launch_t(cudaStream_t st, int sm_count, const void* d_bmat, const typename F::E* d_in,
                                          uint64_t N, uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
                                          typename F::E* d_out, uint8_t* d_err, unsigned long long* d_count) {
-  static bool prepared = false;
-  if (!prepared) {
-    cudaError_t e = cudaFuncSetAttribute(k_recover_d_tc<F, kRdGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdDynSmem);
-    if (e != cudaSuccess) return e;
-    prepared = true;
-  }
+  // per launch: the attribute belongs to the current device's instance of the kernel, and this is a few microseconds
+  cudaError_t e = cudaFuncSetAttribute(k_recover_d_tc<F, kRdGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdDynSmem);
+  if (e != cudaSuccess) return e;
   const uint64_t tiles = (N + 127) / 128;
   const int grid = (int)std::min<uint64_t>((tiles + kRdGroups - 1) / kRdGroups, (uint64_t)sm_count);
   k_recover_d_tc<F, kRdGroups><<<grid, 128 * kRdGroups, kRdDynSmem, st>>>(reinterpret_cast<const uint4*>(d_bmat), d_in, N, si, sj, m,
