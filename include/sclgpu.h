@@ -285,6 +285,13 @@ int sclgpu_fp127_vec_muladd(sclgpu_ctx* ctx, const void* e, const void* b, const
                             const void* a, const void* c, uint64_t n, void* z);
 int sclgpu_fp127_dot(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, void* out);
 int sclgpu_fp127_sum(sclgpu_ctx* ctx, const void* a, uint64_t n, void* out);
+/* Vector::equals (vector.h:358-375; also Matrix::equals on rows*cols elements): *equal = 1 iff all n
+ * elements agree.  Every element is compared (no early exit, as in the reference).  The _dev forms take
+ * device pointers and synchronise the stream to return the answer. */
+int sclgpu_fp61_vec_equal(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, int* equal);
+int sclgpu_fp127_vec_equal(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, int* equal);
+int sclgpu_fp61_vec_equal_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, int* equal);
+int sclgpu_fp127_vec_equal_dev(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, int* equal);
 /* device-pointer forms; `scalar` of vec_scale_dev is a HOST pointer, dot/sum
  * write one element to DEVICE memory */
 int sclgpu_fp61_vec_add_dev(sclgpu_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);

@@ -84,6 +84,7 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto vec_mul = &sclgpu_##SUF##_vec_mul;                                                  \
     static constexpr auto vec_scale = &sclgpu_##SUF##_vec_scale;                                              \
     static constexpr auto vec_muladd = &sclgpu_##SUF##_vec_muladd;                                            \
+    static constexpr auto vec_equal = &sclgpu_##SUF##_vec_equal;                                              \
     static constexpr auto dot = &sclgpu_##SUF##_dot;                                                          \
     static constexpr auto sum = &sclgpu_##SUF##_sum;                                                          \
     static constexpr auto matvec = &sclgpu_##SUF##_matvec;                                                    \
@@ -363,6 +364,15 @@ FF dot(Context& ctx, const scl::math::Vector<FF>& a, const scl::math::Vector<FF>
   ctx.check(detail::Abi<FF>::dot(ctx.get(), detail::raw<FF>(a.toStlVector().data()),
                                  detail::raw<FF>(b.toStlVector().data()), a.size(), detail::raw<FF>(&out)));
   return out;
+}
+// Vector::equals, vector.h:358-375
+template <class FF>
+bool equals(Context& ctx, const scl::math::Vector<FF>& a, const scl::math::Vector<FF>& b) {
+  if (a.size() != b.size()) return false;
+  int eq = 0;
+  ctx.check(detail::Abi<FF>::vec_equal(ctx.get(), detail::raw<FF>(a.toStlVector().data()),
+                                       detail::raw<FF>(b.toStlVector().data()), a.size(), &eq));
+  return eq != 0;
 }
 template <class FF>
 FF sum(Context& ctx, const scl::math::Vector<FF>& a) {

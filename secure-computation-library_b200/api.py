@@ -364,6 +364,20 @@ class Context:
             self._check(f(self._ctx, _p(a), _p(b), n, _p(out)))
         return out
 
+    def vec_equal(self, field: int, a, b) -> bool:
+        """Vector::equals (vector.h:358-375)."""
+        a, b = _c(a), _c(b)
+        if _nelem(a, field) != _nelem(b, field):
+            return False
+        eq = C.c_int(0)
+        self._check(self._f(field, "vec_equal")(self._ctx, _p(a), _p(b), _nelem(a, field), C.byref(eq)))
+        return bool(eq.value)
+
+    def vec_equal_dev(self, field: int, a, b, n: int) -> bool:
+        eq = C.c_int(0)
+        self._check(self._f(field, "vec_equal_dev")(self._ctx, _dp(a), _dp(b), n, C.byref(eq)))
+        return bool(eq.value)
+
     def vec_op_dev(self, field: int, op: int, a, b, n: int, out):
         f = self._f(field, self._OPS[op] + "_dev")
         if op == 5:

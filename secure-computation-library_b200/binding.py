@@ -80,6 +80,7 @@ def load() -> C.CDLL:
             for op in ("add", "sub", "mul", "scale"):
                 _sig(lib, f"sclgpu_{f}_vec_{op}{suf}", _int, _vp, _vp, _vp, _u64, _vp)
             _sig(lib, f"sclgpu_{f}_vec_muladd{suf}", _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp)
+            _sig(lib, f"sclgpu_{f}_vec_equal{suf}", _int, _vp, _vp, _vp, _u64, C.POINTER(_int))
             _sig(lib, f"sclgpu_{f}_dot{suf}", _int, _vp, _vp, _vp, _u64, _vp)
             _sig(lib, f"sclgpu_{f}_sum{suf}", _int, _vp, _vp, _u64, _vp)
             _sig(lib, f"sclgpu_{f}_matvec{suf}", _int, _vp, _vp, _u32, _u32, _vp, _vp)

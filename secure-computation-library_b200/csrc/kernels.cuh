@@ -974,6 +974,19 @@ k_sum_final(const typename F::E* __restrict__ partial, uint32_t m, typename F::E
   if (threadIdx.x == 0) out[0] = s;
 }
 
+// Vector::equals (vector.h:358-375): number of positions where a and b differ, accumulated over the
+// whole vector like the reference does (no early exit); the host turns "count == 0" into the bool.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_vec_mismatch(const typename F::E* __restrict__ a, const typename F::E* __restrict__ b, uint64_t n,
+               unsigned long long* __restrict__ count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) local += !F::eq(a[i], b[i]);
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
 // ==================================================== Matrix::multiply(Vector)
 // matrix.h:498-513: y[r] = innerProd(row r, x).  One CTA per row; A is streamed
 // once with coalesced loads (8 bytes of HBM traffic per modmul), x comes from L2.

@@ -1580,6 +1580,43 @@ static int vec_host(sclgpu_ctx* ctx, int op, const void* a, const void* b, const
   extern "C" int sclgpu_##SUF##_dot_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 4, a, b, 0, 0, 0, n, o); }  \
   extern "C" int sclgpu_##SUF##_sum_dev(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return vec_dev<F>(c, 5, a, 0, 0, 0, 0, n, o); }
 
+// Vector::equals (vector.h:358-375): *equal = 1 iff all n elements agree (sizes are the caller's check)
+template <class F>
+static int vec_equal_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* a, const typename F::E* b, uint64_t n, int* equal) {
+  *equal = 1;
+  if (n == 0) return SCLGPU_OK;
+  CK(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
+  k_vec_mismatch<F><<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(a, b, n, ctx->d_count);
+  CKL();
+  unsigned long long bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->d_count, sizeof(bad), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *equal = bad == 0;
+  return SCLGPU_OK;
+}
+template <class F>
+static int vec_equal_dev(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, int* equal) {
+  typedef typename F::E E;
+  if (!ctx || !equal || (n && (!a || !b))) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  return vec_equal_on<F>(ctx, ctx->stream, (const E*)a, (const E*)b, n, equal);
+}
+template <class F>
+static int vec_equal_host(sclgpu_ctx* ctx, const void* a, const void* b, uint64_t n, int* equal) {
+  typedef typename F::E E;
+  if (!ctx || !equal || (n && (!a || !b))) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  HostOp hop(ctx);
+  void *da, *db;
+  RET(hop.up(a, n * sizeof(E), &da));
+  RET(hop.up(b, n * sizeof(E), &db));
+  return vec_equal_on<F>(ctx, hop.st, (const E*)da, (const E*)db, n, equal);
+}
+extern "C" int sclgpu_fp61_vec_equal(sclgpu_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n, int* eq) { return vec_equal_host<F61>(c, a, b, n, eq); }
+extern "C" int sclgpu_fp127_vec_equal(sclgpu_ctx* c, const void* a, const void* b, uint64_t n, int* eq) { return vec_equal_host<F127>(c, a, b, n, eq); }
+extern "C" int sclgpu_fp61_vec_equal_dev(sclgpu_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n, int* eq) { return vec_equal_dev<F61>(c, a, b, n, eq); }
+extern "C" int sclgpu_fp127_vec_equal_dev(sclgpu_ctx* c, const void* a, const void* b, uint64_t n, int* eq) { return vec_equal_dev<F127>(c, a, b, n, eq); }
+
 SCLGPU_VEC_API(fp61, F61, uint64_t*, const uint64_t*)
 SCLGPU_VEC_API(fp127, F127, void*, const void*)
 

@@ -246,6 +246,7 @@ int main() {
     REQUIRE(sclgpu::scalarMultiply(ctx, v, w[3]).equals(v.scalarMultiply(w[3])));
     REQUIRE(sclgpu::dot(ctx, v, w) == v.dot(w));
     REQUIRE(sclgpu::sum(ctx, v) == v.sum());
+    REQUIRE(sclgpu::equals(ctx, v, v) && !sclgpu::equals(ctx, v, w) && !sclgpu::equals(ctx, v, math::Vector<Fp61>(3)));
     const auto e = v, bb = w, d = sclgpu::add(ctx, v, v), aa = sclgpu::multiplyEntryWise(ctx, w, w), c = sclgpu::subtract(ctx, w, v);
     const auto z = e.multiplyEntryWise(bb).add(d.multiplyEntryWise(aa)).add(c).add(e.multiplyEntryWise(d));
     REQUIRE(sclgpu::beaverCombine(ctx, e, bb, d, aa, c).equals(z));

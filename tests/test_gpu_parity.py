@@ -233,6 +233,21 @@ def test_vec_ops_vs_oracle(ctx, orc, field, n):
 
 
 @pytest.mark.parametrize("field", [61, 127])
+def test_vec_equal(ctx, port, field):
+    """Vector::equals (vector.h:358-375, test_vector.cc): equal, one element off (first / last / middle), sizes."""
+    for n in (1, 2, 1000, (1 << 18) + 5):
+        a = port.vector_random(field, "eq", 0, n)
+        assert ctx.vec_equal(field, a, a.copy())
+        for pos in {0, n - 1, n // 2}:
+            b = a.copy()
+            b.reshape(n, -1)[pos, -1] ^= np.uint64(1 << 40)
+            assert not ctx.vec_equal(field, a, b)
+    assert not ctx.vec_equal(field, port.vector_random(field, "eq", 0, 4), port.vector_random(field, "eq", 0, 5))
+    e = port.from_ints([], field)
+    assert ctx.vec_equal(field, e, e)
+
+
+@pytest.mark.parametrize("field", [61, 127])
 def test_field_edge_values(ctx, port, field):
     p = P[field]
     vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, (1 << 60) + 5, p // 3, (1 << 32) - 1, 1 << 32]
