@@ -1,16 +1,17 @@
-// matmul_tc.cu -- Matrix<Fp61>::multiply(Matrix) (include/scl/math/matrix.h:476-495) on the
-// 5th-generation tensor cores, and a generic integer-pipe kernel for every other case.
+// matmul_tc.cu -- Matrix<Fp>::multiply(Matrix) (include/scl/math/matrix.h:476-495) on the
+// 5th-generation tensor cores (both fields), and a generic integer-pipe kernel for the remaining shapes.
 //
 // Same byte-limb identity as the Shamir kernels (share_tc.cu): with a_{ik} = sum_a a_{ik,a} 2^(8a)
 // (the eight bytes of the canonical residue) and C_{kj,a} = b_{kj} 2^(8a) mod p = sum_s C_{kj,a,s} 2^(8s)
 //     (A B)_{ij} = sum_s 2^(8s) * acc_{ij,s},    acc_{ij,s} = sum_{k,a} a_{ik,a} * C_{kj,a,s}
-// which is a u8 x u8 -> s32 GEMM with inner dimension 8K (exact while 8K * 255^2 < 2^31, i.e. up to
-// 4096 elements of K per accumulation round).  B is expanded ONCE into that limb image
-// (k_matmul61_prep: 64 bytes per element, stored tile by tile in the canonical 128B-swizzled
+// which is a u8 x u8 -> s32 GEMM with inner dimension BYTES*K (exact while BYTES*K * 255^2 < 2^31, i.e. up to
+// 32768 bytes = 4096 Fp61 / 2048 Fp127 elements of K per accumulation round).  BYTES = 8 limbs for Fp61, 16 for
+// Fp127 (then a, s = 0..15, 2^127 = 1).  B is expanded ONCE into that limb image
+// (k_matmul_prep: BYTES^2 bytes per element, stored tile by tile in the canonical 128B-swizzled
 // K-major layout tcgen05 reads), A is used as it lies in memory: a row-major row of A is already a
 // K-major operand row.
 //
-// k_matmul61_tc: one CTA per 128 x 32 tile of the result.  Per 16-element chunk of K (128 bytes of
+// k_matmul_tc<F, RT>: one CTA per (128 RT) x (256 / BYTES) tile of the result.  Per chunk of K (128 bytes of
 // an A row): cp.async brings the A chunk (16 KiB, swizzled on the fly) and the matching 32 KiB of
 // the limb image into a 4-stage shared-memory ring; one thread issues four
 // tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32 bytes) accumulating in 256 TMEM columns;
@@ -34,7 +35,7 @@ template <int RT> struct MmCfg {
   static constexpr uint32_t kStage = RT * kMmATile + kMmBTileBytes;
   static constexpr uint32_t kDynSmem = kStages * kStage + 1024u + 256u;
 };
-static constexpr uint32_t kMmRoundChunks = 4096u / kMmKChunk;         // accumulation round: 4096 elements of K
+static constexpr uint32_t kMmRoundChunks = 32768u / 128u;             // accumulation round: 32768 bytes of K per A row
 static constexpr uint32_t kMmRaster = 8;                              // CTA row tiles per rasterisation band
 
 __device__ __forceinline__ uint32_t mm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,43 +96,121 @@ __device__ __forceinline__ uint64_t mm_combine(const uint32_t* v) {
   return r >= F61::P ? r - F61::P : r;
 }
 
-// ---- limb image of B: tile (jt, kc) = 32 columns x 16 rows of B -> 256 x 128 bytes, stored at
-// ((jt * KC) + kc) * 32 KiB in the canonical swizzled layout.  One CTA per tile; thread (jl, q) takes the
-// two elements B[kc*16 + 2q .. +1][jt*32 + jl] and writes, for every limb s, the 16-byte chunk q of row
-// (jl, s): the eight threads q = 0..7 of a row together write its whole 128-byte line.
-__global__ void __launch_bounds__(256)
-k_matmul61_prep(const uint64_t* __restrict__ B, uint32_t K, uint32_t N, uint32_t KC, uint8_t* __restrict__ img) {
-  const uint32_t kc = blockIdx.x % KC, jt = blockIdx.x / KC;
-  const uint32_t q = threadIdx.x & 7u, jl = threadIdx.x >> 3;
-  const uint32_t j = jt * kMmNTile + jl, k0 = kc * kMmKChunk + 2u * q;
-  uint64_t c0 = (j < N && k0 < K) ? B[(uint64_t)k0 * N + j] : 0;
-  uint64_t c1 = (j < N && k0 + 1 < K) ? B[(uint64_t)(k0 + 1) * N + j] : 0;
-  uint64_t ca[16];  // c * 2^(8a), a = 0..7, for both elements
+// sixteen limbs v[s] < 2^31 at 2^(8s) -> canonical residue mod 2^127 - 1.  The four residue classes of s mod 4
+// are word aligned (v_r, v_r+4, v_r+8, v_r+12 concatenate into a 128-bit number S_r); X = sum_r S_r << 8r is
+// formed in five 32-bit words, folded at bit 127 twice, and p is mapped to 0.
+__device__ __forceinline__ E127 mm_combine127(const uint32_t* v) {
+  uint32_t x0 = v[0], x1 = v[4], x2 = v[8], x3 = v[12], x4 = 0;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    ca[a] = c0;
-    ca[8 + a] = c1;
-    c0 = F61::mul(c0, 256);
-    c1 = F61::mul(c1, 256);
+  for (int r = 1; r < 4; ++r) {
+    const uint32_t a0 = v[r], a1 = v[r + 4], a2 = v[r + 8], a3 = v[r + 12];
+    const uint32_t w0 = a0 << (8 * r), w1 = __funnelshift_l(a0, a1, 8 * r), w2 = __funnelshift_l(a1, a2, 8 * r),
+                   w3 = __funnelshift_l(a2, a3, 8 * r), w4 = a3 >> (32 - 8 * r);
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, %9;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4)
+        : "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4));
   }
+  // X < 2^152: hi = X >> 127 < 2^25
+  uint32_t hi = __funnelshift_l(x3, x4, 1);
+  x3 &= 0x7FFFFFFFu;
+  asm("add.cc.u32 %0, %0, %4;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.u32 %3, %3, 0;"
+      : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3)
+      : "r"(hi));
+  x0 += x3 >> 31;  // < 2^127 + 2^25: if bit 127 is set the rest is < 2^25, no ripple
+  x3 &= 0x7FFFFFFFu;
+  const bool is_p = (x0 & x1 & x2 & (x3 | 0x80000000u)) == 0xFFFFFFFFu;
+  E127 r;
+  r.lo = is_p ? 0 : ((uint64_t)x0 | ((uint64_t)x1 << 32));
+  r.hi = is_p ? 0 : ((uint64_t)x2 | ((uint64_t)x3 << 32));
+  return r;
+}
+
+template <class F> struct MmField;
+template <> struct MmField<F61> {
+  static constexpr uint32_t kKChunk = 16, kNTile = 32;      // 128 / 8, 256 / 8
+  static __device__ __forceinline__ uint64_t combine(const uint32_t* v) { return mm_combine(v); }
+};
+template <> struct MmField<F127> {
+  static constexpr uint32_t kKChunk = 8, kNTile = 16;       // 128 / 16, 256 / 16
+  static __device__ __forceinline__ E127 combine(const uint32_t* v) { return mm_combine127(v); }
+};
+
+// ---- limb image of B: tile (jt, kc) = kNTile columns x kKChunk rows of B -> 256 x 128 bytes, stored at
+// ((jt * KC) + kc) * 32 KiB in the canonical swizzled layout.  One CTA per tile; the eight threads q = 0..7 of
+// an image row (jl, s) each write its 16-byte chunk q, together the whole 128-byte line.
+//   Fp61 : thread (jl 0..31, q): elements B[kc*16 + 2q .. +1][jt*32 + jl], rows s = 0..7
+//   Fp127: thread (jl 0..15, q, h 0..1): element B[kc*8 + q][jt*16 + jl], rows s = 8h .. 8h+7
+template <class F>
+__global__ void __launch_bounds__(256)
+k_matmul_prep(const typename F::E* __restrict__ B, uint32_t K, uint32_t N, uint32_t KC, uint8_t* __restrict__ img) {
+  const uint32_t kc = blockIdx.x % KC, jt = blockIdx.x / KC;
+  const uint32_t q = threadIdx.x & 7u;
   uint8_t* tile = img + (uint64_t)blockIdx.x * kMmBTileBytes;
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    uint64_t w0 = 0, w1 = 0;  // bytes a = 0..7: byte_s(C_a) of element k0 and of element k0 + 1
+  if constexpr (F::BYTES == 8) {
+    const uint32_t jl = threadIdx.x >> 3;
+    const uint32_t j = jt * 32u + jl, k0 = kc * 16u + 2u * q;
+    uint64_t c0 = (j < N && k0 < K) ? B[(uint64_t)k0 * N + j] : 0;
+    uint64_t c1 = (j < N && k0 + 1 < K) ? B[(uint64_t)(k0 + 1) * N + j] : 0;
+    uint64_t ca[16];  // c * 2^(8a), a = 0..7, for both elements
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-      w0 |= ((ca[a] >> (8 * s)) & 0xFFull) << (8 * a);
-      w1 |= ((ca[8 + a] >> (8 * s)) & 0xFFull) << (8 * a);
+      ca[a] = c0;
+      ca[8 + a] = c1;
+      c0 = F61::mul(c0, 256);
+      c1 = F61::mul(c1, 256);
     }
-    const uint32_t r = jl * 8u + s;
-    *reinterpret_cast<ulonglong2*>(tile + (r >> 3) * 1024u + (r & 7u) * 128u + ((q ^ (r & 7u)) << 4)) = make_ulonglong2(w0, w1);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      uint64_t w0 = 0, w1 = 0;  // bytes a = 0..7: byte_s(C_a) of element k0 and of element k0 + 1
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        w0 |= ((ca[a] >> (8 * s)) & 0xFFull) << (8 * a);
+        w1 |= ((ca[8 + a] >> (8 * s)) & 0xFFull) << (8 * a);
+      }
+      const uint32_t r = jl * 8u + s;
+      *reinterpret_cast<ulonglong2*>(tile + (r >> 3) * 1024u + (r & 7u) * 128u + ((q ^ (r & 7u)) << 4)) = make_ulonglong2(w0, w1);
+    }
+  } else {
+    const uint32_t jl = (threadIdx.x >> 3) & 15u, h = threadIdx.x >> 7;
+    const uint32_t j = jt * 16u + jl, k = kc * 8u + q;
+    E127 c = (j < N && k < K) ? B[(uint64_t)k * N + j] : E127{0, 0};
+    E127 ca[16];  // c * 2^(8a), a = 0..15
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      ca[a] = c;
+      c = F127::mul(c, E127{256, 0});
+    }
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) {
+      const uint32_t s = h * 8u + ss;  // limb = byte s of the 16-byte residue
+      uint64_t w0 = 0, w1 = 0;         // bytes a = 0..7 and a = 8..15 of image row (jl, s)
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        const uint64_t word = (h == 0) ? ca[a].lo : ca[a].hi;
+        const uint64_t byte = (word >> (8 * ss)) & 0xFFull;
+        if (a < 8) w0 |= byte << (8 * a);
+        else w1 |= byte << (8 * (a - 8));
+      }
+      const uint32_t r = jl * 16u + s;
+      *reinterpret_cast<ulonglong2*>(tile + (r >> 3) * 1024u + (r & 7u) * 128u + ((q ^ (r & 7u)) << 4)) = make_ulonglong2(w0, w1);
+    }
   }
 }
 
-template <int RT>
+template <class F, int RT>
 __global__ void __launch_bounds__(kMmThreads, 1)
-k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint8_t* __restrict__ img, uint32_t KC,
-              uint32_t N, uint32_t NT, uint64_t* __restrict__ C) {
+k_matmul_tc(const typename F::E* __restrict__ A, uint32_t M, uint32_t K, const uint8_t* __restrict__ img, uint32_t KC,
+            uint32_t N, uint32_t NT, typename F::E* __restrict__ C) {
+  typedef typename F::E E;
+  constexpr uint32_t kMmKChunk = MmField<F>::kKChunk, kMmNTile = MmField<F>::kNTile;
+  constexpr uint32_t kPieceElems = 16u / F::BYTES;    // elements per 16-byte cp.async piece
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   constexpr uint32_t kMmStages = MmCfg<RT>::kStages, kMmStage = MmCfg<RT>::kStage;
   constexpr uint32_t kRows = 128u * RT;               // result rows per CTA
@@ -172,9 +251,9 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
 #pragma unroll
     for (uint32_t q = tid; q < 1024u * RT; q += kMmThreads) {
       const uint32_t row = q >> 3, piece = q & 7u;
-      const uint32_t k = kc * kMmKChunk + piece * 2u;
-      const bool in = (m0 + row < M) && (k < K);  // K is even: a piece is inside or outside as a whole
-      const uint64_t* src = A + (uint64_t)(in ? m0 + row : 0) * K + (in ? k : 0);
+      const uint32_t k = kc * kMmKChunk + piece * kPieceElems;
+      const bool in = (m0 + row < M) && (k < K);  // Fp61: K is even, so a piece is inside or outside as a whole
+      const E* src = A + (uint64_t)(in ? m0 + row : 0) * K + (in ? k : 0);
       mm_cp16(st + (row >> 3) * 1024u + (row & 7u) * 128u + ((piece ^ (row & 7u)) << 4), src, in ? 16u : 0u);
     }
     // limb image tile: already in shared-memory layout
@@ -183,9 +262,9 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
     for (uint32_t q = tid; q < kMmBTileBytes / 16u; q += kMmThreads) mm_cp16(st + RT * kMmATile + q * 16u, bsrc + q * 16u, 16u);
   };
 
-  uint64_t acc[kMmNTile];
+  E acc[kMmNTile];
 #pragma unroll
-  for (uint32_t j = 0; j < kMmNTile; ++j) acc[j] = 0;
+  for (uint32_t j = 0; j < kMmNTile; ++j) acc[j] = F::zero();
   uint32_t done_phase = 0;
   // empty[s] completes once per chunk that used stage s (tcgen05.commit after its MMAs), in chunk order:
   // before chunk kc (>= stages) may overwrite its stage, completion number kc/stages - 1 must have happened
@@ -226,7 +305,7 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
         if (kc + 1 == r1) mm_commit(done_bar);
       }
     }
-    // drain this accumulation round (at most 4096 elements of K: the s32 accumulators are exact)
+    // drain this accumulation round (at most 32768 bytes of K per row: the s32 accumulators are exact)
     mm_wait(done_bar, done_phase);
     done_phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -236,8 +315,10 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
       for (uint32_t g = 0; g < 8; ++g) {
         uint32_t v[32];
         mm_tmem_ld32(tmem + (warp >> 2) * 256u + lane_off + g * 32u, v);
+        constexpr uint32_t kPer = 32u / F::BYTES;  // outputs per 32 TMEM columns
 #pragma unroll
-        for (uint32_t jj = 0; jj < 4; ++jj) acc[g * 4 + jj] = F61::add(acc[g * 4 + jj], mm_combine(v + 8 * jj));
+        for (uint32_t jj = 0; jj < kPer; ++jj)
+          acc[g * kPer + jj] = F::add(acc[g * kPer + jj], MmField<F>::combine(v + F::BYTES * jj));
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -246,7 +327,7 @@ k_matmul61_tc(const uint64_t* __restrict__ A, uint32_t M, uint32_t K, const uint
   if (warp < 4u * RT) {
     const uint32_t row = m0 + tid;
     if (row < M) {
-      uint64_t* dst = C + (uint64_t)row * N + (uint64_t)jt * kMmNTile;
+      E* dst = C + (uint64_t)row * N + (uint64_t)jt * kMmNTile;
 #pragma unroll
       for (uint32_t j = 0; j < kMmNTile; ++j)
         if (jt * kMmNTile + j < N) dst[j] = acc[j];
@@ -282,30 +363,41 @@ k_matmul_generic(const typename F::E* __restrict__ A, uint32_t M, uint32_t K, co
   }
 }
 
-size_t matmul61_image_bytes(uint32_t K, uint32_t N) {
-  const uint64_t KC = (K + kMmKChunk - 1) / kMmKChunk, NT = (N + kMmNTile - 1) / kMmNTile;
+template <class F>
+static size_t image_bytes_t(uint32_t K, uint32_t N) {
+  const uint64_t KC = (K + MmField<F>::kKChunk - 1) / MmField<F>::kKChunk, NT = (N + MmField<F>::kNTile - 1) / MmField<F>::kNTile;
   return (size_t)(KC * NT * kMmBTileBytes);
 }
+size_t matmul61_image_bytes(uint32_t K, uint32_t N) { return image_bytes_t<F61>(K, N); }
+size_t matmul127_image_bytes(uint32_t K, uint32_t N) { return image_bytes_t<F127>(K, N); }
 
-cudaError_t matmul61_tc_launch(cudaStream_t st, int sm_count, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B,
-                               uint32_t N, uint8_t* d_img, uint64_t* d_C) {
-  const uint32_t KC = (K + kMmKChunk - 1) / kMmKChunk, NT = (N + kMmNTile - 1) / kMmNTile;
-  (void)sm_count;
-  k_matmul61_prep<<<KC * NT, 256, 0, st>>>(d_B, K, N, KC, d_img);
+template <class F>
+static cudaError_t matmul_tc_launch_t(cudaStream_t st, const typename F::E* d_A, uint32_t M, uint32_t K, const typename F::E* d_B,
+                                      uint32_t N, uint8_t* d_img, typename F::E* d_C) {
+  const uint32_t KC = (K + MmField<F>::kKChunk - 1) / MmField<F>::kKChunk, NT = (N + MmField<F>::kNTile - 1) / MmField<F>::kNTile;
+  k_matmul_prep<F><<<KC * NT, 256, 0, st>>>(d_B, K, N, KC, d_img);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (M > 128) {  // two row tiles per CTA: every image chunk feeds twice the MMAs
-    e = cudaFuncSetAttribute(k_matmul61_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmCfg<2>::kDynSmem);
+    e = cudaFuncSetAttribute(k_matmul_tc<F, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmCfg<2>::kDynSmem);
     if (e != cudaSuccess) return e;
     const uint32_t MT = (M + 255) / 256, bands = (MT + kMmRaster - 1) / kMmRaster;
-    k_matmul61_tc<2><<<bands * kMmRaster * NT, kMmThreads, MmCfg<2>::kDynSmem, st>>>(d_A, M, K, d_img, KC, N, NT, d_C);
+    k_matmul_tc<F, 2><<<bands * kMmRaster * NT, kMmThreads, MmCfg<2>::kDynSmem, st>>>(d_A, M, K, d_img, KC, N, NT, d_C);
   } else {
-    e = cudaFuncSetAttribute(k_matmul61_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmCfg<1>::kDynSmem);
+    e = cudaFuncSetAttribute(k_matmul_tc<F, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmCfg<1>::kDynSmem);
     if (e != cudaSuccess) return e;
     const uint32_t MT = (M + 127) / 128, bands = (MT + kMmRaster - 1) / kMmRaster;
-    k_matmul61_tc<1><<<bands * kMmRaster * NT, kMmThreads, MmCfg<1>::kDynSmem, st>>>(d_A, M, K, d_img, KC, N, NT, d_C);
+    k_matmul_tc<F, 1><<<bands * kMmRaster * NT, kMmThreads, MmCfg<1>::kDynSmem, st>>>(d_A, M, K, d_img, KC, N, NT, d_C);
   }
   return cudaGetLastError();
+}
+cudaError_t matmul61_tc_launch(cudaStream_t st, int, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B, uint32_t N,
+                               uint8_t* d_img, uint64_t* d_C) {
+  return matmul_tc_launch_t<F61>(st, d_A, M, K, d_B, N, d_img, d_C);
+}
+cudaError_t matmul127_tc_launch(cudaStream_t st, int, const E127* d_A, uint32_t M, uint32_t K, const E127* d_B, uint32_t N,
+                                uint8_t* d_img, E127* d_C) {
+  return matmul_tc_launch_t<F127>(st, d_A, M, K, d_B, N, d_img, d_C);
 }
 
 cudaError_t matmul61_generic_launch(cudaStream_t st, int sm_count, const uint64_t* A, uint32_t M, uint32_t K, const uint64_t* B,

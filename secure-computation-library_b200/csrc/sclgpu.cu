@@ -1686,7 +1686,16 @@ static int matmul_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, u
       e = matmul61_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
     }
   } else {
-    e = matmul127_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
+    const bool tc = (uint64_t)rows * cols * inner >= (1ull << 16) && getenv("SCLGPU_MATMUL_GENERIC") == nullptr;
+    if (tc) {
+      void* img = nullptr;
+      CK(cudaMallocAsync(&img, matmul127_image_bytes(inner, cols), st));
+      ctx->launches++;
+      e = matmul127_tc_launch(st, ctx->sm_count, A, rows, inner, B, cols, (uint8_t*)img, C);
+      cudaFreeAsync(img, st);
+    } else {
+      e = matmul127_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
+    }
   }
   if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
   return SCLGPU_OK;

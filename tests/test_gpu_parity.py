@@ -275,11 +275,12 @@ def test_matvec_golden_and_vs_oracle(ctx, orc, port, golden):
 
 @pytest.mark.parametrize("field,rows,inner,cols", [
     (61, 128, 16, 32), (61, 1, 2, 1), (61, 300, 520, 70), (61, 129, 4100, 33), (61, 64, 8200, 40), (61, 257, 130, 257),
-    (61, 5, 7, 3), (61, 200, 333, 100), (127, 40, 50, 30), (127, 3, 1, 2)])
+    (61, 5, 7, 3), (61, 200, 333, 100), (127, 40, 50, 30), (127, 3, 1, 2), (127, 130, 520, 40), (127, 200, 2100, 20),
+    (127, 257, 9, 33), (127, 64, 64, 16), (127, 129, 31, 17)])
 def test_matmul_vs_oracle(ctx, pkg, port, field, rows, inner, cols):
-    """Matrix::multiply(Matrix) (matrix.h:476-495).  Fp61 with even inner dimension runs on the tensor cores
-    (inner > 4096: more than one accumulation round; ragged tiles in every dimension), everything else on the
-    integer pipe; edge residues 0, 1, p-1 planted in both operands."""
+    """Matrix::multiply(Matrix) (matrix.h:476-495).  Fp61 with even inner dimension and Fp127 run on the tensor
+    cores (inner > 4096 / 2048: more than one accumulation round; ragged tiles in every dimension), tiny or
+    odd-inner Fp61 products on the integer pipe; edge residues 0, 1, p-1 planted in both operands."""
     sh = () if field == 61 else (2,)
     A = port.vector_random(field, "mat A", 0, rows * inner).reshape((rows, inner) + sh).copy()
     Bm = port.vector_random(field, "mat B", 7, inner * cols).reshape((inner, cols) + sh).copy()
@@ -298,6 +299,15 @@ def test_matmul_all_max_residues(ctx, port):
     Bm = np.full((inner, cols), P[61] - 1, dtype=np.uint64)
     got = ctx.matmul(61, A, Bm)
     assert np.all(got == np.uint64(inner % P[61]))
+
+
+def test_matmul_all_max_residues_fp127(ctx, port):
+    rows, inner, cols = 128, 2048, 16
+    pm1 = port.from_ints([P[127] - 1], 127)[0]
+    A = np.broadcast_to(pm1, (rows, inner, 2)).copy()
+    Bm = np.broadcast_to(pm1, (inner, cols, 2)).copy()
+    got = ctx.matmul(127, A, Bm)
+    assert ints(port, got, 127) == [inner] * (rows * cols)
 
 
 def test_matmul_errors_and_golden_identity(ctx, pkg, port):
