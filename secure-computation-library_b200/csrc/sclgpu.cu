@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -81,10 +82,9 @@ static int cuda_fail(sclgpu_ctx* ctx, cudaError_t e, const char* what) {
 // FIPS-197 5.2 (== aes128LoadKey, prg.cc:54-75).  S-box from its definition.
 static uint8_t g_sbox[256];
 static uint32_t g_t0[256];
-static bool g_aes_ready = false;
+static std::once_flag g_aes_once;
 
-static void aes_host_init() {
-  if (g_aes_ready) return;
+static void aes_host_init_once() {
   uint8_t p = 1, q = 1;
   do {
     p = (uint8_t)(p ^ (p << 1) ^ ((p & 0x80) ? 0x1b : 0));
@@ -103,8 +103,8 @@ static void aes_host_init() {
     const uint8_t s3 = (uint8_t)(s2 ^ s);
     g_t0[i] = (uint32_t)s2 | ((uint32_t)s << 8) | ((uint32_t)s << 16) | ((uint32_t)s3 << 24);
   }
-  g_aes_ready = true;
 }
+static void aes_host_init() { std::call_once(g_aes_once, aes_host_init_once); }  // contexts may be created on several threads
 
 static AesKey aes_expand(const uint8_t seed[16]) {
   static const uint8_t rcon[10] = {0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36};
