@@ -387,10 +387,11 @@ static int g_share_tc = -1;
 static bool share_tc_enabled() {
   if (g_share_tc < 0) {
     // 0 = integer-pipe kernel (k_share61); tcgen05 kernels: 1 = A operand in shared memory (3 groups),
-    // 2 / 3 = A operand in tensor memory with 4 / 5 groups of warps (3 is the default)
+    // 2 / 3 = A operand in tensor memory with 4 / 5 groups of warps (3 is the default),
+    // 4 = warp-specialised: 4 producer groups (AES) + 2 consumer groups (MMA, epilogue)
     const char* e = getenv("SCLGPU_SHARE_TC");
     g_share_tc = e ? atoi(e) : 3;
-    if (g_share_tc < 0 || g_share_tc > 3) g_share_tc = 3;
+    if (g_share_tc < 0 || g_share_tc > 4) g_share_tc = 3;
   }
   return g_share_tc != 0;
 }

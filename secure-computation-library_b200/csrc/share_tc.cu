@@ -529,6 +529,198 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
   }
 }
 
+// ---------------------------------------------------------------------------
+// Warp-specialised variant (variant 4).  The groups of k_share_tcm alternate between the AES phase (LSU + ALU)
+// and the MMA / epilogue phase, so the LSU -- the limiting pipe -- idles whenever several groups happen to be in
+// their epilogues.  Here the roles are fixed: 4 PRODUCER groups (16 warps) only draw keystream into double-
+// buffered A rows in tensor memory, 2 CONSUMER groups (8 warps) only issue the MMAs, drain the accumulators and
+// store; consumer c serves producers 2c and 2c+1.  Hand-off through mbarriers: fullA[pg][buf] (128 producer
+// arrivals after tcgen05.wait::st), emptyA[pg][buf] (tcgen05.commit after the tile's last MMA), dfull[c][b]
+// (tcgen05.commit per pass); the consumer's own accumulator reuse is ordered by a named barrier.
+// TMEM: 4 x 2 x 32 columns of A + 2 x 2 x 64 of D = 512.  Measured (2^26, n=32, t=15): 11.67 ms against 11.06 ms for
+// k_share_tcm<F61,5,1,64> -- the unspecialised groups already keep ~16 warps in the AES phase, and the limit is the
+// joint saturation of the LSU and ALU pipes, not phase bubbles.  Kept selectable (SCLGPU_SHARE_TC=4) and tested.
+static constexpr int kWsProducers = 4, kWsConsumers = 2;
+static constexpr int kWsThreads = 128 * (kWsProducers + kWsConsumers);
+
+template <class F>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_share_ws(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0, const uint4* __restrict__ g_bmat,
+           uint64_t first_block, const typename F::E* __restrict__ secrets, uint64_t N, uint32_t t, uint32_t n,
+           typename F::E* __restrict__ out, uint64_t stride_i, uint64_t stride_j) {
+  typedef typename F::E E;
+  constexpr uint32_t EB = F::BYTES;
+  constexpr uint32_t PCOLS = 64, kPassParties = PCOLS / EB, kLdParties = 32u / EB;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t dyn = smem_u32(dyn_smem);
+  const uint32_t tbase = aes_table_base(dyn_smem);
+  const uint32_t b_base = tbase + kAesTableBytes;
+  const uint32_t ctl = b_base + kTcBmatBytes;  // fullA[4][2] | emptyA[4][2] | dfull[2][2] | TMEM address
+  if (ctl + 256u > dyn + kTcmDynSmem + 128u) __trap();
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_full = ctl, bar_empty = ctl + 64u, bar_dfull = ctl + 128u, tmem_slot = ctl + 160u;
+
+  aes_fill_tables(tbase, g_t0);
+  for (uint32_t e = tid; e < kTcBmatBytes / 16; e += kWsThreads) {
+    const uint4 w = __ldg(g_bmat + e);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint32_t i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(bar_full + 8u * i) : "memory");
+    for (uint32_t i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_empty + 8u * i) : "memory");
+    for (uint32_t i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_dfull + 8u * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+  const uint32_t nblk = ((t + 1u) * EB + 15u) / 16u;
+  const uint32_t ksteps = ((t + 1u) * EB + 31u) / 32u;
+  const uint32_t npass = (n + kPassParties - 1u) / kPassParties;
+  const uint64_t tiles = (N + 127u) / 128u;
+  const uint64_t tile_stride = (uint64_t)gridDim.x * kWsProducers;
+  const uint32_t gt = tid & 127u;
+  const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
+
+  if (warp < 4u * kWsProducers) {
+    // ------------------------------------------------------------------ producer: AES-CTR -> A rows in TMEM
+    uint32_t lanebase = tbase + (tid & 31u) * 4u;
+    asm volatile("" : "+r"(lanebase)::"memory");
+    const uint32_t pg = warp >> 2;
+    uint32_t it = 0;
+    for (uint64_t tile = (uint64_t)blockIdx.x * kWsProducers + pg; tile < tiles; tile += tile_stride, ++it) {
+      const uint32_t buf = it & 1u;
+      if (it >= 2u) mbar_wait(bar_empty + 8u * (pg * 2u + buf), ((it >> 1) - 1u) & 1u);  // MMAs of tile it-2 are done with this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t j = tile * 128u + gt;
+      const uint64_t jj = j < N ? j : N - 1;
+      const uint32_t a_lane = tmem + pg * 64u + buf * 32u + lane_off;
+      uint32_t s0, s1, s2 = 0, s3 = 0;
+      if constexpr (EB == 8) {
+        const uint64_t sec = secrets[jj];
+        s0 = (uint32_t)sec;
+        s1 = (uint32_t)(sec >> 32);
+      } else {
+        const E sec = secrets[jj];
+        s0 = (uint32_t)sec.lo;
+        s1 = (uint32_t)(sec.lo >> 32);
+        s2 = (uint32_t)sec.hi;
+        s3 = (uint32_t)(sec.hi >> 32);
+      }
+      const uint64_t ctr0 = first_block + jj * nblk;
+      if (t == 0 || EB == 16)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+      if (t != 0) {
+        PrgGroup grp;
+        const uint32_t b0 = (EB == 16) ? 1u : 0u;
+        uint64_t gid = (ctr0 + b0) >> 8;
+        prg_group(key, lanebase, ctr0 + b0, grp);
+#pragma unroll 1
+        for (uint32_t b = b0; b < nblk; ++b) {
+          const uint64_t ctr = ctr0 + b;
+          if ((ctr >> 8) != gid) {
+            gid = ctr >> 8;
+            prg_group(key, lanebase, ctr, grp);
+          }
+          uint32_t o0, o1, o2, o3;
+          prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+          if (EB == 8 && b == 0) {
+            o0 = s0;
+            o1 = s1;
+          }
+          __syncwarp();
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8u * (pg * 2u + buf)) : "memory");
+    }
+  } else {
+    // ------------------------------------------------------------------ consumer: MMA issue, drain, recombine, store
+    const uint32_t cg = (warp >> 2) - kWsProducers;       // 0, 1
+    const uint32_t d0 = tmem + 256u + cg * 128u;          // two 64-column accumulators
+    const uint32_t df0 = bar_dfull + 16u * cg, df1 = df0 + 8u;
+    uint32_t ph0 = 0, ph1 = 0;
+    auto emit = [&](const uint32_t (&v)[32], E* dst, uint32_t first_party) {
+#pragma unroll
+      for (uint32_t ii = 0; ii < kLdParties; ++ii) {
+        if (first_party + ii < n) {
+          if constexpr (EB == 8) dst[(uint64_t)ii * stride_i] = tc_combine(v + 8 * ii);
+          else dst[(uint64_t)ii * stride_i] = tc_combine127(v + 16 * ii);
+        }
+      }
+    };
+    // tiles in the order the two producers make them: (it, pg) with pg = 2cg, 2cg+1
+    for (uint32_t it = 0;; ++it) {
+      bool any = false;
+      for (uint32_t q = 0; q < 2u; ++q) {
+        const uint32_t pg = 2u * cg + q;
+        const uint64_t tile = (uint64_t)blockIdx.x * kWsProducers + pg + (uint64_t)it * tile_stride;
+        if (tile >= tiles) continue;
+        any = true;
+        const uint32_t buf = it & 1u;
+        const uint32_t a_tm = tmem + pg * 64u + buf * 32u;
+        auto issue_pass = [&](uint32_t p) {
+          const uint32_t b = p & 1u;
+          for (uint32_t ks = 0; ks < ksteps; ++ks)
+            tc_mma_ts(d0 + b * PCOLS, a_tm + ks * 8u, tc_desc(b_base + p * (PCOLS * 128u) + ks * 32u), tc_idesc(PCOLS), ks);
+          tc_commit(b ? df1 : df0);
+          if (p + 1u == npass) tc_commit(bar_empty + 8u * (pg * 2u + buf));  // every MMA reading this A buffer is issued
+        };
+        mbar_wait(bar_full + 8u * (pg * 2u + buf), (it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (gt == 0) {
+          issue_pass(0);
+          if (npass > 1) issue_pass(1);
+        }
+        const uint64_t j = tile * 128u + gt;
+        const bool valid = j < N;
+        for (uint32_t p = 0; p < npass; ++p) {
+          if (p & 1u) {
+            mbar_wait(df1, ph1);
+            ph1 ^= 1u;
+          } else {
+            mbar_wait(df0, ph0);
+            ph0 ^= 1u;
+          }
+          __syncwarp();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t acc = d0 + (p & 1u) * PCOLS + lane_off;
+          E* dst = out + j * stride_j + (uint64_t)(p * kPassParties) * stride_i;
+          uint32_t v[32];
+          tmem_ld32(acc, v);
+          if (valid) emit(v, dst, p * kPassParties);
+          tmem_ld32(acc + 32u, v);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1u + cg) : "memory");  // accumulator drained by all four consumer warps
+          if (gt == 0 && p + 2u < npass) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_pass(p + 2u);
+          }
+          if (valid) emit(v, dst + (uint64_t)kLdParties * stride_i, p * kPassParties + kLdParties);
+        }
+      }
+      if (!any) break;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
 // (variant, groups, accumulators, columns per pass).  Measured at 2^26 secrets, n=32, t=15 on B200
 // (gpurun, CUDA events): A in shared memory 3 groups 13.45 ms | (3,2,64) 12.72 | (4,1,64) 11.70 |
 // (4,2,32) 13.11 | (5,1,64) 11.33 | (5,2,32) 12.42 | (6,1,32) 12.27 | (7,1,32) 12.25 | (8,1,32) 12.19.
@@ -725,10 +917,13 @@ cudaError_t share_tc_prepare() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
   SCLGPU_TCM_VARIANTS(X)
 #undef X
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_ws<F61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTcmDynSmem + 128u));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_ws<F127>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTcmDynSmem + 128u));
   return e;
 }
 
 int tc_variant_groups(int variant) {
+  if (variant == 4) return kWsProducers;
 #define X(V, G, NB, PC) \
   if (variant == V) return G;
   SCLGPU_TCM_VARIANTS(X)
@@ -740,6 +935,10 @@ cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesK
                               uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
                               uint64_t* d_out, uint64_t stride_i, uint64_t stride_j) {
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
+  if (variant == 4) {
+    k_share_ws<F61><<<grid, kWsThreads, kTcmDynSmem + 128u, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    return cudaGetLastError();
+  }
   bool done = false;
 #define X(V, G, NB, PC)                                                                                               \
   if (variant == V) {                                                                                                 \
@@ -758,6 +957,10 @@ cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const Aes
                                const void* d_bmat, uint64_t first_block, const E127* d_secrets, uint64_t N, uint32_t t,
                                uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j) {
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
+  if (variant == 4) {
+    k_share_ws<F127><<<grid, kWsThreads, kTcmDynSmem + 128u, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    return cudaGetLastError();
+  }
   if (variant == 2) {
     k_share_tcm<F127, 4, 1, 64, false><<<grid, 512, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
   } else {

@@ -636,11 +636,12 @@ def test_additive_errors(ctx, pkg, port):
 
 
 # ------------------------------------------------------------------ both Fp61 share kernels
-@pytest.mark.parametrize("tc", ["3", "2", "1", "0"])
+@pytest.mark.parametrize("tc", ["3", "4", "2", "1", "0"])
 def test_share_kernel_paths_vs_oracle(tc):
     """tests/tc_check.py sweeps (t, n, N) on the device-pointer path against the plain-C oracle;
     SCLGPU_SHARE_TC selects the tcgen05 kernels (3 = default: A operand in tensor memory, 5 groups;
-    2 = 4 groups; 1 = A operand in shared memory) or the integer-pipe kernel (0).
+    4 = warp-specialised producers / consumers; 2 = 4 groups; 1 = A operand in shared memory) or the
+    integer-pipe kernel (0).
     A separate process because the library reads the knob once."""
     import os
     import subprocess
