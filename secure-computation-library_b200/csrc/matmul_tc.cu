@@ -341,6 +341,153 @@ k_matmul_tc(const typename F::E* __restrict__ A, uint32_t M, uint32_t K, const u
   }
 }
 
+// ============================================================================================================
+// Second form: pre-tiled A, bulk async copies, warp-specialised roles (the default; the cp.async form above is
+// kept behind SCLGPU_MATMUL_V1 as the measured comparison).
+//   k_matmul_prep_a : A (row-major) -> tiles of 128 rows x 128 bytes in the swizzled K-major layout, zero padded to
+//                     an even number of row tiles, so that a stage is three contiguous bulk copies (any K, any M).
+//   k_matmul_ws     : 10 warps per CTA, one 256 x (256/BYTES) result tile per CTA.
+//                     warp 0 (one lane): producer -- cp.async.bulk of two A tiles and one image tile per stage into a
+//                                        3-stage ring, completion by mbarrier transaction bytes;
+//                     warp 1 (one lane): tcgen05.mma issuer -- 8 MMAs per stage, tcgen05.commit frees the stage;
+//                     warps 2-9        : epilogue -- each drains one 32-lane quadrant of one of the two accumulators.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_matmul_prep_a(const typename F::E* __restrict__ A, uint32_t M, uint32_t K, uint32_t KC, uint8_t* __restrict__ tiles) {
+  typedef typename F::E E;
+  constexpr uint32_t kChunk = MmField<F>::kKChunk, kPiece = 16u / F::BYTES;
+  const uint32_t kc = blockIdx.x % KC, mt = blockIdx.x / KC;
+  uint8_t* tile = tiles + (uint64_t)blockIdx.x * kMmATile;
+#pragma unroll
+  for (uint32_t q = threadIdx.x; q < 1024u; q += 256u) {
+    const uint32_t row = q >> 3, piece = q & 7u;
+    const uint32_t m = mt * 128u + row, k = kc * kChunk + piece * kPiece;
+    E e[kPiece];
+#pragma unroll
+    for (uint32_t i = 0; i < kPiece; ++i) e[i] = (m < M && k + i < K) ? A[(uint64_t)m * K + k + i] : F::zero();
+    uint8_t* dst = tile + (row >> 3) * 1024u + (row & 7u) * 128u + ((piece ^ (row & 7u)) << 4);
+    if constexpr (F::BYTES == 8) *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(e[0], e[1]);
+    else *reinterpret_cast<E127*>(dst) = e[0];
+  }
+}
+
+__device__ __forceinline__ void mm_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+static constexpr uint32_t kWsMmThreads = 320;
+static constexpr uint32_t kWsMmStages = 3;
+static constexpr uint32_t kWsMmStage = 2u * kMmATile + kMmBTileBytes;  // 64 KiB
+static constexpr uint32_t kWsMmDynSmem = kWsMmStages * kWsMmStage + 1024u + 256u;
+
+template <class F>
+__global__ void __launch_bounds__(kWsMmThreads, 1)
+k_matmul_ws(const uint8_t* __restrict__ a_tiles, uint32_t M, uint32_t MT2, const uint8_t* __restrict__ img, uint32_t KC, uint32_t N,
+            uint32_t NT, typename F::E* __restrict__ C) {
+  typedef typename F::E E;
+  constexpr uint32_t kNTile = MmField<F>::kNTile;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t base = (mm_smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t ctl = base + kWsMmStages * kWsMmStage;
+  const uint32_t bar_full = ctl, bar_empty = ctl + 32u, bar_done = ctl + 64u, bar_drained = ctl + 72u, tmem_slot = ctl + 96u;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+
+  const uint32_t per_band = kMmRaster * NT;
+  const uint32_t band = blockIdx.x / per_band, in_band = blockIdx.x % per_band;
+  const uint32_t band_rows = min(kMmRaster, MT2 - band * kMmRaster);
+  const uint32_t mt2 = band * kMmRaster + in_band % band_rows, jt = in_band / band_rows;
+  if (jt >= NT) return;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint32_t i = 0; i < kWsMmStages; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_full + 8u * i) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_empty + 8u * i) : "memory");
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_done) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(bar_drained) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot) : "memory");
+
+  const uint32_t rounds = (KC + kMmRoundChunks - 1u) / kMmRoundChunks;
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------------------------------------------------------- producer
+      const uint8_t* a0 = a_tiles + (uint64_t)(2u * mt2) * KC * kMmATile;
+      const uint8_t* a1 = a0 + (uint64_t)KC * kMmATile;
+      const uint8_t* bi = img + (uint64_t)jt * KC * kMmBTileBytes;
+      for (uint32_t kc = 0; kc < KC; ++kc) {
+        const uint32_t s = kc % kWsMmStages;
+        if (kc >= kWsMmStages) mm_wait(bar_empty + 8u * s, ((kc / kWsMmStages) - 1u) & 1u);
+        const uint32_t st = base + s * kWsMmStage, fb = bar_full + 8u * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(kWsMmStage) : "memory");
+        mm_bulk(st, a0 + (uint64_t)kc * kMmATile, kMmATile, fb);
+        mm_bulk(st + kMmATile, a1 + (uint64_t)kc * kMmATile, kMmATile, fb);
+        mm_bulk(st + 2u * kMmATile, bi + (uint64_t)kc * kMmBTileBytes, kMmBTileBytes, fb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
+      for (uint32_t kc = 0; kc < KC; ++kc) {
+        const uint32_t s = kc % kWsMmStages, r = kc / kMmRoundChunks, first = r * kMmRoundChunks;
+        if (kc == first && r > 0) mm_wait(bar_drained, (r - 1u) & 1u);  // the epilogue has read the previous round out of TMEM
+        mm_wait(bar_full + 8u * s, (kc / kWsMmStages) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = base + s * kWsMmStage;
+#pragma unroll
+        for (uint32_t rt = 0; rt < 2u; ++rt)
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4u; ++ks)
+            mm_mma(tmem + rt * 256u, mm_desc(st + rt * kMmATile + ks * 32u), mm_desc(st + 2u * kMmATile + ks * 32u), (kc > first) | ks);
+        mm_commit(bar_empty + 8u * s);
+        if (kc + 1u == KC || kc + 1u == first + kMmRoundChunks) mm_commit(bar_done);
+      }
+    }
+  } else {  // ---------------------------------------------------------------------------- epilogue warps 2..9
+    const uint32_t e = warp - 2u, rt = e >> 2, quad = warp & 3u;  // a warp may only read TMEM lanes 32 * (warp % 4) ...
+    E acc[kNTile];
+#pragma unroll
+    for (uint32_t j = 0; j < kNTile; ++j) acc[j] = F::zero();
+    for (uint32_t r = 0; r < rounds; ++r) {
+      mm_wait(bar_done, r & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + rt * 256u + ((quad * 32u) << 16);
+#pragma unroll
+      for (uint32_t g = 0; g < 8; ++g) {
+        uint32_t v[32];
+        mm_tmem_ld32(taddr + g * 32u, v);
+        constexpr uint32_t kPer = 32u / F::BYTES;
+#pragma unroll
+        for (uint32_t jj = 0; jj < kPer; ++jj) acc[g * kPer + jj] = F::add(acc[g * kPer + jj], MmField<F>::combine(v + F::BYTES * jj));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
+    }
+    const uint32_t row = mt2 * 256u + rt * 128u + quad * 32u + lane;
+    if (row < M) {
+      E* dst = C + (uint64_t)row * N + (uint64_t)jt * kNTile;
+#pragma unroll
+      for (uint32_t j = 0; j < kNTile; ++j)
+        if (jt * kNTile + j < N) dst[j] = acc[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
 // ---- generic kernel (any field, any shape): thread = one output element, lazy accumulation
 template <class F>
 __global__ void __launch_bounds__(256)
@@ -391,6 +538,41 @@ static cudaError_t matmul_tc_launch_t(cudaStream_t st, const typename F::E* d_A,
   }
   return cudaGetLastError();
 }
+// scratch layout of the warp-specialised form: [limb image of B][tiles of A, padded to an even number of row tiles]
+template <class F>
+static size_t ws_scratch_bytes_t(uint32_t M, uint32_t K, uint32_t N) {
+  const uint64_t KC = (K + MmField<F>::kKChunk - 1) / MmField<F>::kKChunk, MT2 = (M + 255) / 256;
+  return image_bytes_t<F>(K, N) + (size_t)(2 * MT2 * KC * kMmATile);
+}
+size_t matmul61_ws_scratch_bytes(uint32_t M, uint32_t K, uint32_t N) { return ws_scratch_bytes_t<F61>(M, K, N); }
+size_t matmul127_ws_scratch_bytes(uint32_t M, uint32_t K, uint32_t N) { return ws_scratch_bytes_t<F127>(M, K, N); }
+
+template <class F>
+static cudaError_t matmul_ws_launch_t(cudaStream_t st, const typename F::E* d_A, uint32_t M, uint32_t K, const typename F::E* d_B,
+                                      uint32_t N, uint8_t* d_scratch, typename F::E* d_C) {
+  const uint32_t KC = (K + MmField<F>::kKChunk - 1) / MmField<F>::kKChunk, NT = (N + MmField<F>::kNTile - 1) / MmField<F>::kNTile;
+  const uint32_t MT2 = (M + 255) / 256;
+  uint8_t* d_img = d_scratch;
+  uint8_t* d_at = d_scratch + image_bytes_t<F>(K, N);
+  k_matmul_prep<F><<<KC * NT, 256, 0, st>>>(d_B, K, N, KC, d_img);
+  k_matmul_prep_a<F><<<2 * MT2 * KC, 256, 0, st>>>(d_A, M, K, KC, d_at);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_matmul_ws<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsMmDynSmem);
+  if (e != cudaSuccess) return e;
+  const uint32_t bands = (MT2 + kMmRaster - 1) / kMmRaster;
+  k_matmul_ws<F><<<bands * kMmRaster * NT, kWsMmThreads, kWsMmDynSmem, st>>>(d_at, M, MT2, d_img, KC, N, NT, d_C);
+  return cudaGetLastError();
+}
+cudaError_t matmul61_ws_launch(cudaStream_t st, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B, uint32_t N,
+                               uint8_t* d_scratch, uint64_t* d_C) {
+  return matmul_ws_launch_t<F61>(st, d_A, M, K, d_B, N, d_scratch, d_C);
+}
+cudaError_t matmul127_ws_launch(cudaStream_t st, const E127* d_A, uint32_t M, uint32_t K, const E127* d_B, uint32_t N,
+                                uint8_t* d_scratch, E127* d_C) {
+  return matmul_ws_launch_t<F127>(st, d_A, M, K, d_B, N, d_scratch, d_C);
+}
+
 cudaError_t matmul61_tc_launch(cudaStream_t st, int, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B, uint32_t N,
                                uint8_t* d_img, uint64_t* d_C) {
   return matmul_tc_launch_t<F61>(st, d_A, M, K, d_B, N, d_img, d_C);

@@ -20,6 +20,13 @@ cudaError_t matmul127_tc_launch(cudaStream_t st, int sm_count, const E127* d_A, 
                                 uint8_t* d_img, E127* d_C);
 cudaError_t matmul61_tc_launch(cudaStream_t st, int sm_count, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B,
                                uint32_t N, uint8_t* d_img, uint64_t* d_C);
+// warp-specialised form (default): any inner dimension; scratch = limb image of B + pre-tiled A
+size_t matmul61_ws_scratch_bytes(uint32_t M, uint32_t K, uint32_t N);
+size_t matmul127_ws_scratch_bytes(uint32_t M, uint32_t K, uint32_t N);
+cudaError_t matmul61_ws_launch(cudaStream_t st, const uint64_t* d_A, uint32_t M, uint32_t K, const uint64_t* d_B, uint32_t N,
+                               uint8_t* d_scratch, uint64_t* d_C);
+cudaError_t matmul127_ws_launch(cudaStream_t st, const E127* d_A, uint32_t M, uint32_t K, const E127* d_B, uint32_t N,
+                                uint8_t* d_scratch, E127* d_C);
 cudaError_t matmul61_generic_launch(cudaStream_t st, int sm_count, const uint64_t* A, uint32_t M, uint32_t K, const uint64_t* B,
                                     uint32_t N, uint64_t* C);
 cudaError_t matmul127_generic_launch(cudaStream_t st, int sm_count, const E127* A, uint32_t M, uint32_t K, const E127* B, uint32_t N,

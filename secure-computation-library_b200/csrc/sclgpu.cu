@@ -1674,29 +1674,28 @@ static int matmul_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, u
                      const typename F::E* B, uint32_t cols, typename F::E* C) {
   ctx->launches++;
   cudaError_t e;
-  if constexpr (F::BYTES == 8) {
-    const bool tc = (inner % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (uint64_t)rows * cols * inner >= (1ull << 18) &&
-                    getenv("SCLGPU_MATMUL_GENERIC") == nullptr;
-    if (tc) {
-      void* img = nullptr;
-      CK(cudaMallocAsync(&img, matmul61_image_bytes(inner, cols), st));
-      ctx->launches++;
-      e = matmul61_tc_launch(st, ctx->sm_count, A, rows, inner, B, cols, (uint8_t*)img, C);
-      cudaFreeAsync(img, st);
+  const uint64_t work = (uint64_t)rows * cols * inner;
+  const bool big = work >= (F::BYTES == 8 ? (1ull << 18) : (1ull << 16)) && getenv("SCLGPU_MATMUL_GENERIC") == nullptr;
+  const bool v1 = getenv("SCLGPU_MATMUL_V1") != nullptr;  // the cp.async form (Fp61: even inner dimension, aligned A)
+  if (big && !(v1 && F::BYTES == 8 && ((inner & 1) || (reinterpret_cast<uintptr_t>(A) & 15)))) {
+    void* scratch = nullptr;
+    size_t bytes;
+    if constexpr (F::BYTES == 8) bytes = v1 ? matmul61_image_bytes(inner, cols) : matmul61_ws_scratch_bytes(rows, inner, cols);
+    else bytes = v1 ? matmul127_image_bytes(inner, cols) : matmul127_ws_scratch_bytes(rows, inner, cols);
+    CK(cudaMallocAsync(&scratch, bytes, st));
+    ctx->launches += v1 ? 1 : 2;
+    if constexpr (F::BYTES == 8) {
+      e = v1 ? matmul61_tc_launch(st, ctx->sm_count, A, rows, inner, B, cols, (uint8_t*)scratch, C)
+             : matmul61_ws_launch(st, A, rows, inner, B, cols, (uint8_t*)scratch, C);
     } else {
-      e = matmul61_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
+      e = v1 ? matmul127_tc_launch(st, ctx->sm_count, A, rows, inner, B, cols, (uint8_t*)scratch, C)
+             : matmul127_ws_launch(st, A, rows, inner, B, cols, (uint8_t*)scratch, C);
     }
+    cudaFreeAsync(scratch, st);
+  } else if constexpr (F::BYTES == 8) {
+    e = matmul61_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
   } else {
-    const bool tc = (uint64_t)rows * cols * inner >= (1ull << 16) && getenv("SCLGPU_MATMUL_GENERIC") == nullptr;
-    if (tc) {
-      void* img = nullptr;
-      CK(cudaMallocAsync(&img, matmul127_image_bytes(inner, cols), st));
-      ctx->launches++;
-      e = matmul127_tc_launch(st, ctx->sm_count, A, rows, inner, B, cols, (uint8_t*)img, C);
-      cudaFreeAsync(img, st);
-    } else {
-      e = matmul127_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
-    }
+    e = matmul127_generic_launch(st, ctx->sm_count, A, rows, inner, B, cols, C);
   }
   if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
   return SCLGPU_OK;
