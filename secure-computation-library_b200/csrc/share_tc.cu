@@ -734,7 +734,7 @@ k_share_ws(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0
 // bytes, written by its thread into its TMEM lane), B = bytes of L_r[k] * 2^(8a) (built on the
 // host from the device-computed Lagrange rows), D = (n_checks+1) x BYTES limb columns.  No AES,
 // so shared memory holds only B; the kernel is HBM-bound (reads d+t shares per secret once).
-template <class F, int GROUPS>
+template <class F, int GROUPS, int ACOLS>
 __global__ void __launch_bounds__(128 * GROUPS, 1)
 k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict__ in, uint64_t N,
                uint64_t stride_i, uint64_t stride_j, uint32_t m, uint32_t n_checks,
@@ -744,9 +744,9 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
   constexpr uint32_t EB = F::BYTES;
   constexpr uint32_t kThreads = 128 * GROUPS;
   constexpr uint32_t PCOLS = 64;
-  constexpr uint32_t kACols = 64u;                         // A rows of up to 256 bytes: two K tiles of 128
+  constexpr uint32_t kACols = ACOLS;                       // 32: A rows of 128 bytes; 64: up to 256 bytes = two K tiles
   constexpr uint32_t kColsPerGroup = kACols + PCOLS;
-  constexpr uint32_t kMaxM = 256u / EB;                    // shares in one A row
+  constexpr uint32_t kMaxM = 4u * ACOLS / EB;              // shares in one A row
   constexpr uint32_t kLdRows = 32u / EB;                   // output rows per 32-column TMEM load
   static_assert(GROUPS * kColsPerGroup <= 512, "tensor memory has 512 columns");
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -889,13 +889,21 @@ template <class F>
 static cudaError_t recover_d_tc_launch_t(cudaStream_t st, int sm_count, const void* d_bmat, const typename F::E* d_in,
                                          uint64_t N, uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
                                          typename F::E* d_out, uint8_t* d_err, unsigned long long* d_count) {
-  // per launch: the attribute belongs to the current device's instance of the kernel, and this is a few microseconds
-  cudaError_t e = cudaFuncSetAttribute(k_recover_d_tc<F, kRdGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdDynSmem);
-  if (e != cudaSuccess) return e;
   const uint64_t tiles = (N + 127) / 128;
-  const int grid = (int)std::min<uint64_t>((tiles + kRdGroups - 1) / kRdGroups, (uint64_t)sm_count);
-  k_recover_d_tc<F, kRdGroups><<<grid, 128 * kRdGroups, kRdDynSmem, st>>>(reinterpret_cast<const uint4*>(d_bmat), d_in, N, si, sj, m,
-                                                                         n_checks, d_out, d_err, d_count);
+  const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
+  // per launch: the attribute belongs to the current device's instance of the kernel, and this is a few microseconds
+  if (m * F::BYTES <= 128u) {  // one K tile: 32 columns of A, five groups
+    constexpr int G = 5;
+    cudaError_t e = cudaFuncSetAttribute(k_recover_d_tc<F, G, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdDynSmem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)std::min<uint64_t>((tiles + G - 1) / G, (uint64_t)sm_count);
+    k_recover_d_tc<F, G, 32><<<grid, 128 * G, kRdDynSmem, st>>>(bm, d_in, N, si, sj, m, n_checks, d_out, d_err, d_count);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(k_recover_d_tc<F, kRdGroups, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdDynSmem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)std::min<uint64_t>((tiles + kRdGroups - 1) / kRdGroups, (uint64_t)sm_count);
+    k_recover_d_tc<F, kRdGroups, 64><<<grid, 128 * kRdGroups, kRdDynSmem, st>>>(bm, d_in, N, si, sj, m, n_checks, d_out, d_err, d_count);
+  }
   return cudaGetLastError();
 }
 
