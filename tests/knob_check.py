@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""TEST HELPER (run by tests/test_gpu_parity.py in subprocesses with different SCLGPU_* knobs set): a compact sweep
+of share / recoverP / recoverD / mat-mul against the plain-C oracle, so that every selectable kernel stays verified."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import __graft_entry__ as entry
+
+pkg = entry.load_package()
+o = entry.load_oracle(); port = o.PortOracle()
+ctx = pkg.Context(0)
+for field, t, n, N in [(61, 15, 32, 3000), (61, 2, 5, 777), (127, 7, 16, 1500), (127, 2, 7, 300), (61, 7, 16, 2048)]:
+    sec = port.vector_random(field, "secrets", 0, N)
+    sh = ctx.shamir_share(field, sec, t, n, "knobs", 11)
+    assert np.array_equal(sh, port.shamir_share(field, sec, t, n, "knobs", 11)), ("share", field, t, n)
+    assert np.array_equal(ctx.recover_p(field, sh), sec), ("recover_p", field, n)
+    if n >= 2 * t + 1:
+        bad = sh.copy()
+        bad.reshape(N, n, -1)[::7, t + 1, 0] ^= np.uint64(3)
+        g, w = ctx.recover_d(field, bad, t), port.recover_d(field, bad, t)
+        assert np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) and g[2] == w[2], ("recover_d", field, t)
+for field, rows, inner, cols in [(61, 300, 520, 70), (61, 129, 4100, 33), (61, 257, 130, 257), (127, 130, 520, 40), (127, 64, 2100, 20)]:
+    shp = () if field == 61 else (2,)
+    A = port.vector_random(field, "mat A", 0, rows * inner).reshape((rows, inner) + shp)
+    Bm = port.vector_random(field, "mat B", 7, inner * cols).reshape((inner, cols) + shp)
+    assert np.array_equal(ctx.matmul(field, A, Bm), port.matmul(field, A, Bm)), ("matmul", field, rows, inner, cols)
+ctx.close()
+print("KNOB_CHECK PASSED", {k: v for k, v in os.environ.items() if k.startswith("SCLGPU_")})

@@ -654,6 +654,22 @@ def test_share_kernel_paths_vs_oracle(tc):
     assert r.returncode == 0 and "TC_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC"])
+def test_selectable_kernels_vs_oracle(knob):
+    """tests/knob_check.py with one kernel-selection knob set: the first GEMM form, the
+    integer-pipe GEMM, the integer-pipe reconstruction kernels, the staged share path."""
+    import os
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env[knob] = "1"
+    r = subprocess.run([sys.executable, os.path.join(repo, "tests", "knob_check.py")], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "KNOB_CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 # ------------------------------------------------------------------ full-size properties, configs C3 / C4 / C5
 def test_full_size_c3_fp127_recover_d_tamper_set(ctx, pkg, orc, port):
     """BASELINE config C3 at its full size: Fp127 n=16 t=7, 2^24 secrets, share -> recoverD with the tamper
