@@ -406,17 +406,28 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
     }
   };
 
-  for (uint64_t tile = (uint64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (uint64_t)gridDim.x * GROUPS) {
+  // COEFFS: the (t+1) coalesced plane loads of a tile are requested one tile ahead (right after the previous tile's
+  // rows went to tensor memory), so they are in flight under that tile's MMAs and epilogue
+  constexpr uint32_t kMaxC = COEFFS ? 128u / EB : 1u;
+  E c[kMaxC];
+  auto load_coeffs = [&](uint64_t tile_) {
+    const uint64_t j_ = tile_ * 128u + gt;
+    const E* p = secrets + (j_ < N ? j_ : N - 1);
+#pragma unroll
+    for (uint32_t k = 0; k < kMaxC; ++k, p += N) c[k] = (k <= t) ? *p : F::zero();
+  };
+  const uint64_t tile_first = (uint64_t)blockIdx.x * GROUPS + g, tile_step = (uint64_t)gridDim.x * GROUPS;
+  if constexpr (COEFFS) {
+    if (tile_first < tiles) load_coeffs(tile_first);
+  }
+
+  for (uint64_t tile = tile_first; tile < tiles; tile += tile_step) {
     const uint64_t j = tile * 128u + gt;
     const bool valid = j < N;
     const uint64_t jj = valid ? j : N - 1;                 // tail lanes recompute the last secret (never stored)
     const uint32_t a_lane = a_tm + lane_off;
     if constexpr (COEFFS) {
-      // (t+1) coalesced plane loads, all requested before the first is consumed, then 16 bytes per tcgen05.st
-      constexpr uint32_t kMaxC = 128u / EB;
-      E c[kMaxC];
-#pragma unroll
-      for (uint32_t k = 0; k < kMaxC; ++k) c[k] = (k <= t) ? secrets[(uint64_t)k * N + jj] : F::zero();
+      // 16 bytes per tcgen05.st
       if constexpr (EB == 8) {
 #pragma unroll
         for (uint32_t q = 0; q < kMaxC / 2; ++q)
@@ -484,6 +495,9 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       issue_pass(0);
       if (NBUF == 2 && npass > 1) issue_pass(1);
+    }
+    if constexpr (COEFFS) {
+      if (tile + tile_step < tiles) load_coeffs(tile + tile_step);
     }
     for (uint32_t p = 0; p < npass; ++p) {
       if (NBUF == 2 && (p & 1u)) {
@@ -982,13 +996,13 @@ template <class F>
 static cudaError_t share_coeffs_tc_launch_t(cudaStream_t st, int sm_count, const void* d_bmat, const typename F::E* d_coeffs,
                                             uint64_t N, uint32_t t, uint32_t n, typename F::E* d_out, uint64_t stride_i,
                                             uint64_t stride_j) {
-  auto kern = k_share_tcm<F, 5, 1, 64, true>;
+  auto kern = k_share_tcm<F, 4, 1, 64, true>;  // four groups: the prefetched coefficients stay in registers
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcCoeffDynSmem);
   if (e != cudaSuccess) return e;
   const uint64_t tiles = (N + 127) / 128;
-  const int grid = (int)std::min<uint64_t>((tiles + 4) / 5, (uint64_t)sm_count);
+  const int grid = (int)std::min<uint64_t>((tiles + 3) / 4, (uint64_t)sm_count);
   AesKey unused{};
-  kern<<<grid, 640, kTcCoeffDynSmem, st>>>(unused, nullptr, reinterpret_cast<const uint4*>(d_bmat), 0, d_coeffs, N, t, n, d_out,
+  kern<<<grid, 512, kTcCoeffDynSmem, st>>>(unused, nullptr, reinterpret_cast<const uint4*>(d_bmat), 0, d_coeffs, N, t, n, d_out,
                                           stride_i, stride_j);
   return cudaGetLastError();
 }
