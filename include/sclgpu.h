@@ -166,6 +166,48 @@ int sclgpu_fp127_recover_c_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N
                                const void* alphas, void* d_f, void* d_err, uint8_t* d_status,
                                uint64_t* n_failed);
 
+/* ---- array-valued secrets: ss::shamirSecretShare / shamirRecoverP on math::Array<FF, W> ----
+ * The templates of shamir.h:52-68 / :100-104 instantiated with T = math::Array<FF, W>
+ * (include/scl/math/array.h:69-), as ss::pedersenSecretShare does with W = 2 for
+ * {secret, randomness} (include/scl/ss/pedersen.h:137-138).  Sharing j draws ONE
+ * Vector<Array>::random(t+1) = (t+1)*W*byteSize keystream bytes (vector.h:508-519; Array::read
+ * takes W consecutive elements, array.h:82-88): component w of coefficient k is stream element
+ * k*W + w, the first W elements are consumed and replaced by the secret, and the call uses
+ * sclgpu_share_array_blocks(byteSize, W, t) = ceil((t+1)*W*byteSize/16) blocks; Array arithmetic
+ * is component-wise, x runs over Array(1), Array(2), ...  secrets: [N][W].
+ * SCLGPU_SECRET_MAJOR shares: [N][n][W] (the N Vectors SCL returns, concatenated);
+ * SCLGPU_PARTY_MAJOR: [n][N][W] (party i's N Arrays contiguous).  Host versions are secret-major.
+ * recover_p_array: alphas 1..n, x = 0 (the one-argument overload), out [N][W].
+ * 1 <= W <= 4096; W = 1 equals shamir_share / recover_p. */
+uint64_t sclgpu_share_array_blocks(uint32_t element_bytes, uint32_t W, uint32_t t);
+int sclgpu_fp61_shamir_share_array(sclgpu_ctx* ctx, const uint64_t* secrets, uint64_t N, uint32_t W,
+                                   uint32_t t, uint32_t n, const uint8_t seed[16],
+                                   uint64_t first_block, uint64_t* shares);
+int sclgpu_fp127_shamir_share_array(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t W,
+                                    uint32_t t, uint32_t n, const uint8_t seed[16],
+                                    uint64_t first_block, void* shares);
+int sclgpu_fp61_shamir_share_array_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N,
+                                       uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16],
+                                       uint64_t first_block, uint64_t* d_shares, int layout);
+int sclgpu_fp127_shamir_share_array_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N,
+                                        uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16],
+                                        uint64_t first_block, void* d_shares, int layout);
+int sclgpu_fp61_recover_p_array(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t W,
+                                uint32_t n, uint64_t* out);
+int sclgpu_fp127_recover_p_array(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t W,
+                                 uint32_t n, void* out);
+int sclgpu_fp61_recover_p_array_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N, uint32_t W,
+                                    uint32_t n, int layout, uint64_t* d_out);
+int sclgpu_fp127_recover_p_array_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t W,
+                                     uint32_t n, int layout, void* d_out);
+
+/* ---- math::Matrix<FF>::hyperInvertible(n, m) (matrix.h:462-475) ----------------
+ * Row i = computeLagrangeBasis(range(1, m+1), -i), -i being the field element p - i
+ * (lagrange.h:80-82 -> FF(int)).  out: host, row-major n x m.  SCLGPU_EINVAL
+ * ("n or m cannot be 0", matrix.h:165) for an empty shape. */
+int sclgpu_fp61_hyper_invertible(sclgpu_ctx* ctx, uint32_t n, uint32_t m, uint64_t* out);
+int sclgpu_fp127_hyper_invertible(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out);
+
 /* ---- per-party packets: Serializer<math::Vector<FF>> wire layout ------------------
  * What a dealer sends to party i after sharing N secrets is a net::Packet holding the
  * math::Vector of party i's N shares, i.e. Serializer<Vector<FF>>::write

@@ -27,6 +27,10 @@
 //   Vector add / subtract / multiplyEntryWise / scalarMultiply / dot / sum   vector.h:192-301
 //   Matrix::multiply(Vector)                             matrix.h:498-513
 //   Matrix::multiply(Matrix)                             matrix.h:476-495
+//   Matrix::hyperInvertible(n, m)                        matrix.h:462-475   -> sclgpu::hyperInvertible<FF>(ctx, n, m)
+//   scl::ss::shamirSecretShare(math::Array<FF, W>, t, n, prg)   (pedersen.h:137-138: W = 2, {secret, randomness})
+//     -> sclgpu::shamirSecretShare(ctx, std::vector<math::Array<FF, W>>, t, n, prg) : N Vectors of n Arrays
+//        sclgpu::shamirRecoverP(ctx, std::vector<math::Vector<math::Array<FF, W>>>)  : N Arrays
 //   Beaver combination e*b + d*a + c + e*d               test/scl/protocol/beaver.h:57-61
 //
 // There is no CPU fallback: Context's constructor throws when no B200 is usable.
@@ -39,6 +43,7 @@
 #include <string>
 #include <vector>
 
+#include "scl/math/array.h"
 #include "scl/math/fp.h"
 #include "scl/math/matrix.h"
 #include "scl/math/vector.h"
@@ -89,6 +94,9 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto sum = &sclgpu_##SUF##_sum;                                                          \
     static constexpr auto matvec = &sclgpu_##SUF##_matvec;                                                    \
     static constexpr auto matmul = &sclgpu_##SUF##_matmul;                                                    \
+    static constexpr auto share_array = &sclgpu_##SUF##_shamir_share_array;                                   \
+    static constexpr auto recover_p_array = &sclgpu_##SUF##_recover_p_array;                                  \
+    static constexpr auto hyper_invertible = &sclgpu_##SUF##_hyper_invertible;                                \
   }
 SCLGPU_SCL_ABI(scl::math::ff::Mersenne61, fp61, 8);
 SCLGPU_SCL_ABI(scl::math::ff::Mersenne127, fp127, 16);
@@ -419,6 +427,71 @@ scl::math::Matrix<FF> multiply(Context& ctx, const scl::math::Matrix<FF>& A, con
                                     detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(B)(0, 0)),
                                     (std::uint32_t)B.cols(), detail::raw<FF>(&C(0, 0))));
   return C;
+}
+
+// ---- Matrix::hyperInvertible(n, m), matrix.h:462-475
+template <class FF>
+scl::math::Matrix<FF> hyperInvertible(Context& ctx, std::size_t n, std::size_t m) {
+  if (n == 0 || m == 0) throw std::invalid_argument("n or m cannot be 0");  // matrix.h:165
+  scl::math::Matrix<FF> him(n, m);
+  ctx.check(detail::Abi<FF>::hyper_invertible(ctx.get(), (std::uint32_t)n, (std::uint32_t)m, detail::raw<FF>(&him(0, 0))));
+  return him;
+}
+
+// ---- shamirSecretShare on array-valued secrets (shamir.h:52-68 with T = math::Array<FF, W>; the sharing
+// step of ss::pedersenSecretShare, pedersen.h:137-138).  Element j of the result is what
+// scl::ss::shamirSecretShare(secrets[j], t, n, prg) returns, for the calls made in order on `prg`.
+// Arrays cross the ABI as their Array::write bytes (array.h:407-411): W x FF::write.
+template <class FF, std::size_t W>
+std::vector<scl::math::Vector<scl::math::Array<FF, W>>> shamirSecretShare(
+    Context& ctx, const std::vector<scl::math::Array<FF, W>>& secrets, std::size_t t, std::size_t n,
+    scl::util::PRG& prg) {
+  using A = detail::Abi<FF>;
+  using Arr = scl::math::Array<FF, W>;
+  const std::size_t N = secrets.size();
+  const std::uint64_t blocks = sclgpu_share_array_blocks((std::uint32_t)A::BYTES, (std::uint32_t)W, (std::uint32_t)t);
+  std::vector<FF> in(N * W), flat(N * n * W);
+  for (std::size_t j = 0; j < N; ++j) secrets[j].write(reinterpret_cast<unsigned char*>(in.data() + j * W));
+  long& ctr = detail::prgCounter(prg);
+  const auto seed = prg.Seed();
+  if (N != 0 && n != 0) {
+    ctx.check(A::share_array(ctx.get(), detail::raw<FF>(static_cast<const FF*>(in.data())), N, (std::uint32_t)W,
+                             (std::uint32_t)t, (std::uint32_t)n, seed.data(), (std::uint64_t)ctr,
+                             detail::raw<FF>(flat.data())));
+  }
+  ctr += (long)(N * blocks);
+  std::vector<scl::math::Vector<Arr>> out;
+  out.reserve(N);
+  for (std::size_t j = 0; j < N; ++j) {
+    std::vector<Arr> row;
+    row.reserve(n);
+    for (std::size_t i = 0; i < n; ++i)
+      row.emplace_back(Arr::read(reinterpret_cast<const unsigned char*>(flat.data() + (j * n + i) * W)));
+    out.emplace_back(scl::math::Vector<Arr>(std::move(row)));
+  }
+  return out;
+}
+
+// ---- shamirRecoverP(shares) on Vectors of Arrays, shamir.h:100-104 (all sharings of the same size n)
+template <class FF, std::size_t W>
+std::vector<scl::math::Array<FF, W>> shamirRecoverP(Context& ctx,
+                                                    const std::vector<scl::math::Vector<scl::math::Array<FF, W>>>& shares) {
+  using A = detail::Abi<FF>;
+  using Arr = scl::math::Array<FF, W>;
+  const std::size_t N = shares.size();
+  std::vector<Arr> out;
+  if (N == 0) return out;
+  const std::size_t n = shares[0].size();
+  std::vector<FF> flat(N * n * W), rec(N * W);
+  for (std::size_t j = 0; j < N; ++j) {
+    if (shares[j].size() != n) throw std::invalid_argument("Vec sizes mismatch");  // vector.h:483
+    for (std::size_t i = 0; i < n; ++i) shares[j][i].write(reinterpret_cast<unsigned char*>(flat.data() + (j * n + i) * W));
+  }
+  ctx.check(A::recover_p_array(ctx.get(), detail::raw<FF>(static_cast<const FF*>(flat.data())), N, (std::uint32_t)W,
+                               (std::uint32_t)n, detail::raw<FF>(rec.data())));
+  out.reserve(N);
+  for (std::size_t j = 0; j < N; ++j) out.emplace_back(Arr::read(reinterpret_cast<const unsigned char*>(rec.data() + j * W)));
+  return out;
 }
 
 }  // namespace sclgpu

@@ -143,6 +143,12 @@ class PortOracle(_Base):
                 g(n).restype = None
             g("shamir_share").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
             g("shamir_share").restype = None
+            g("shamir_share_array").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
+            g("shamir_share_array").restype = None
+            g("recover_p_array").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
+            g("recover_p_array").restype = C.c_int
+            g("hyper_invertible").argtypes = [C.c_uint64, C.c_uint64, _vp]
+            g("hyper_invertible").restype = C.c_int
             g("recover_c").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]
             g("recover_c").restype = C.c_int64
             g("additive_share").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
@@ -206,6 +212,28 @@ class PortOracle(_Base):
         N = _nelem(secrets, field)
         out = empty(field, N, n)
         self._f(field, "shamir_share")(_p(secrets), N, t, n, seed16(seed), first_block, _p(out))
+        return out
+
+    def shamir_share_array(self, field, secrets, t, n, seed, first_block=0):
+        """secrets [N, W] -> shares [N, n, W] (shamirSecretShare on math::Array<FF, W>)."""
+        secrets = _c(secrets)
+        N, W = secrets.shape[0], secrets.shape[1]
+        out = empty(field, N, n, W)
+        self._f(field, "shamir_share_array")(_p(secrets), N, W, t, n, seed16(seed), first_block, _p(out))
+        return out
+
+    def recover_p_array(self, field, shares):
+        shares = _c(shares)
+        N, n, W = shares.shape[0], shares.shape[1], shares.shape[2]
+        out = empty(field, N, W)
+        if self._f(field, "recover_p_array")(_p(shares), N, W, n, _p(out)):
+            raise ValueError("0 not invertible modulo prime")
+        return out
+
+    def hyper_invertible(self, field, n, m):
+        out = empty(field, n, m)
+        if self._f(field, "hyper_invertible")(n, m, _p(out)):
+            raise ValueError("0 not invertible modulo prime")
         return out
 
     def additive_share(self, field, secrets, n, seed, first_block=0):
@@ -328,6 +356,12 @@ class RefOracle(_Base):
                 g(n).restype = None
             g("shamir_share").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
             g("shamir_share").restype = None
+            g("shamir_share_array").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
+            g("shamir_share_array").restype = C.c_int
+            g("recover_p_array").argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
+            g("recover_p_array").restype = C.c_int
+            g("hyper_invertible").argtypes = [C.c_uint64, C.c_uint64, _vp]
+            g("hyper_invertible").restype = None
             g("recover_c").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]
             g("recover_c").restype = C.c_int64
             g("additive_share").argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]
@@ -405,6 +439,29 @@ class RefOracle(_Base):
         N = _nelem(secrets, field)
         out = empty(field, N, n)
         self._f(field, "shamir_share")(_p(secrets), N, t, n, s, sl, first_block, _p(out))
+        return out
+
+    def shamir_share_array(self, field, secrets, t, n, seed, first_block=0):
+        """secrets [N, W] -> shares [N, n, W]; W in 1..5 (the widths instantiated in ref_driver.cc)."""
+        s, sl = self._seed(seed)
+        secrets = _c(secrets)
+        N, W = secrets.shape[0], secrets.shape[1]
+        out = empty(field, N, n, W)
+        if self._f(field, "shamir_share_array")(_p(secrets), N, W, t, n, s, sl, first_block, _p(out)):
+            raise ValueError("array width not instantiated in the reference driver")
+        return out
+
+    def recover_p_array(self, field, shares):
+        shares = _c(shares)
+        N, n, W = shares.shape[0], shares.shape[1], shares.shape[2]
+        out = empty(field, N, W)
+        if self._f(field, "recover_p_array")(_p(shares), N, W, n, _p(out)):
+            raise ValueError("array width not instantiated in the reference driver")
+        return out
+
+    def hyper_invertible(self, field, n, m):
+        out = empty(field, n, m)
+        self._f(field, "hyper_invertible")(n, m, _p(out))
         return out
 
     def additive_share(self, field, secrets, n, seed, first_block=0):

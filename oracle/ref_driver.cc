@@ -18,6 +18,9 @@
 //     math::computeLagrangeBasis         (include/scl/math/lagrange.h:55-71)
 //     math::Matrix<T>::multiply(Vector)  (include/scl/math/matrix.h:498-513)
 //     math::Matrix<T>::multiply(Matrix)  (include/scl/math/matrix.h:476-495)
+//     math::Matrix<T>::hyperInvertible   (include/scl/math/matrix.h:462-475)
+//     ss::shamirSecretShare on math::Array<T, W> (the sharing step of
+//         ss::pedersenSecretShare, include/scl/ss/pedersen.h:137-138)
 //     Vector add/subtract/multiplyEntryWise/scalarMultiply/dot/sum
 // All element buffers are the reference's FF::write bytes (little-endian
 // canonical residues, 8 B for Fp<61>, 16 B for Fp<127>).
@@ -30,6 +33,7 @@
 #include <thread>
 #include <vector>
 
+#include "scl/math/array.h"
 #include "scl/math/fp.h"
 #include "scl/math/lagrange.h"
 #include "scl/math/matrix.h"
@@ -115,6 +119,74 @@ void shamirShare(const unsigned char* secrets, uint64_t N, uint64_t t,
     const auto sh = scl::ss::shamirSecretShare(secret, t, n, prg);
     writeVec(sh, shares + j * n * bs);
   }
+}
+
+// ss::shamirSecretShare(math::Array<T, W>, t, n, prg) per array-valued secret
+// on one PRG: the sharing step of pedersenSecretShare (pedersen.h:137-138 uses
+// W = 2: {secret, randomness}).  secrets: N x W elements, shares: N x n x W.
+template <typename T, std::size_t W>
+void shamirShareArrayW(const unsigned char* secrets, uint64_t N, uint64_t t,
+                       uint64_t n, PRG& prg, unsigned char* shares) {
+  using A = scl::math::Array<T, W>;
+  const std::size_t bs = A::byteSize();
+  for (uint64_t j = 0; j < N; ++j) {
+    const A secret = A::read(secrets + j * bs);
+    const auto sh = scl::ss::shamirSecretShare(secret, t, n, prg);
+    for (uint64_t i = 0; i < n; ++i) sh[i].write(shares + (j * n + i) * bs);
+  }
+}
+
+template <typename T>
+int shamirShareArray(const unsigned char* secrets, uint64_t N, uint64_t W,
+                     uint64_t t, uint64_t n, const unsigned char* seed,
+                     uint64_t seed_len, uint64_t skip, unsigned char* shares) {
+  PRG prg = makePrg(seed, seed_len, skip);
+  switch (W) {
+    case 1: shamirShareArrayW<T, 1>(secrets, N, t, n, prg, shares); return 0;
+    case 2: shamirShareArrayW<T, 2>(secrets, N, t, n, prg, shares); return 0;
+    case 3: shamirShareArrayW<T, 3>(secrets, N, t, n, prg, shares); return 0;
+    case 4: shamirShareArrayW<T, 4>(secrets, N, t, n, prg, shares); return 0;
+    case 5: shamirShareArrayW<T, 5>(secrets, N, t, n, prg, shares); return 0;
+    default: return -1;  // widths instantiated in this driver: 1..5
+  }
+}
+
+// ss::shamirRecoverP on a Vector<Array<T, W>> (shamir.h:100-104 -> :82-87, the
+// Lagrange basis being Array-valued with equal components).
+template <typename T, std::size_t W>
+void recoverPArrayW(const unsigned char* shares, uint64_t N, uint64_t n,
+                    unsigned char* out) {
+  using A = scl::math::Array<T, W>;
+  const std::size_t bs = A::byteSize();
+  for (uint64_t j = 0; j < N; ++j) {
+    std::vector<A> v;
+    v.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) v.emplace_back(A::read(shares + (j * n + i) * bs));
+    const A s = scl::ss::shamirRecoverP(scl::math::Vector<A>(v));
+    s.write(out + j * bs);
+  }
+}
+
+template <typename T>
+int recoverPArray(const unsigned char* shares, uint64_t N, uint64_t W,
+                  uint64_t n, unsigned char* out) {
+  switch (W) {
+    case 1: recoverPArrayW<T, 1>(shares, N, n, out); return 0;
+    case 2: recoverPArrayW<T, 2>(shares, N, n, out); return 0;
+    case 3: recoverPArrayW<T, 3>(shares, N, n, out); return 0;
+    case 4: recoverPArrayW<T, 4>(shares, N, n, out); return 0;
+    case 5: recoverPArrayW<T, 5>(shares, N, n, out); return 0;
+    default: return -1;
+  }
+}
+
+// math::Matrix<T>::hyperInvertible(n, m) (matrix.h:462-475), row-major.
+template <typename T>
+void hyperInvertible(uint64_t n, uint64_t m, unsigned char* out) {
+  const auto him = scl::math::Matrix<T>::hyperInvertible(n, m);
+  const std::size_t bs = T::byteSize();
+  for (uint64_t i = 0; i < n; ++i)
+    for (uint64_t j = 0; j < m; ++j) him(i, j).write(out + (i * m + j) * bs);
 }
 
 // ss::additiveShare(secret, n, prg) per secret on one PRG; reconstruction is
@@ -403,6 +475,22 @@ double benchShareRecover(uint64_t N, uint64_t t, uint64_t n, int detect,
       const unsigned char* seed, uint64_t seed_len, uint64_t skip,             \
       unsigned char* shares) {                                                 \
     shamirShare<T>(secrets, N, t, n, seed, seed_len, skip, shares);            \
+  }                                                                            \
+  int sclref_##SUF##_shamir_share_array(                                       \
+      const unsigned char* secrets, uint64_t N, uint64_t W, uint64_t t,        \
+      uint64_t n, const unsigned char* seed, uint64_t seed_len, uint64_t skip, \
+      unsigned char* shares) {                                                 \
+    return shamirShareArray<T>(secrets, N, W, t, n, seed, seed_len, skip,      \
+                               shares);                                        \
+  }                                                                            \
+  int sclref_##SUF##_recover_p_array(const unsigned char* shares, uint64_t N,  \
+                                     uint64_t W, uint64_t n,                   \
+                                     unsigned char* out) {                     \
+    return recoverPArray<T>(shares, N, W, n, out);                             \
+  }                                                                            \
+  void sclref_##SUF##_hyper_invertible(uint64_t n, uint64_t m,                 \
+                                       unsigned char* out) {                   \
+    hyperInvertible<T>(n, m, out);                                             \
   }                                                                            \
   int64_t sclref_##SUF##_recover_c(const unsigned char* shares, uint64_t N,    \
                                    uint64_t n, const unsigned char* alphas,    \

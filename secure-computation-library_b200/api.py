@@ -77,6 +77,11 @@ def blocks_per_share_call(field: int, t: int) -> int:
     return ((t + 1) * bs + 15) // 16
 
 
+def blocks_per_array_share_call(field: int, width: int, t: int) -> int:
+    """Blocks one shamirSecretShare(math::Array<FF, width>, t, ...) consumes."""
+    return ((t + 1) * width * (8 if field == 61 else 16) + 15) // 16
+
+
 def _c(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint64)
 
@@ -269,6 +274,39 @@ class Context:
         A = None if alphas is None else _c(alphas)
         X = from_ints([x or 0], field)
         self._check(self._f(field, "recover_p_packets")(self._ctx, ptrs, N, n, _p(A), _p(X), _p(out)))
+        return out
+
+    # ------------------------------------------------------------ array-valued secrets
+    def shamir_share_array(self, field: int, secrets, t: int, n: int, seed, first_block: int = 0) -> np.ndarray:
+        """shamirSecretShare on math::Array<FF, W> (shamir.h:52-68; pedersen.h:137-138 for W = 2):
+        secrets [N, W] -> shares [N, n, W]; consumes N*ceil((t+1)*W*bs/16) blocks."""
+        secrets = _c(secrets)
+        if secrets.ndim != (2 if field == 61 else 3):
+            raise InvalidArgument("secrets must be [N, W]")
+        N, W = secrets.shape[0], secrets.shape[1]
+        out = empty(field, N, n, W)
+        self._check(self._f(field, "shamir_share_array")(self._ctx, _p(secrets), N, W, t, n, seed16(seed), first_block, _p(out)))
+        return out
+
+    def shamir_share_array_dev(self, field: int, secrets, N: int, W: int, t: int, n: int, seed, first_block: int,
+                               shares, layout: int = B.PARTY_MAJOR):
+        self._check(self._f(field, "shamir_share_array_dev")(self._ctx, _dp(secrets), N, W, t, n, seed16(seed), first_block, _dp(shares), layout))
+
+    def recover_p_array(self, field: int, shares) -> np.ndarray:
+        """shamirRecoverP on Vector<Array<FF, W>> (shamir.h:100-104): shares [N, n, W] -> [N, W]."""
+        shares = _c(shares)
+        N, n, W = shares.shape[0], shares.shape[1], shares.shape[2]
+        out = empty(field, N, W)
+        self._check(self._f(field, "recover_p_array")(self._ctx, _p(shares), N, W, n, _p(out)))
+        return out
+
+    def recover_p_array_dev(self, field: int, shares, N: int, W: int, n: int, out, layout: int = B.PARTY_MAJOR):
+        self._check(self._f(field, "recover_p_array_dev")(self._ctx, _dp(shares), N, W, n, layout, _dp(out)))
+
+    def hyper_invertible(self, field: int, n: int, m: int) -> np.ndarray:
+        """Matrix::hyperInvertible(n, m) (matrix.h:462-475), row-major [n, m]."""
+        out = empty(field, max(n, 0), max(m, 0))
+        self._check(self._f(field, "hyper_invertible")(self._ctx, n, m, _p(out)))
         return out
 
     # ------------------------------------------------------------ additive sharing

@@ -97,6 +97,11 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_additive_recover", _int, _vp, _vp, _u64, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_additive_recover_dev", _int, _vp, _vp, _u64, _u32, _int, _vp)
         _sig(lib, f"sclgpu_{f}_lagrange_basis", _int, _vp, _vp, _u32, _vp, _vp)
+        _sig(lib, f"sclgpu_{f}_shamir_share_array", _int, _vp, _vp, _u64, _u32, _u32, _u32, _vp, _u64, _vp)
+        _sig(lib, f"sclgpu_{f}_shamir_share_array_dev", _int, _vp, _vp, _u64, _u32, _u32, _u32, _vp, _u64, _vp, _int)
+        _sig(lib, f"sclgpu_{f}_recover_p_array", _int, _vp, _vp, _u64, _u32, _u32, _vp)
+        _sig(lib, f"sclgpu_{f}_recover_p_array_dev", _int, _vp, _vp, _u64, _u32, _u32, _int, _vp)
+        _sig(lib, f"sclgpu_{f}_hyper_invertible", _int, _vp, _u32, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_recover_p", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp)
         _sig(lib, f"sclgpu_{f}_recover_p_dev", _int, _vp, _vp, _u64, _u32, _int, _vp, _vp, _vp)
         _sig(lib, f"sclgpu_{f}_recover_d", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u32, _u32, _vp, _vp,
@@ -106,6 +111,7 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_vandermonde", _int, _vp, _u32, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_transpose_dev", _int, _vp, _vp, _u64, _u64, _vp)
     _sig(lib, "sclgpu_packet_bytes", _u64, _u32, _u64)
+    _sig(lib, "sclgpu_share_array_blocks", _u64, _u32, _u32, _u32)
     _sig(lib, "sclgpu_pipe_microbench", _int, _vp, _int, _u32, C.POINTER(C.c_double))
     _LIB = lib
     return lib

@@ -569,27 +569,38 @@ k_additive_recover(const typename F::E* __restrict__ in, uint64_t N, uint32_t n,
 }
 
 // PRG -> coefficient planes, for thresholds without a register-resident
-// instantiation: coeffs[k*N + j], k = 0..t (k = 0 is the secret).
+// instantiation and for array-valued secrets (shamirSecretShare on
+// math::Array<FF, W>, the sharing step of pedersen.h:137-138).  Sharing j draws
+// one Vector<Array>::random(t+1): stream element s = k*W + w is component w of
+// coefficient k (array.h:82-88 inside vector.h:508-519), B = ceil((t+1)*W*bs/16)
+// blocks per sharing; elements s < W are consumed and replaced by the secret.
+// Output: coeffs[k*(N*W) + j*W + w], i.e. N*W independent polynomials.  W = 1
+// is the plain shamirSecretShare.
 template <class F>
 __global__ void __launch_bounds__(kAesThreads, 1)
 k_expand_coeffs(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
                 uint64_t first_block, const typename F::E* __restrict__ secrets, uint64_t N,
-                uint32_t t, typename F::E* __restrict__ coeffs) {
+                uint32_t t, uint32_t W, typename F::E* __restrict__ coeffs) {
   const uint32_t lanebase = aes_prologue(g_t0);
-  const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
+  const uint64_t S = (uint64_t)(t + 1) * W;  // stream elements per sharing
+  const uint64_t B = (S * F::BYTES + 15) / 16;
+  const uint64_t NW = N * W;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  auto put = [&](uint64_t j, uint64_t s, typename F::E v) {
+    if (s >= W && s < S) coeffs[(s / W) * NW + j * W + (s % W)] = v;
+  };
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
-    coeffs[j] = secrets[j];
+    for (uint32_t w = 0; w < W; ++w) coeffs[j * W + w] = secrets[j * W + w];
     const uint64_t ctr0 = first_block + j * B;
-    for (uint64_t b = (F::BYTES == 16 ? 1 : 0); b < B; ++b) {
+    for (uint64_t b = (F::BYTES == 16 ? W : W / 2); b < B; ++b) {
       uint32_t o0, o1, o2, o3;
       prg_block(key, lanebase, ctr0 + b, o0, o1, o2, o3);
       const uint64_t w0 = (uint64_t)o0 | ((uint64_t)o1 << 32), w1 = (uint64_t)o2 | ((uint64_t)o3 << 32);
       if constexpr (F::BYTES == 16) {
-        coeffs[b * N + j] = F127::from_raw(E127{w0, w1});
+        put(j, b, F127::from_raw(E127{w0, w1}));
       } else {
-        if (2 * b >= 1 && 2 * b <= t) coeffs[(2 * b) * N + j] = F61::from_raw(w0);
-        if (2 * b + 1 <= t) coeffs[(2 * b + 1) * N + j] = F61::from_raw(w1);
+        put(j, 2 * b, F61::from_raw(w0));
+        put(j, 2 * b + 1, F61::from_raw(w1));
       }
     }
   }
@@ -1109,6 +1120,44 @@ k_transpose(const E* __restrict__ in, uint64_t rows, uint64_t cols, E* __restric
     for (uint32_t k = ty; k < 32; k += 8) {
       const uint64_t c = tc * 32 + k, r = tr * 32 + tx;
       if (r < rows && c < cols) out[c * rows + r] = tile[tx][k];
+    }
+    __syncthreads();
+  }
+}
+
+// [rows][cols][W] -> [cols][rows][W]: the same transposition on W-wide elements
+// (Vector<Array<FF, W>> shares, secret-major <-> party-major).  32 x 32 tiles of
+// up to CW components at a time, contiguous runs of 32*cw elements on both sides.
+template <class E, int CW>
+__global__ void __launch_bounds__(256)
+k_transpose_wide(const E* __restrict__ in, uint64_t rows, uint64_t cols, uint32_t W, E* __restrict__ out) {
+  __shared__ E tile[32][32 * CW + 1];
+  const uint64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  const uint32_t n_chunks = (W + CW - 1) / CW;
+  const uint64_t n_tiles = tiles_c * tiles_r * n_chunks;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint64_t tid = blockIdx.x; tid < n_tiles; tid += gridDim.x) {
+    const uint32_t w0 = (uint32_t)(tid % n_chunks) * CW;
+    const uint32_t cw = (W - w0 < (uint32_t)CW) ? W - w0 : (uint32_t)CW;
+    const uint64_t tc = (tid / n_chunks) % tiles_c, tr = tid / (n_chunks * tiles_c);
+    for (uint32_t k = wid; k < 32; k += 8) {
+      const uint64_t r = tr * 32 + k;
+      if (r >= rows) break;
+      for (uint32_t e = lane; e < 32 * cw; e += 32) {
+        const uint32_t q = e / cw, w = e % cw;
+        const uint64_t c = tc * 32 + q;
+        if (c < cols) tile[k][q * CW + w] = in[(r * cols + c) * W + w0 + w];
+      }
+    }
+    __syncthreads();
+    for (uint32_t k = wid; k < 32; k += 8) {
+      const uint64_t c = tc * 32 + k;
+      if (c >= cols) break;
+      for (uint32_t e = lane; e < 32 * cw; e += 32) {
+        const uint32_t q = e / cw, w = e % cw;
+        const uint64_t r = tr * 32 + q;
+        if (r < rows) out[(c * rows + r) * W + w0 + w] = tile[q][k * CW + w];
+      }
     }
     __syncthreads();
   }

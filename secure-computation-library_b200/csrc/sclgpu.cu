@@ -572,7 +572,7 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
     const uint64_t nc = std::min(chunk, N - c0);
     k_expand_coeffs<F><<<grid_for(ctx, nc, kAesThreads, 1), kAesThreads, kAesDynSmem, st>>>(
-        key, ctx->d_t0, first_block + c0 * B, d_secrets + c0, nc, t, planes.as<E>());
+        key, ctx->d_t0, first_block + c0 * B, d_secrets + c0, nc, t, 1u, planes.as<E>());
     CKL();
     RET(share_coeffs_on<F>(ctx, st, planes.as<E>(), nc, t, n, d_out + c0 * sj, si, sj));
   }
@@ -1002,6 +1002,155 @@ static int share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, u
 extern "C" int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, uint32_t n, uint64_t* o, int layout) { return share_coeffs_dev<F61>(c, k, N, t, n, o, layout); }
 extern "C" int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, uint32_t n, void* o, int layout) { return share_coeffs_dev<F127>(c, k, N, t, n, o, layout); }
 
+// ------------------------------------------------------------------ array-valued secrets
+// shamirSecretShare on math::Array<FF, W> (shamir.h:52-68 with T = Array; pedersenSecretShare's sharing
+// step, pedersen.h:137-138, is W = 2).  The N*W component polynomials are independent, so after the
+// keystream is laid out as coefficient planes over the N*W "virtual secrets" (k_expand_coeffs) the
+// evaluation is the plain coefficient-plane share on N*W columns, and party-major output
+// [n][N][W] is contiguous.  Secret-major [N][n][W] (SCL's N Vectors of Arrays) is one wide transposition.
+template <class E>
+static int transpose_wide_on(sclgpu_ctx* ctx, cudaStream_t st, const E* d_in, uint64_t rows, uint64_t cols,
+                             uint32_t W, E* d_out) {
+  if (rows == 0 || cols == 0 || W == 0) return SCLGPU_OK;
+  if (W == 1) return transpose_on<E>(ctx, st, d_in, rows, cols, d_out);
+  if (sizeof(E) == 8 && W == 2 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0)
+    return transpose_on<E127>(ctx, st, reinterpret_cast<const E127*>(d_in), rows, cols, reinterpret_cast<E127*>(d_out));  // pairs move as 16-byte elements
+  constexpr int CW = sizeof(E) == 8 ? 4 : 2;
+  const uint64_t tiles = ((rows + 31) / 32) * ((cols + 31) / 32) * ((W + CW - 1) / CW);
+  const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16);
+  k_transpose_wide<E, CW><<<grid, 256, 0, st>>>(d_in, rows, cols, W, d_out);
+  CKL();
+  return SCLGPU_OK;
+}
+
+static bool array_args_ok(sclgpu_ctx* ctx, uint64_t N, uint32_t W, uint32_t n, int& rc) {
+  rc = SCLGPU_OK;
+  if (W == 0 || W > 4096) rc = fail(ctx, SCLGPU_EINVAL, "array width must be in 1..4096");
+  else if (n >= (1u << 31)) rc = fail(ctx, SCLGPU_EINVAL, "n too large");
+  else if (N > (~0ull) / W / std::max<uint64_t>(n, 1) / 16) rc = fail(ctx, SCLGPU_EINVAL, "batch too large");
+  return rc == SCLGPU_OK;
+}
+
+// PRG fused on the tensor-core kernel when the component pairs line up with the keystream blocks
+template <class F>
+static bool share_array_fused(uint32_t W, uint32_t t, uint32_t n) {
+  const bool fits = F::BYTES == 8 ? (t <= kTcMaxT && n <= kTcMaxParties && W % 2 == 0) : (t <= kTcMaxT127 && n <= kTcMaxParties127);
+  return fits && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr;
+}
+
+// one chunk of nc sharings, secrets and output on the device; planes: (t+1)*nc*W elements of scratch,
+// tmp: n*nc*W elements (secret-major only)
+template <class F>
+static int share_array_chunk(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint64_t block0,
+                             const typename F::E* d_secrets, uint64_t nc, uint32_t W, uint32_t t, uint32_t n,
+                             typename F::E* planes, typename F::E* tmp, typename F::E* d_out, uint64_t out_si,
+                             bool secret_major) {
+  typedef typename F::E E;
+  if (share_array_fused<F>(W, t, n)) {
+    const void* d_bmat = nullptr;
+    RET(share_tc_bmat<F>(ctx, st, t, n, &d_bmat));
+    E* dst = secret_major ? tmp : d_out;
+    const uint64_t si = secret_major ? nc * W : out_si;
+    ctx->launches++;
+    cudaError_t e;
+    if constexpr (F::BYTES == 8) {
+      e = share61_wide_tc_launch(st, ctx->sm_count, key, ctx->d_t0, d_bmat, block0, d_secrets, nc * W, W, t, n, dst, si, 1);
+    } else {
+      e = share127_wide_tc_launch(st, ctx->sm_count, key, ctx->d_t0, d_bmat, block0, d_secrets, nc * W, W, t, n, dst, si, 1);
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
+    if (!secret_major) return SCLGPU_OK;
+    return transpose_wide_on<E>(ctx, st, tmp, n, nc, W, d_out);
+  }
+  RET(aes_opt_in(ctx, k_expand_coeffs<F>));
+  k_expand_coeffs<F><<<grid_for(ctx, nc, kAesThreads, 1), kAesThreads, kAesDynSmem, st>>>(
+      key, ctx->d_t0, block0, d_secrets, nc, t, W, planes);
+  CKL();
+  if (!secret_major) return share_coeffs_on<F>(ctx, st, planes, nc * W, t, n, d_out, out_si, 1);
+  RET(share_coeffs_on<F>(ctx, st, planes, nc * W, t, n, tmp, nc * W, 1));
+  return transpose_wide_on<E>(ctx, st, tmp, n, nc, W, d_out);
+}
+
+template <class F>
+static uint64_t share_array_chunk_len(uint64_t N, uint32_t W, uint32_t t, uint32_t n, uint64_t budget) {
+  const uint64_t per = (uint64_t)W * sizeof(typename F::E) * std::max<uint64_t>((uint64_t)t + 1, n);
+  uint64_t chunk = std::max<uint64_t>(budget / per, 256);
+  return std::min(chunk, N);
+}
+
+template <class F>
+static int share_array_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_t W, uint32_t t, uint32_t n,
+                           const uint8_t seed[16], uint64_t first_block, void* d_shares, int layout) {
+  typedef typename F::E E;
+  if (!ctx || !seed || ((!d_secrets || !d_shares) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  int rc;
+  if (!array_args_ok(ctx, N, W, n, rc)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const AesKey key = aes_expand(seed);
+  const uint64_t B = ((uint64_t)(t + 1) * W * F::BYTES + 15) / 16;
+  const bool sm = layout == SCLGPU_SECRET_MAJOR;
+  const bool fused = share_array_fused<F>(W, t, n);
+  const uint64_t chunk = (fused && !sm) ? N : share_array_chunk_len<F>(N, W, t, n, 512ull << 20);
+  DevBuf planes, tmp;
+  if (!fused) CK(planes.alloc(chunk * W * (uint64_t)(t + 1) * sizeof(E)));
+  if (sm) CK(tmp.alloc(chunk * W * (uint64_t)n * sizeof(E)));
+  const E* sec = reinterpret_cast<const E*>(d_secrets);
+  E* out = reinterpret_cast<E*>(d_shares);
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    RET(share_array_chunk<F>(ctx, ctx->stream, key, first_block + c0 * B, sec + c0 * W, nc, W, t, n, planes.as<E>(),
+                             tmp.as<E>(), sm ? out + c0 * n * W : out + c0 * W, N * W, sm));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // scratch is freed on return
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int share_array_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t W, uint32_t t, uint32_t n,
+                            const uint8_t seed[16], uint64_t first_block, void* shares) {
+  typedef typename F::E E;
+  if (!ctx || !seed || ((!secrets || !shares) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  int rc;
+  if (!array_args_ok(ctx, N, W, n, rc)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const AesKey key = aes_expand(seed);
+  const uint64_t B = ((uint64_t)(t + 1) * W * F::BYTES + 15) / 16;
+  uint64_t chunk = share_array_chunk_len<F>(N, W, t, n, 256ull << 20);
+  chunk = std::min(chunk, kHostChunk);
+  PoolScope pool_scope(ctx);
+  PoolBuf dsec[2], dpl[2], dpm[2], dsm[2];
+  const int nbuf = N > chunk ? 2 : 1;
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsec[k].alloc(chunk * W * sizeof(E)));
+    if (!share_array_fused<F>(W, t, n)) CK(dpl[k].alloc(chunk * W * (uint64_t)(t + 1) * sizeof(E)));
+    CK(dpm[k].alloc(chunk * W * (uint64_t)n * sizeof(E)));
+    CK(dsm[k].alloc(chunk * W * (uint64_t)n * sizeof(E)));
+  }
+  const E* hs = reinterpret_cast<const E*>(secrets);
+  E* ho = reinterpret_cast<E*>(shares);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    CK(cudaMemcpyAsync(dsec[k].p, hs + c0 * W, nc * W * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(share_array_chunk<F>(ctx, st, key, first_block + c0 * B, dsec[k].as<E>(), nc, W, t, n, dpl[k].as<E>(),
+                             dpm[k].as<E>(), dsm[k].as<E>(), 0, true));
+    CK(cudaMemcpyAsync(ho + c0 * n * W, dsm[k].p, nc * n * W * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+
+extern "C" int sclgpu_fp61_shamir_share_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return share_array_host<F61>(c, s, N, W, t, n, seed, fb, o); }
+extern "C" int sclgpu_fp127_shamir_share_array(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return share_array_host<F127>(c, s, N, W, t, n, seed, fb, o); }
+extern "C" int sclgpu_fp61_shamir_share_array_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return share_array_dev<F61>(c, s, N, W, t, n, seed, fb, o, layout); }
+extern "C" int sclgpu_fp127_shamir_share_array_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return share_array_dev<F127>(c, s, N, W, t, n, seed, fb, o, layout); }
+extern "C" uint64_t sclgpu_share_array_blocks(uint32_t element_bytes, uint32_t W, uint32_t t) { return ((uint64_t)(t + 1) * W * element_bytes + 15) / 16; }
+
 // ------------------------------------------------------------------ per-party packets
 // Serializer<math::Vector<FF>>::write (vector.h:596-629 -> serializer.h:160-176): a u32 element count
 // (StlVecSizeType, serializer.h:111) followed by the elements' FF::write bytes (ff.h:355-391).  Party i's
@@ -1183,6 +1332,27 @@ static int lagrange_host(sclgpu_ctx* ctx, const void* nodes, uint32_t n, const v
 extern "C" int sclgpu_fp61_lagrange_basis(sclgpu_ctx* c, const uint64_t* nodes, uint32_t n, const uint64_t* x, uint64_t* o) { return lagrange_host<F61>(c, nodes, n, x, o); }
 extern "C" int sclgpu_fp127_lagrange_basis(sclgpu_ctx* c, const void* nodes, uint32_t n, const void* x, void* o) { return lagrange_host<F127>(c, nodes, n, x, o); }
 
+// Matrix::hyperInvertible(n, m), matrix.h:462-475: row i = computeLagrangeBasis(range(1, m+1), -i); the
+// int overload (lagrange.h:80-82) makes -i the field element p - i (FF(int), mersenne61.cc:38-40).
+template <class F>
+static int hyper_invertible_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (n == 0 || m == 0) return fail(ctx, SCLGPU_EINVAL, "n or m cannot be 0");  // matrix.h:165
+  if (!out) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n >= (1u << 31) || m >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n or m too large");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<E> xs(n);
+  for (uint32_t i = 0; i < n; ++i) xs[i] = F::neg(F::from_u32(i));
+  const E* d_mat = nullptr;
+  RET(basis_rows<F>(ctx, ctx->pipe[0], nullptr, m, xs.data(), n, &d_mat));
+  CK(cudaMemcpyAsync(out, d_mat, (size_t)n * m * sizeof(E), cudaMemcpyDeviceToHost, ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_hyper_invertible(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return hyper_invertible_host<F61>(c, n, m, o); }
+extern "C" int sclgpu_fp127_hyper_invertible(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return hyper_invertible_host<F127>(c, n, m, o); }
+
 // ------------------------------------------------------------------ recover P
 template <class F>
 static int recover_p_basis(sclgpu_ctx* ctx, cudaStream_t st, uint32_t n, const void* alphas, const void* x,
@@ -1302,6 +1472,78 @@ extern "C" int sclgpu_fp61_recover_p(sclgpu_ctx* c, const uint64_t* s, uint64_t 
 extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return recover_p_host<F127>(c, s, N, n, a, x, o); }
 extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }
 extern "C" int sclgpu_fp127_recover_p_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, const void* x, void* o) { return recover_p_dev<F127>(c, s, N, n, layout, a, x, o); }
+
+// shamirRecoverP on Vector<Array<FF, W>> (shamir.h:100-104 with T = Array): the basis of nodes 1..n at 0
+// applied component-wise, i.e. the plane kernel on N*W columns.
+template <class F>
+static int recover_p_array_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N, uint32_t W, uint32_t n, int layout,
+                               void* d_out) {
+  typedef typename F::E E;
+  if (!ctx || ((!d_shares && n) || !d_out) && N) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  int rc;
+  if (!array_args_ok(ctx, N, W, n, rc)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  const E* d_basis = nullptr;
+  RET(recover_p_basis<F>(ctx, ctx->stream, n, nullptr, nullptr, &d_basis));
+  const E* in = reinterpret_cast<const E*>(d_shares);
+  E* out = reinterpret_cast<E*>(d_out);
+  if (layout == SCLGPU_PARTY_MAJOR || n == 0)
+    return recover_p_on<F>(ctx, ctx->stream, in, N * W, n, N * W, 1, d_basis, out);
+  uint64_t chunk = std::max<uint64_t>((512ull << 20) / ((uint64_t)n * W * sizeof(E)), 256);
+  chunk = std::min(chunk, N);
+  DevBuf tmp;
+  CK(tmp.alloc(chunk * n * W * sizeof(E)));
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    RET(transpose_wide_on<E>(ctx, ctx->stream, in + c0 * n * W, nc, n, W, tmp.as<E>()));
+    RET(recover_p_on<F>(ctx, ctx->stream, tmp.as<E>(), nc * W, n, nc * W, 1, d_basis, out + c0 * W));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SCLGPU_OK;
+}
+
+template <class F>
+static int recover_p_array_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t W, uint32_t n, void* out) {
+  typedef typename F::E E;
+  if (!ctx || ((!shares && n) || !out) && N) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  int rc;
+  if (!array_args_ok(ctx, N, W, n, rc)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  const E* d_basis = nullptr;
+  RET(recover_p_basis<F>(ctx, ctx->pipe[0], n, nullptr, nullptr, &d_basis));
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n, 1) * W * sizeof(E)), 256);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  const int nbuf = N > chunk ? 2 : 1;
+  PoolScope pool_scope(ctx);
+  PoolBuf dsh[2], dpm[2], dout[2];
+  for (int k = 0; k < nbuf; ++k) {
+    CK(dsh[k].alloc(chunk * n * W * sizeof(E)));
+    CK(dpm[k].alloc(chunk * n * W * sizeof(E)));
+    CK(dout[k].alloc(chunk * W * sizeof(E)));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  const E* hs = reinterpret_cast<const E*>(shares);
+  E* ho = reinterpret_cast<E*>(out);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n * W, nc * n * W * sizeof(E), cudaMemcpyHostToDevice, st));
+    RET(transpose_wide_on<E>(ctx, st, dsh[k].as<E>(), nc, n, W, dpm[k].as<E>()));
+    RET(recover_p_on<F>(ctx, st, dpm[k].as<E>(), nc * W, n, nc * W, 1, d_basis, dout[k].as<E>()));
+    CK(cudaMemcpyAsync(ho + c0 * W, dout[k].p, nc * W * sizeof(E), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_recover_p_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, uint64_t* o) { return recover_p_array_host<F61>(c, s, N, W, n, o); }
+extern "C" int sclgpu_fp127_recover_p_array(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t n, void* o) { return recover_p_array_host<F127>(c, s, N, W, n, o); }
+extern "C" int sclgpu_fp61_recover_p_array_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, int layout, uint64_t* o) { return recover_p_array_dev<F61>(c, s, N, W, n, layout, o); }
+extern "C" int sclgpu_fp127_recover_p_array_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t n, int layout, void* o) { return recover_p_array_dev<F127>(c, s, N, W, n, layout, o); }
 
 // ------------------------------------------------------------------ recover D
 static int finish_detect(sclgpu_ctx* ctx, cudaStream_t st, uint64_t* n_detected) {

@@ -329,13 +329,21 @@ __device__ __forceinline__ E127 tc_combine127(const uint32_t* v) {
 // COEFFS = false: coefficients drawn from the PRG (shamirSecretShare).  COEFFS = true: coefficient planes
 // supplied by the caller (Polynomial::create + evaluate, poly.h:56-64,179-198): `secrets` is then the
 // [t+1][N] array (coefficient k of secret j at k*N + j), no AES tables, and the kernel is HBM-bound.
-template <class F, int GROUPS, int NBUF, int PCOLS, bool COEFFS>
+// MODE 2 (array-valued secrets, shamirSecretShare on math::Array<FF, W>; pedersen.h:137-138): the N "secrets"
+// are the N/W sharings' components, v = j*W + c; sharing j draws (t+1)*W stream elements, element k*W + c being
+// coefficient k of component c (array.h:82-88 inside vector.h:508-519).  Fp127: one block per element, so thread v
+// draws blocks ctr0(j) + k*W + c itself.  Fp61 (W even): block (k*W + c)/2 holds coefficient k of components c
+// and c^1, which sit in adjacent lanes: the even lane draws the blocks of coefficients 0..h-1, the odd lane those
+// of h..2h-1 (h = ceil((t+1)/2)), and the two exchange the halves they do not own with one shuffle pair per block
+// -- the same AES work per thread as the plain kernel.
+template <class F, int GROUPS, int NBUF, int PCOLS, int MODE>
 __global__ void __launch_bounds__(128 * GROUPS, 1)
 k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
             const uint4* __restrict__ g_bmat, uint64_t first_block, const typename F::E* __restrict__ secrets,
             uint64_t N, uint32_t t, uint32_t n, typename F::E* __restrict__ out, uint64_t stride_i,
-            uint64_t stride_j) {
+            uint64_t stride_j, uint32_t W) {
   typedef typename F::E E;
+  constexpr bool COEFFS = MODE == 1, WIDE = MODE == 2;
   constexpr uint32_t EB = F::BYTES;                        // bytes = 8-bit limbs per element
   constexpr uint32_t kThreads = 128 * GROUPS;
   constexpr uint32_t kColsPerGroup = 32u + NBUF * PCOLS;
@@ -458,6 +466,55 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
       s2 = (uint32_t)sec.hi;
       s3 = (uint32_t)(sec.hi >> 32);
     }
+    if constexpr (WIDE) {
+      const uint64_t sh = jj / W;                          // the sharing, and the component within it
+      const uint32_t c = (uint32_t)(jj - sh * W);
+      PrgGroup grp;
+      if constexpr (EB == 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+        const uint64_t ctr0 = first_block + sh * ((uint64_t)(t + 1u) * W) + c;
+        uint64_t gid = ~0ull;
+#pragma unroll 1
+        for (uint32_t k = 1; k <= t; ++k) {
+          const uint64_t ctr = ctr0 + (uint64_t)k * W;
+          if ((ctr >> 8) != gid) {
+            gid = ctr >> 8;
+            prg_group(key, lanebase, ctr, grp);
+          }
+          uint32_t o0, o1, o2, o3;
+          prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+          __syncwarp();
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * k), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        }
+      } else {
+        const uint32_t h = (t + 2u) / 2u, odd = c & 1u, hw = W / 2u;
+        // block of coefficient k of this component pair: base + k*(W/2)
+        const uint64_t base = first_block + sh * ((uint64_t)(t + 1u) * hw) + (c >> 1);
+        uint64_t gid = ~0ull;
+#pragma unroll 1
+        for (uint32_t i = 0; i < h; ++i) {
+          const uint64_t ctr = base + (uint64_t)(odd ? h + i : i) * hw;  // k = h + i > t on the odd lane: drawn, unused
+          if ((ctr >> 8) != gid) {
+            gid = ctr >> 8;
+            prg_group(key, lanebase, ctr, grp);
+          }
+          uint32_t o0, o1, o2, o3;
+          prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
+          __syncwarp();
+          // words 0,1 = the even component, words 2,3 = the odd one: keep mine, hand the others to the neighbour
+          const uint32_t r0 = __shfl_xor_sync(0xFFFFFFFFu, odd ? o0 : o2, 1);
+          const uint32_t r1 = __shfl_xor_sync(0xFFFFFFFFu, odd ? o1 : o3, 1);
+          uint32_t lo0 = odd ? r0 : o0, lo1 = odd ? r1 : o1;   // coefficient i
+          const uint32_t hi0 = odd ? o2 : r0, hi1 = odd ? o3 : r1;  // coefficient h + i
+          if (i == 0) {
+            lo0 = s0;
+            lo1 = s1;
+          }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a_lane + 2u * i), "r"(lo0), "r"(lo1) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a_lane + 2u * (h + i)), "r"(hi0), "r"(hi1) : "memory");
+        }
+      }
+    } else {
     const uint64_t ctr0 = first_block + jj * nblk;
     if (t == 0 || EB == 16) {
       // Fp61, t = 0: one block is consumed, none of it is used.  Fp127: block 0 is slot 0 of the draw,
@@ -486,6 +543,7 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
         // keystream block b = K bytes [16b, 16b+16) of the row = TMEM columns 4b..4b+3 of this lane
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
       }
+    }
     }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -935,8 +993,8 @@ cudaError_t recover_d127_tc_launch(cudaStream_t st, int sm_count, const void* d_
 cudaError_t share_tc_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_share61_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDynSmem);
 #define X(V, G, NB, PC)                                                                                                                       \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F61, G, NB, PC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_tcm<F127, G, NB, PC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
   SCLGPU_TCM_VARIANTS(X)
 #undef X
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_ws<F61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTcmDynSmem + 128u));
@@ -964,8 +1022,8 @@ cudaError_t share61_tc_launch(int variant, cudaStream_t st, int grid, const AesK
   bool done = false;
 #define X(V, G, NB, PC)                                                                                               \
   if (variant == V) {                                                                                                 \
-    k_share_tcm<F61, G, NB, PC, false><<<grid, 128 * G, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
-                                                                  d_out, stride_i, stride_j);                         \
+    k_share_tcm<F61, G, NB, PC, 0><<<grid, 128 * G, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n,     \
+                                                                  d_out, stride_i, stride_j, 1u);                     \
     done = true;                                                                                                      \
   }
   SCLGPU_TCM_VARIANTS(X)
@@ -984,9 +1042,9 @@ cudaError_t share127_tc_launch(int variant, cudaStream_t st, int grid, const Aes
     return cudaGetLastError();
   }
   if (variant == 2) {
-    k_share_tcm<F127, 4, 1, 64, false><<<grid, 512, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    k_share_tcm<F127, 4, 1, 64, 0><<<grid, 512, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j, 1u);
   } else {
-    k_share_tcm<F127, 5, 1, 64, false><<<grid, 640, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j);
+    k_share_tcm<F127, 5, 1, 64, 0><<<grid, 640, kTcmDynSmem, st>>>(key, d_t0, bm, first_block, d_secrets, N, t, n, d_out, stride_i, stride_j, 1u);
   }
   return cudaGetLastError();
 }
@@ -996,14 +1054,14 @@ template <class F>
 static cudaError_t share_coeffs_tc_launch_t(cudaStream_t st, int sm_count, const void* d_bmat, const typename F::E* d_coeffs,
                                             uint64_t N, uint32_t t, uint32_t n, typename F::E* d_out, uint64_t stride_i,
                                             uint64_t stride_j) {
-  auto kern = k_share_tcm<F, 4, 1, 64, true>;  // four groups: the prefetched coefficients stay in registers
+  auto kern = k_share_tcm<F, 4, 1, 64, 1>;  // four groups: the prefetched coefficients stay in registers
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcCoeffDynSmem);
   if (e != cudaSuccess) return e;
   const uint64_t tiles = (N + 127) / 128;
   const int grid = (int)std::min<uint64_t>((tiles + 3) / 4, (uint64_t)sm_count);
   AesKey unused{};
   kern<<<grid, 512, kTcCoeffDynSmem, st>>>(unused, nullptr, reinterpret_cast<const uint4*>(d_bmat), 0, d_coeffs, N, t, n, d_out,
-                                          stride_i, stride_j);
+                                          stride_i, stride_j, 1u);
   return cudaGetLastError();
 }
 cudaError_t share61_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const uint64_t* d_coeffs, uint64_t N,
@@ -1013,6 +1071,32 @@ cudaError_t share61_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* 
 cudaError_t share127_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_coeffs, uint64_t N,
                                       uint32_t t, uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j) {
   return share_coeffs_tc_launch_t<F127>(st, sm_count, d_bmat, d_coeffs, N, t, n, d_out, stride_i, stride_j);
+}
+
+// shamirSecretShare on math::Array<FF, W>: NW = N*W component polynomials, PRG fused (k_share_tcm MODE 2).
+// Fp61 needs an even W (the neighbour exchange); Fp127 takes any W.
+template <class F>
+static cudaError_t share_wide_tc_launch_t(cudaStream_t st, int sm_count, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+                                          uint64_t first_block, const typename F::E* d_secrets, uint64_t NW, uint32_t W,
+                                          uint32_t t, uint32_t n, typename F::E* d_out, uint64_t stride_i, uint64_t stride_j) {
+  auto kern = k_share_tcm<F, 5, 1, 64, 2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcmDynSmem);
+  if (e != cudaSuccess) return e;
+  const uint64_t tiles = (NW + 127) / 128;
+  const int grid = (int)std::min<uint64_t>((tiles + 4) / 5, (uint64_t)sm_count);
+  kern<<<grid, 640, kTcmDynSmem, st>>>(key, d_t0, reinterpret_cast<const uint4*>(d_bmat), first_block, d_secrets, NW, t, n, d_out,
+                                      stride_i, stride_j, W);
+  return cudaGetLastError();
+}
+cudaError_t share61_wide_tc_launch(cudaStream_t st, int sm_count, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+                                   uint64_t first_block, const uint64_t* d_secrets, uint64_t NW, uint32_t W, uint32_t t, uint32_t n,
+                                   uint64_t* d_out, uint64_t stride_i, uint64_t stride_j) {
+  return share_wide_tc_launch_t<F61>(st, sm_count, key, d_t0, d_bmat, first_block, d_secrets, NW, W, t, n, d_out, stride_i, stride_j);
+}
+cudaError_t share127_wide_tc_launch(cudaStream_t st, int sm_count, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+                                    uint64_t first_block, const E127* d_secrets, uint64_t NW, uint32_t W, uint32_t t, uint32_t n,
+                                    E127* d_out, uint64_t stride_i, uint64_t stride_j) {
+  return share_wide_tc_launch_t<F127>(st, sm_count, key, d_t0, d_bmat, first_block, d_secrets, NW, W, t, n, d_out, stride_i, stride_j);
 }
 
 }  // namespace sclgpu

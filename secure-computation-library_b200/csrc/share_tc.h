@@ -63,4 +63,13 @@ cudaError_t share61_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* 
 cudaError_t share127_coeffs_tc_launch(cudaStream_t st, int sm_count, const void* d_bmat, const E127* d_coeffs, uint64_t N,
                                       uint32_t t, uint32_t n, E127* d_out, uint64_t stride_i, uint64_t stride_j);
 
+// shamirSecretShare on math::Array<FF, W> with the PRG fused: NW = N*W component polynomials (secrets[j*W + c]),
+// sharing j drawing ceil((t+1)*W*BYTES/16) blocks from first_block + j*that.  Fp61: W even.
+cudaError_t share61_wide_tc_launch(cudaStream_t st, int sm_count, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+                                   uint64_t first_block, const uint64_t* d_secrets, uint64_t NW, uint32_t W, uint32_t t, uint32_t n,
+                                   uint64_t* d_out, uint64_t stride_i, uint64_t stride_j);
+cudaError_t share127_wide_tc_launch(cudaStream_t st, int sm_count, const AesKey& key, const uint32_t* d_t0, const void* d_bmat,
+                                    uint64_t first_block, const E127* d_secrets, uint64_t NW, uint32_t W, uint32_t t, uint32_t n,
+                                    E127* d_out, uint64_t stride_i, uint64_t stride_j);
+
 }  // namespace sclgpu

@@ -268,6 +268,43 @@ int main() {
     const auto B3 = math::Matrix<Fp127>::random(5, 11, mb);
     REQUIRE(sclgpu::multiply(ctx, A3, B3).equals(A3.multiply(B3)));
     REQUIRE(throwsInvalid([&] { (void)sclgpu::multiply(ctx, A2, A2); }, "matmul: this->cols() != that->rows()"));
+    // test_matrix.cc:397-406 (HIM) -- here against the reference's matrix itself
+    REQUIRE(sclgpu::hyperInvertible<Fp61>(ctx, 4, 5).equals(math::Matrix<Fp61>::hyperInvertible(4, 5)));
+    REQUIRE(sclgpu::hyperInvertible<Fp127>(ctx, 7, 3).equals(math::Matrix<Fp127>::hyperInvertible(7, 3)));
+    REQUIRE(throwsInvalid([&] { (void)sclgpu::hyperInvertible<Fp61>(ctx, 0, 5); }, "n or m cannot be 0"));
+  }
+  {  // array-valued secrets: the sharing step of pedersenSecretShare (pedersen.h:137-138), W = 2 and 3
+    PRG a = PRG::create("pedersen"), b = PRG::create("pedersen");
+    using A2 = math::Array<Fp61, 2>;
+    using A3 = math::Array<Fp127, 3>;
+    std::vector<A2> s2;
+    for (int j = 0; j < 300; ++j) s2.push_back(A2{{Fp61(1000 + j), Fp61::random(a)}});
+    for (int j = 0; j < 300; ++j) (void)Fp61::random(b);  // keep both PRGs at the same counter
+    const auto g2 = sclgpu::shamirSecretShare(ctx, s2, 4, 9, b);
+    REQUIRE(g2.size() == s2.size());
+    bool same = true;
+    for (std::size_t j = 0; j < s2.size(); ++j) {
+      const auto want = ss::shamirSecretShare(s2[j], 4, 9, a);
+      same = same && want.equals(g2[j]);
+    }
+    REQUIRE(same);
+    REQUIRE(math::Vector<Fp61>::random(5, a).equals(math::Vector<Fp61>::random(5, b)));  // PRG state after the batch
+    const auto r2 = sclgpu::shamirRecoverP(ctx, g2);
+    same = true;
+    for (std::size_t j = 0; j < s2.size(); ++j) same = same && r2[j] == s2[j] && r2[j] == ss::shamirRecoverP(g2[j]);
+    REQUIRE(same);
+    std::vector<A3> s3;
+    for (int j = 0; j < 77; ++j) s3.push_back(A3::random(a));
+    for (int j = 0; j < 77; ++j) (void)A3::random(b);
+    const auto g3 = sclgpu::shamirSecretShare(ctx, s3, 7, 16, b);
+    same = true;
+    for (std::size_t j = 0; j < s3.size(); ++j) same = same && ss::shamirSecretShare(s3[j], 7, 16, a).equals(g3[j]);
+    REQUIRE(same);
+    const auto r3 = sclgpu::shamirRecoverP(ctx, g3);
+    same = true;
+    for (std::size_t j = 0; j < s3.size(); ++j) same = same && r3[j] == s3[j];
+    REQUIRE(same);
+    REQUIRE(math::Vector<Fp127>::random(3, a).equals(math::Vector<Fp127>::random(3, b)));
   }
   std::printf("SHIM_OK checks=%d launches=%llu\n", g_checks, (unsigned long long)ctx.launches());
   return 0;

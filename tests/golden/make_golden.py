@@ -110,6 +110,21 @@ def main():
                               "secrets": hx(secrets, field), "shares": hx(sh, field),
                               "recover": hx(r.additive_recover(field, sh), field)})
 
+    # --- shamirSecretShare / shamirRecoverP on math::Array<FF, W> (pedersen.h:137-138 uses W = 2), and
+    #     Matrix::hyperInvertible (matrix.h:462-475)
+    g["share_array"] = []
+    for field, W, t, n, N, seed, first in [(61, 2, 2, 5, 3, "pedersen", 0), (61, 2, 15, 32, 2, "shamir bench", 7),
+                                           (61, 3, 1, 4, 2, "array", 0), (61, 1, 2, 5, 2, "shamir passive", 0),
+                                           (127, 2, 2, 5, 2, "pedersen", 0), (127, 3, 7, 16, 2, "m127", 11)]:
+        secrets = from_ints([[100 * j + w + 1 for w in range(W)] for j in range(N)], field)
+        sh = r.shamir_share_array(field, secrets, t, n, seed, first)
+        g["share_array"].append({"field": field, "W": W, "t": t, "n": n, "N": N, "seed": seed, "first_block": first,
+                                 "secrets": hx(secrets, field), "shares": hx(sh, field),
+                                 "recover": hx(r.recover_p_array(field, sh), field)})
+    g["hyper_invertible"] = []
+    for field, n, m in [(61, 4, 5), (61, 1, 1), (61, 6, 3), (127, 4, 5), (127, 3, 3)]:
+        g["hyper_invertible"].append({"field": field, "n": n, "m": m, "him": hx(r.hyper_invertible(field, n, m), field)})
+
     # sum over all shares of 1024 calls (secrets 123..1146), t=15 n=32, PRG("shamir bench")
     secrets = from_ints([123 + j for j in range(1024)], 61)
     sh = r.shamir_share(61, secrets, 15, 32, "shamir bench", 0)

@@ -19,6 +19,11 @@ for field, t, n, N in [(61, 15, 32, 3000), (61, 2, 5, 777), (127, 7, 16, 1500), 
         bad.reshape(N, n, -1)[::7, t + 1, 0] ^= np.uint64(3)
         g, w = ctx.recover_d(field, bad, t), port.recover_d(field, bad, t)
         assert np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) and g[2] == w[2], ("recover_d", field, t)
+for field, W, t, n, N in [(61, 2, 15, 32, 1500), (61, 4, 2, 5, 301), (127, 2, 7, 16, 700), (127, 3, 1, 4, 129)]:   # array-valued secrets
+    sec = port.vector_random(field, "pairs", 0, N * W).reshape((N, W) + (() if field == 61 else (2,)))
+    sh = ctx.shamir_share_array(field, sec, t, n, "knobs", 5)
+    assert np.array_equal(sh, port.shamir_share_array(field, sec, t, n, "knobs", 5)), ("share_array", field, W, t, n)
+    assert np.array_equal(ctx.recover_p_array(field, sh), sec), ("recover_p_array", field, W, n)
 for field, rows, inner, cols in [(61, 300, 520, 70), (61, 129, 4100, 33), (61, 257, 130, 257), (127, 130, 520, 40), (127, 64, 2100, 20)]:
     shp = () if field == 61 else (2,)
     A = port.vector_random(field, "mat A", 0, rows * inner).reshape((rows, inner) + shp)

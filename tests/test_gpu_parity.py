@@ -593,6 +593,79 @@ def test_share_packets_wire_layout(ctx, pkg, orc, field, t, n, N):
         ctx.recover_p_packets(field, bad, N)
 
 
+# ------------------------------------------------------------------ array-valued secrets, hyperInvertible
+def test_share_array_and_him_golden(ctx, port, golden):
+    for c in golden["share_array"]:
+        f, W, N, n = c["field"], c["W"], c["N"], c["n"]
+        secrets = unhex(port, c["secrets"], f, (N, W))
+        sh = ctx.shamir_share_array(f, secrets, c["t"], n, c["seed"], c["first_block"])
+        assert ints(port, sh, f) == [int(h, 16) for h in c["shares"]], c
+        assert ints(port, ctx.recover_p_array(f, sh), f) == [int(h, 16) for h in c["recover"]]
+    for c in golden["hyper_invertible"]:
+        f = c["field"]
+        assert ints(port, ctx.hyper_invertible(f, c["n"], c["m"]), f) == [int(h, 16) for h in c["him"]]
+
+
+@pytest.mark.parametrize("field,W,t,n,N", [(61, 2, 15, 32, 1 << 14), (61, 2, 2, 5, 4099), (61, 3, 7, 16, 3001), (61, 1, 4, 9, 777),
+                                           (61, 5, 1, 3, 130), (61, 2, 20, 40, 515), (61, 4, 0, 2, 33), (61, 9, 3, 7, 260),
+                                           (61, 2, 14, 31, 70001), (61, 6, 1, 32, 1111), (61, 2, 0, 1, 129), (61, 4, 9, 17, 6400),
+                                           (61, 2, 7, 16, 1 << 17),
+                                           (127, 2, 7, 16, 1 << 12), (127, 3, 2, 5, 1025), (127, 1, 3, 8, 300), (127, 5, 9, 12, 129),
+                                           (127, 2, 0, 3, 257), (127, 4, 6, 13, 20000)])
+def test_share_array_vs_oracle(ctx, pkg, port, orc, field, W, t, n, N):
+    """shamirSecretShare on math::Array<FF, W> + shamirRecoverP, host and device-pointer paths, both layouts."""
+    import torch
+
+    o = orc if (orc.kind == "port" or W <= 5) else port      # the reference driver instantiates W = 1..5
+    es = () if field == 61 else (2,)
+    secrets = port.vector_random(field, "secrets", 0, N * W).reshape((N, W) + es)
+    first = (1 << 33) - 77 if o.kind == "port" else 1234
+    want = o.shamir_share_array(field, secrets, t, n, "shamir bench", first)
+    got = ctx.shamir_share_array(field, secrets, t, n, "shamir bench", first)
+    assert np.array_equal(got, want)
+    rec = ctx.recover_p_array(field, got)
+    assert np.array_equal(rec, o.recover_p_array(field, want))
+    if t < n:
+        assert np.array_equal(rec, secrets)
+    if W == 1:
+        assert np.array_equal(got.reshape(-1), ctx.shamir_share(field, secrets.reshape((N,) + es), t, n, "shamir bench", first).reshape(-1))
+    assert pkg.binding.load().sclgpu_share_array_blocks(8 if field == 61 else 16, W, t) == pkg.api.blocks_per_array_share_call(field, W, t)
+    # device pointers: secret-major [N][n][W] and party-major [n][N][W]
+    ctx.use_torch_stream()
+    w = 1 if field == 61 else 2
+    d_sec = torch.from_numpy(secrets.view(np.int64)).cuda()
+    for layout in (pkg.binding.SECRET_MAJOR, pkg.binding.PARTY_MAJOR):
+        shape = (N, n, W, w) if layout == pkg.binding.SECRET_MAJOR else (n, N, W, w)
+        d_sh = torch.zeros(shape, dtype=torch.int64, device="cuda")
+        d_out = torch.zeros((N, W, w), dtype=torch.int64, device="cuda")
+        ctx.shamir_share_array_dev(field, d_sec, N, W, t, n, "shamir bench", first, d_sh, layout)
+        ctx.recover_p_array_dev(field, d_sh, N, W, n, d_out, layout)
+        torch.cuda.synchronize()
+        h = d_sh.cpu().numpy().view(np.uint64)
+        if layout == pkg.binding.PARTY_MAJOR:
+            h = np.swapaxes(h, 0, 1)
+        assert np.array_equal(h.reshape(want.shape), want), layout
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(rec.shape), rec), layout
+
+
+@pytest.mark.parametrize("field", [61, 127])
+def test_hyper_invertible_vs_oracle(ctx, pkg, orc, field):
+    for n, m in ((4, 5), (1, 1), (7, 3), (16, 16), (33, 20), (2, 64)):
+        assert np.array_equal(ctx.hyper_invertible(field, n, m), orc.hyper_invertible(field, n, m)), (n, m)
+    with pytest.raises(pkg.InvalidArgument):
+        ctx.hyper_invertible(field, 0, 3)
+    with pytest.raises(pkg.InvalidArgument):
+        ctx.hyper_invertible(field, 3, 0)
+
+
+def test_share_array_errors_and_empty(ctx, pkg, port):
+    with pytest.raises(pkg.InvalidArgument):
+        ctx.shamir_share_array(61, np.zeros((3, 0), dtype=np.uint64), 1, 3, "x")
+    out = ctx.shamir_share_array(61, np.zeros((0, 2), dtype=np.uint64), 1, 3, "x")
+    assert out.shape == (0, 3, 2)
+    assert ctx.recover_p_array(61, out).shape == (0, 2)
+
+
 # ------------------------------------------------------------------ additive sharing (SURVEY 8f.2)
 def test_additive_golden(ctx, port, golden):
     for c in golden["additive"]:

@@ -156,6 +156,44 @@ def test_port_vs_reference_recover_c(port, ref):
             assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3], (field, n, "alphas")
 
 
+def test_golden_share_array_and_him(port, golden):
+    """shamirSecretShare / shamirRecoverP on math::Array<FF, W> (pedersen.h:137-138) and
+    Matrix::hyperInvertible (matrix.h:462-475): vectors recorded from the reference."""
+    for c in golden["share_array"]:
+        f, W, N, n = c["field"], c["W"], c["N"], c["n"]
+        secrets = unhex(port, c["secrets"], f, (N, W))
+        sh = port.shamir_share_array(f, secrets, c["t"], n, c["seed"], c["first_block"])
+        assert ints(port, sh, f) == [int(h, 16) for h in c["shares"]], c
+        assert ints(port, port.recover_p_array(f, sh), f) == [int(h, 16) for h in c["recover"]] == ints(port, secrets, f)
+    for c in golden["hyper_invertible"]:
+        f = c["field"]
+        assert ints(port, port.hyper_invertible(f, c["n"], c["m"]), f) == [int(h, 16) for h in c["him"]]
+    # W = 1 is the plain shamirSecretShare; component w of coefficient k is stream element k*W + w
+    sec = port.from_ints([[5, 6], [7, 8]], 61)
+    sh = port.shamir_share_array(61, sec, 1, 3, "pattern", 4)           # t = 1: share_i = s + c_1 * i
+    c1 = port.vector_random(61, "pattern", 4, 8).reshape(2, 4)[:, 2:]   # 2 blocks per sharing, elements 2, 3
+    p = (1 << 61) - 1
+    want = [[[(int(sec[j, w]) + int(c1[j, w]) * i) % p for w in range(2)] for i in (1, 2, 3)] for j in range(2)]
+    assert port.to_ints(sh, 61).tolist() == want
+
+
+def test_port_vs_reference_share_array_and_him(port, ref):
+    for field in (61, 127):
+        for W in (1, 2, 3, 5):
+            for t, n in ((2, 5), (15, 32), (0, 3), (7, 16), (4, 4), (20, 40)):
+                sec = port.vector_random(field, "secrets", 0, 9 * W).reshape((9, W) + (() if field == 61 else (2,)))
+                a = port.shamir_share_array(field, sec, t, n, "shamir bench", 3)
+                assert np.array_equal(a, ref.shamir_share_array(field, sec, t, n, "shamir bench", 3)), (field, W, t, n)
+                ra = port.recover_p_array(field, a)
+                assert np.array_equal(ra, ref.recover_p_array(field, a))
+                if t < n:
+                    assert np.array_equal(ra, sec)
+                if W == 1:
+                    assert np.array_equal(a.reshape(-1), port.shamir_share(field, sec.reshape((9,) + (() if field == 61 else (2,))), t, n, "shamir bench", 3).reshape(-1))
+        for n, m in ((4, 5), (1, 1), (7, 3), (16, 16), (33, 20)):
+            assert np.array_equal(port.hyper_invertible(field, n, m), ref.hyper_invertible(field, n, m))
+
+
 def test_golden_additive(port, golden):
     """additiveShare (additive.h:42-53): vectors recorded from the reference; reconstruction = sum."""
     for c in golden["additive"]:

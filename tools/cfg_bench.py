@@ -112,4 +112,20 @@ for dim in (2048, 4096, 8192):
     ms = timeit(lambda: ctx.matmul_dev(61, A, dim, dim, Bm, dim, Cm))
     res[f"matmul_fp61_{dim}"] = {"ms": ms, "field_mults_per_s": dim ** 3 / (ms * 1e-3), "int8_TOPS": 128 * dim ** 3 / (ms * 1e-3) / 1e12}
     del A, Bm, Cm; torch.cuda.empty_cache()
+# Pedersen's sharing step: shamirSecretShare on math::Array<Fp61, 2> ({secret, randomness}), 2^25 pairs, n=32 t=15
+N, W, t, n = 1 << 25, 2, 15, 32
+sec, sh, out = i64(N, W), i64(n, N, W), i64(N, W)
+ctx.random_dev(61, "pairs", 0, N * W, sec)
+r = {"N": N, "W": W, "t": t, "n": n}
+r["share_ms"] = timeit(lambda: ctx.shamir_share_array_dev(61, sec, N, W, t, n, "pedersen", 0, sh, B.PARTY_MAJOR))
+r["recover_p_ms"] = timeit(lambda: ctx.recover_p_array_dev(61, sh, N, W, n, out, B.PARTY_MAJOR))
+r["ok"] = bool(torch.equal(out, sec))
+sm = i64(N, n, W)
+r["share_secret_major_ms"] = timeit(lambda: ctx.shamir_share_array_dev(61, sec, N, W, t, n, "pedersen", 0, sm, B.SECRET_MAJOR))
+r["recover_p_secret_major_ms"] = timeit(lambda: ctx.recover_p_array_dev(61, sm, N, W, n, out, B.SECRET_MAJOR))
+r["ok_secret_major"] = bool(torch.equal(out, sec))
+r["pairs_per_s"] = N / ((r["share_ms"] + r["recover_p_ms"]) * 1e-3)
+res["array2_fp61_n32_t15_2^25_pairs"] = r
+del sec, sh, out, sm
+
 print(json.dumps(res, indent=1))
