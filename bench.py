@@ -278,7 +278,7 @@ def run_b200(args):
                   "share_from_coeffs_ms": sc_ms, "recover_ms": sr_ms,
                   "share_from_coeffs_GBps": (8 * (t + 1) + 8 * n) * N / (sc_ms * 1e-3) / 1e9,
                   "note": "coefficient planes pre-expanded in HBM (PRG outside the timed region); "
-                          "k_share_tcm<F61,5,1,64,coeffs> + k_recover61_pm<2>"}
+                          "k_share_tcm<F61,4,1,64,coeffs> (next tile prefetched) + k_recover61_pm<2>"}
         del d_planes
         torch.cuda.empty_cache()
 
