@@ -166,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------- GPU arm
@@ -413,15 +413,34 @@ def run_b200(args):
                 "value": v, "unit": UNIT, "cores": cores, "kind": "reference" if kind == "reference" else "port",
                 "sample": f"{n_sample} secrets, SCL's per-secret shamirSecretShare+shamirRecoverP on {cores} threads "
                           f"(about {args.cpu_seconds:.0f} s of CPU work)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The contract is ONE JSON line on stdout: libraries that write to fd 1 on their own (NCCL prints its version
+    banner there) are kept off it by pointing fd 1 at stderr for the whole run and printing the line on the saved fd."""
+    sys.stdout.flush()
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
