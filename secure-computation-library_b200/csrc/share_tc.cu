@@ -119,15 +119,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// share = sum_s v[s] * 2^(8s) mod p, v[s] < 2^23; canonical result
+// share = sum_s v[s] * 2^(8s) mod p, v[s] < 2^23; canonical result.
+// R = the limbs gathered below 2^64 (2^61 = 1 folds the top of limb pair 6,7); then with a = R >> 61 (<= 5)
+// q = floor(R / p) = (R + a + 1) >> 61 exactly, and R mod p = (R + q) mod 2^61 -- no compare / select.
 __device__ __forceinline__ uint64_t tc_combine(const uint32_t* v) {
   const uint32_t p01 = v[0] + (v[1] << 8), p23 = v[2] + (v[3] << 8);  // < 2^32
   const uint32_t p45 = v[4] + (v[5] << 8), p67 = v[6] + (v[7] << 8);
   // p67 * 2^48 = (p67 mod 2^13) * 2^48 + (p67 >> 13) * 2^61, and 2^61 = 1
   const uint64_t R = (uint64_t)p01 + ((uint64_t)p23 << 16) + ((uint64_t)p45 << 32) +
-                     ((uint64_t)(p67 & 0x1FFFu) << 48) + (uint64_t)(p67 >> 13);  // < 2^64
-  const uint64_t r = (R & F61::P) + (R >> 61);
-  return r >= F61::P ? r - F61::P : r;
+                     ((uint64_t)(p67 & 0x1FFFu) << 48) + (uint64_t)(p67 >> 13);  // < 2^63 + 2^62
+  const uint32_t lo = (uint32_t)R, hi = (uint32_t)(R >> 32);
+  const uint32_t a1 = (hi >> 29) + 1u;
+  uint32_t t0, q, r0, r1;
+  asm("{\n\t"
+      "add.cc.u32 %0, %4, %6;\n\t"        // R + a + 1: only the bits from 61 up are used
+      "addc.u32 %1, %5, 0;\n\t"
+      "shr.u32 %1, %1, 29;\n\t"           // q
+      "add.cc.u32 %2, %4, %1;\n\t"        // R + q
+      "addc.u32 %3, %5, 0;\n\t"
+      "and.b32 %3, %3, 0x1FFFFFFF;\n\t"
+      "}"
+      : "=&r"(t0), "=&r"(q), "=&r"(r0), "=&r"(r1)
+      : "r"(lo), "r"(hi), "r"(a1));
+  (void)t0;
+  return (uint64_t)r0 | ((uint64_t)r1 << 32);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -402,6 +417,17 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
     tc_commit(b ? mbar1 : mbar0);
   };
   auto emit = [&](const uint32_t (&v)[32], E* dst, uint32_t first_party) {
+    if (first_party + kLdParties <= n) {  // all parties of this load exist (always, when n is a multiple of 4 / 2)
+#pragma unroll
+      for (uint32_t ii = 0; ii < kLdParties; ++ii) {
+        if constexpr (EB == 8) {
+          dst[(uint64_t)ii * stride_i] = tc_combine(v + 8 * ii);
+        } else {
+          dst[(uint64_t)ii * stride_i] = tc_combine127(v + 16 * ii);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (uint32_t ii = 0; ii < kLdParties; ++ii) {
       if (first_party + ii < n) {
