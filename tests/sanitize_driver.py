@@ -35,5 +35,12 @@ A = port.vector_random(61, "mat A", 0, 130 * 4100).reshape(130, 4100); Bm = port
 assert np.array_equal(ctx.matmul(61, A, Bm), port.matmul(61, A, Bm))
 A7 = port.vector_random(127, "mat A", 0, 9 * 6).reshape(9, 6, 2); B7 = port.vector_random(127, "mat B", 0, 6 * 5).reshape(6, 5, 2)
 assert np.array_equal(ctx.matmul(127, A7, B7), port.matmul(127, A7, B7))
+# array-valued secrets: fused pair exchange (Fp61 even W), strided counters (Fp127), staged path (odd W), wide transposes
+for field, W, t, n, N in [(61, 2, 15, 32, 300), (61, 4, 2, 5, 77), (61, 3, 3, 7, 100), (127, 2, 7, 16, 150), (127, 3, 9, 12, 40)]:
+    sec = port.vector_random(field, "pairs", 0, N * W).reshape((N, W) + (() if field == 61 else (2,)))
+    sh = ctx.shamir_share_array(field, sec, t, n, "pedersen", 3)
+    assert np.array_equal(sh, port.shamir_share_array(field, sec, t, n, "pedersen", 3))
+    assert np.array_equal(ctx.recover_p_array(field, sh), sec)
+assert np.array_equal(ctx.hyper_invertible(61, 4, 5), port.hyper_invertible(61, 4, 5))
 ctx.close()
 print("SANITIZE_DRIVER_OK")
