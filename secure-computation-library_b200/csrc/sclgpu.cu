@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "matmul_tc.h"
 #include "share_tc.h"
+#include "host_stage.h"
 
 using namespace sclgpu;
 
@@ -48,6 +49,8 @@ struct sclgpu_ctx {
   // cudaFree pair per buffer per call costs milliseconds and a device synchronisation
   std::vector<std::pair<void*, size_t>> pool;
   size_t pool_next = 0;
+  // pageable host buffers (std::vector-backed SCL containers) go through a pinned ring + copy threads
+  sclgpu::HostStager stager;
 };
 
 static constexpr int kMaxPartials = 2048;
@@ -307,7 +310,10 @@ struct PoolScope {
     g_pool_ctx = ctx;
     if (ctx) ctx->pool_next = 0;
   }
-  ~PoolScope() { g_pool_ctx = nullptr; }
+  ~PoolScope() {
+    if (g_pool_ctx) g_pool_ctx->stager.drain();  // error paths: no staged copy outlives the call
+    g_pool_ctx = nullptr;
+  }
 };
 struct PoolBuf {
   void* p = nullptr;
@@ -805,10 +811,11 @@ extern "C" int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64
     const uint64_t nb = std::min(chunk, n_bytes - off);
     cudaStream_t st = ctx->pipe[k];
     RET(prg_bytes_on(ctx, st, seed, first_block + off / 16, nb, buf[k].as<uint8_t>()));
-    CK(cudaMemcpyAsync(out + off, buf[k].p, nb, cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, out + off, buf[k].p, nb));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 
@@ -823,12 +830,13 @@ struct HostOp {
   explicit HostOp(sclgpu_ctx* c) : ctx(c), st(c->pipe[0]) {}
   ~HostOp() {
     cudaStreamSynchronize(st);
+    ctx->stager.drain();
     for (void* p : bufs) cudaFree(p);
   }
   int up(const void* h, size_t bytes, void** d) {
     CK(cudaMalloc(d, bytes ? bytes : 1));
     bufs.push_back(*d);
-    if (bytes) CK(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st));
+    if (bytes) CK(ctx->stager.h2d(st, *d, h, bytes));
     return SCLGPU_OK;
   }
   int dev(size_t bytes, void** d) {
@@ -837,8 +845,9 @@ struct HostOp {
     return SCLGPU_OK;
   }
   int down(void* h, const void* d, size_t bytes) {
-    if (bytes) CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+    if (bytes) CK(ctx->stager.d2h(st, h, d, bytes));
     CK(cudaStreamSynchronize(st));
+    CK(ctx->stager.drain());
     return SCLGPU_OK;
   }
 };
@@ -862,10 +871,11 @@ static int random_host(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_b
     const uint64_t nc = std::min(chunk, n - off);
     cudaStream_t st = ctx->pipe[k];
     RET((random_on<F, ONE>(ctx, st, seed, first_block + off / per_block, nc, buf[k].as<E>())));
-    CK(cudaMemcpyAsync(reinterpret_cast<E*>(out) + off, buf[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, reinterpret_cast<E*>(out) + off, buf[k].p, nc * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 
@@ -971,14 +981,15 @@ static int share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    CK(cudaMemcpyAsync(dsec[k].p, hs + c0, nc * sizeof(E), cudaMemcpyHostToDevice, st));
+    CK(ctx->stager.h2d(st, dsec[k].p, hs + c0, nc * sizeof(E)));
     RET(share_strided_on<F>(ctx, st, dsec[k].as<E>(), nc, t, n, seed, first_block + c0 * B,
                             dpm[k].as<E>(), nc, 1));
     RET(transpose_on<E>(ctx, st, dpm[k].as<E>(), n, nc, dsm[k].as<E>()));
-    CK(cudaMemcpyAsync(ho + c0 * n, dsm[k].p, nc * n * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0 * n, dsm[k].p, nc * n * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 
@@ -1135,13 +1146,14 @@ static int share_array_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, ui
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    CK(cudaMemcpyAsync(dsec[k].p, hs + c0 * W, nc * W * sizeof(E), cudaMemcpyHostToDevice, st));
+    CK(ctx->stager.h2d(st, dsec[k].p, hs + c0 * W, nc * W * sizeof(E)));
     RET(share_array_chunk<F>(ctx, st, key, first_block + c0 * B, dsec[k].as<E>(), nc, W, t, n, dpl[k].as<E>(),
                              dpm[k].as<E>(), dsm[k].as<E>(), 0, true));
-    CK(cudaMemcpyAsync(ho + c0 * n * W, dsm[k].p, nc * n * W * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0 * n * W, dsm[k].p, nc * n * W * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 
@@ -1186,14 +1198,14 @@ static int share_packets_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, 
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    CK(cudaMemcpyAsync(dsec[k].p, hs + c0, nc * sizeof(E), cudaMemcpyHostToDevice, st));
+    CK(ctx->stager.h2d(st, dsec[k].p, hs + c0, nc * sizeof(E)));
     RET(share_strided_on<F>(ctx, st, dsec[k].as<E>(), nc, t, n, seed, first_block + c0 * B, dpm[k].as<E>(), nc, 1));
     for (uint32_t i = 0; i < n; ++i)
-      CK(cudaMemcpyAsync(packets[i] + kPacketHeader + c0 * sizeof(E), dpm[k].as<E>() + (uint64_t)i * nc, nc * sizeof(E),
-                         cudaMemcpyDeviceToHost, st));
+      CK(ctx->stager.d2h(st, packets[i] + kPacketHeader + c0 * sizeof(E), dpm[k].as<E>() + (uint64_t)i * nc, nc * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 
@@ -1253,13 +1265,14 @@ static int additive_share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N,
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    CK(cudaMemcpyAsync(dsec[k].p, hs + c0, nc * sizeof(E), cudaMemcpyHostToDevice, st));
+    CK(ctx->stager.h2d(st, dsec[k].p, hs + c0, nc * sizeof(E)));
     RET(additive_share_on<F>(ctx, st, dsec[k].as<E>(), nc, n, seed, first_block + c0 * (uint64_t)(n - 1), dpm[k].as<E>(), nc, 1));
     RET(transpose_on<E>(ctx, st, dpm[k].as<E>(), n, nc, dsm[k].as<E>()));
-    CK(cudaMemcpyAsync(ho + c0 * n, dsm[k].p, nc * n * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0 * n, dsm[k].p, nc * n * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 
@@ -1298,13 +1311,14 @@ static int additive_recover_host(sclgpu_ctx* ctx, const void* shares, uint64_t N
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n, nc * n * sizeof(E), cudaMemcpyHostToDevice, st));
+    if (n) CK(ctx->stager.h2d(st, dsh[k].p, hs + c0 * n, nc * n * sizeof(E)));
     k_additive_recover<F><<<grid_for(ctx, nc, 256, 8), 256, 0, st>>>(dsh[k].as<E>(), nc, n, 1, n, dout[k].as<E>());
     CKL();
-    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0, dout[k].p, nc * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 extern "C" int sclgpu_fp61_additive_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return additive_share_host<F61>(c, s, N, n, seed, fb, o); }
@@ -1409,14 +1423,15 @@ static int recover_p_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n, nc * n * sizeof(E), cudaMemcpyHostToDevice, st));
+    if (n) CK(ctx->stager.h2d(st, dsh[k].p, hs + c0 * n, nc * n * sizeof(E)));
     // SCL's [N][n] -> party-major planes on the device (coalesced on both sides), then the plane kernel
     RET(transpose_on<E>(ctx, st, dsh[k].as<E>(), nc, n, dpm[k].as<E>()));
     RET(recover_p_on<F>(ctx, st, dpm[k].as<E>(), nc, n, nc, 1, d_basis, dout[k].as<E>()));
-    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0, dout[k].p, nc * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 // shamirRecoverP from the n packets a reconstructing party received (packet i = Vector of party i's
@@ -1454,13 +1469,13 @@ static int recover_p_packets_host(sclgpu_ctx* ctx, const uint8_t* const* packets
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
     for (uint32_t i = 0; i < n; ++i)
-      CK(cudaMemcpyAsync(dsh[k].as<E>() + (uint64_t)i * nc, packets[i] + kPacketHeader + c0 * sizeof(E), nc * sizeof(E),
-                         cudaMemcpyHostToDevice, st));
+      CK(ctx->stager.h2d(st, dsh[k].as<E>() + (uint64_t)i * nc, packets[i] + kPacketHeader + c0 * sizeof(E), nc * sizeof(E)));
     RET(recover_p_on<F>(ctx, st, dsh[k].as<E>(), nc, n, nc, 1, d_basis, dout[k].as<E>()));
-    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0, dout[k].p, nc * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 extern "C" int sclgpu_fp61_shamir_share_packets(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return share_packets_host<F61>(c, s, N, t, n, seed, fb, p); }
@@ -1531,13 +1546,14 @@ static int recover_p_array_host(sclgpu_ctx* ctx, const void* shares, uint64_t N,
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    if (n) CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n * W, nc * n * W * sizeof(E), cudaMemcpyHostToDevice, st));
+    if (n) CK(ctx->stager.h2d(st, dsh[k].p, hs + c0 * n * W, nc * n * W * sizeof(E)));
     RET(transpose_wide_on<E>(ctx, st, dsh[k].as<E>(), nc, n, W, dpm[k].as<E>()));
     RET(recover_p_on<F>(ctx, st, dpm[k].as<E>(), nc * W, n, nc * W, 1, d_basis, dout[k].as<E>()));
-    CK(cudaMemcpyAsync(ho + c0 * W, dout[k].p, nc * W * sizeof(E), cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0 * W, dout[k].p, nc * W * sizeof(E)));
   }
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
 extern "C" int sclgpu_fp61_recover_p_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, uint64_t* o) { return recover_p_array_host<F61>(c, s, N, W, n, o); }
@@ -1609,14 +1625,16 @@ static int recover_d_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
     const uint64_t nc = std::min(chunk, N - c0);
     cudaStream_t st = ctx->pipe[k];
-    CK(cudaMemcpyAsync(dsh[k].p, hs + c0 * n_given, nc * n_given * sizeof(E), cudaMemcpyHostToDevice, st));
+    CK(ctx->stager.h2d(st, dsh[k].p, hs + c0 * n_given, nc * n_given * sizeof(E)));
     RET(recover_d_on<F>(ctx, st, dsh[k].as<E>(), nc, 1, n_given, m, n_checks, d_mat, dout[k].as<E>(),
                         derr[k].as<uint8_t>()));
-    CK(cudaMemcpyAsync(ho + c0, dout[k].p, nc * sizeof(E), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(err + c0, derr[k].p, nc, cudaMemcpyDeviceToHost, st));
+    CK(ctx->stager.d2h(st, ho + c0, dout[k].p, nc * sizeof(E)));
+    CK(ctx->stager.d2h(st, err + c0, derr[k].p, nc));
   }
   CK(cudaStreamSynchronize(ctx->pipe[1]));
-  return finish_detect(ctx, ctx->pipe[0], n_detected);
+  const int rc = finish_detect(ctx, ctx->pipe[0], n_detected);
+  CK(ctx->stager.drain());
+  return rc;
 }
 extern "C" int sclgpu_fp61_recover_d(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F61>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
 extern "C" int sclgpu_fp127_recover_d(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F127>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
@@ -1689,8 +1707,8 @@ static int recover_c_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
                                  n_failed);
   if (rc != SCLGPU_OK && rc != SCLGPU_ECORRECT) return rc;
   if (N) {
-    CK(cudaMemcpyAsync(f, df, (size_t)N * np * sizeof(E), cudaMemcpyDeviceToHost, hop.st));
-    CK(cudaMemcpyAsync(e, de, (size_t)N * (t + 1) * sizeof(E), cudaMemcpyDeviceToHost, hop.st));
+    CK(ctx->stager.d2h(hop.st, f, df, (size_t)N * np * sizeof(E)));
+    CK(ctx->stager.d2h(hop.st, e, de, (size_t)N * (t + 1) * sizeof(E)));
     RET(hop.down(status, dst, (size_t)N));
   }
   return rc;

@@ -666,6 +666,36 @@ def test_share_array_errors_and_empty(ctx, pkg, port):
     assert ctx.recover_p_array(61, out).shape == (0, 2)
 
 
+# ------------------------------------------------------------------ pageable host buffers (std::vector-backed SCL containers)
+def test_pageable_host_buffers_staged(ctx, pkg, orc):
+    """Host entry points on ordinary (pageable) numpy memory large enough for the pinned-ring stager
+    (csrc/host_stage.h), against the oracle and against the same calls on pinned buffers."""
+    N, t, n = 1 << 19, 3, 9                       # 36 MiB of shares: several ring pieces, ragged tail
+    N -= 12345
+    secrets = orc.vector_random(61, "secrets", 0, N)
+    want = orc.shamir_share(61, secrets, t, n, "pageable", 99)
+    got = ctx.shamir_share(61, secrets, t, n, "pageable", 99)          # numpy in, numpy out: pageable both ways
+    assert np.array_equal(got, want)
+    assert np.array_equal(ctx.recover_p(61, got), secrets)
+    out, err, nd = ctx.recover_d(61, got, t)
+    assert nd == 0 and np.array_equal(out, secrets) and not err.any()
+    pinned = ctx.host_alloc(got.nbytes).view(np.uint64).reshape(got.shape)
+    lib = pkg.binding.load()
+    assert lib.sclgpu_fp61_shamir_share(ctx._ctx, secrets.ctypes.data, N, t, n, pkg.api.seed16("pageable"), 99, pinned.ctypes.data) == 0
+    assert np.array_equal(pinned, want)
+    ctx.host_free(pinned)
+    # Fp127, packets and the vector ops take the same route
+    s127 = orc.vector_random(127, "secrets127", 0, 1 << 18)
+    g127 = ctx.shamir_share(127, s127, 2, 5, "pageable", 7)
+    assert np.array_equal(g127, orc.shamir_share(127, s127, 2, 5, "pageable", 7))
+    assert np.array_equal(ctx.recover_p(127, g127), s127)
+    a = orc.vector_random(61, "a", 0, (1 << 21) + 77)
+    b = orc.vector_random(61, "b", 0, (1 << 21) + 77)
+    assert np.array_equal(ctx.beaver(61, a, b, a, b, a), orc.beaver(61, a, b, a, b, a))
+    assert np.array_equal(ctx.random(61, "pageable", 5, (1 << 22) + 3), orc.vector_random(61, "pageable", 5, (1 << 22) + 3))
+    assert np.array_equal(ctx.prg_expand("pageable", 11, (40 << 20) + 5), orc.prg_next("pageable", 11, (40 << 20) + 5))
+
+
 # ------------------------------------------------------------------ additive sharing (SURVEY 8f.2)
 def test_additive_golden(ctx, port, golden):
     for c in golden["additive"]:
