@@ -365,6 +365,63 @@ k_share61(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t0,
   }
 }
 
+static constexpr uint8_t kRecoverCPending = 2;
+static constexpr uint32_t kRecoverCMaxT = 10;  // 3t+1 <= 32
+
+// Error-free sharings, one thread each.  If all np = 3t+1 points lie on one polynomial f of degree <= t, every
+// Berlekamp-Welch system with e >= 1 has many solutions (E any monic polynomial of degree e, Q = f*E), so the
+// reference's solveLinearSystem rejects e = t..1 (matrix.h:741-764, unique solutions only) and accepts e = 0, whose
+// unique solution is Q = f, E = 1: the result is the interpolant's coefficients and the error locator (1).
+// check: 2t Lagrange rows (nodes a_0..a_t evaluated at a_{t+1}..a_{3t}), coef: the (t+1) x (t+1) matrix taking the
+// first t+1 shares to f's coefficients.  Sharings that fail a check are listed in `pending` for k_recover_c.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_recover_c_clean(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i, uint64_t stride_j,
+                  uint32_t t, const typename F::E* __restrict__ check, const typename F::E* __restrict__ coef,
+                  typename F::E* __restrict__ f_out, typename F::E* __restrict__ e_out,
+                  uint8_t* __restrict__ status, uint32_t* __restrict__ pending,
+                  unsigned long long* __restrict__ n_pending) {
+  typedef typename F::E E;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  E* sm = reinterpret_cast<E*>(dyn_smem);
+  const uint32_t m = t + 1u, np = 3u * t + 1u, n_rows = 3u * t + 1u;  // 2t check rows, then t+1 coefficient rows
+  for (uint32_t i = threadIdx.x; i < n_rows * m; i += blockDim.x) sm[i] = i < 2u * t * m ? check[i] : coef[i - 2u * t * m];
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
+    const E* src = in + j * stride_j;
+    E s[kRecoverCMaxT + 1];
+#pragma unroll
+    for (uint32_t k = 0; k <= kRecoverCMaxT; ++k) s[k] = k < m ? src[(uint64_t)k * stride_i] : F::zero();
+    bool clean = true;
+    E* fo = f_out + j * np;
+    for (uint32_t r = 0; r < n_rows; ++r) {
+      const E* row = sm + r * m;
+      typename F::Acc acc = F::acc_zero();
+#pragma unroll
+      for (uint32_t k = 0; k <= kRecoverCMaxT; ++k)
+        if (k < m) F::mac(acc, s[k], row[k]);  // m <= 11 terms: no fold needed
+      const E y = F::acc_reduce(acc);
+      if (r < 2u * t) {
+        clean = clean && F::eq(y, src[(uint64_t)(m + r) * stride_i]);
+      } else if (clean) {
+        fo[r - 2u * t] = y;
+      }
+      if (r + 1u == 2u * t && !clean) break;
+    }
+    if (clean) {
+      for (uint32_t k = m; k < np; ++k) fo[k] = F::zero();
+      E* eo = e_out + j * (uint64_t)m;
+      eo[0] = F::one();
+      for (uint32_t k = 1; k < m; ++k) eo[k] = F::zero();
+      status[j] = 0;
+    } else {
+      status[j] = kRecoverCPending;
+      pending[atomicAdd(n_pending, 1ull)] = (uint32_t)j;  // compacted: the elimination kernel stays load-balanced
+    }
+  }
+}
+
 // ================================================================ shamirRecoverC
 // include/scl/ss/shamir.h:203-258 (Berlekamp-Welch) + solveLinearSystem (matrix.h:812-828) +
 // Polynomial::divide (poly.h:262-278).  One WARP per sharing, lane i owns row i of the
@@ -381,7 +438,8 @@ __global__ void __launch_bounds__(256)
 k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i, uint64_t stride_j,
             uint32_t t, const typename F::E* __restrict__ alphas, typename F::E* __restrict__ f_out,
             typename F::E* __restrict__ e_out, uint8_t* __restrict__ status,
-            unsigned long long* __restrict__ n_failed) {
+            unsigned long long* __restrict__ n_failed, const uint32_t* __restrict__ pending,
+            const unsigned long long* __restrict__ n_pending) {
   typedef typename F::E E;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const uint32_t np = 3u * t + 1u, cols = np + 1u;
@@ -397,7 +455,9 @@ k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i,
   const E a_i = row ? alphas[lane] : F::zero();
   unsigned long long local_failed = 0;
 
-  for (uint64_t j = warp; j < N; j += warps) {
+  const uint64_t n_work = pending ? *n_pending : N;   // with a list: only what k_recover_c_clean left over
+  for (uint64_t q = warp; q < n_work; q += warps) {
+    const uint64_t j = pending ? pending[q] : q;
     const E s_i = row ? in[(uint64_t)lane * stride_i + j * stride_j] : F::zero();
     int e = (int)t;
     for (;; --e) {

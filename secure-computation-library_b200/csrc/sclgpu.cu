@@ -1659,12 +1659,67 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   CK(dal.alloc(np * sizeof(E)));
   CK(cudaMemcpyAsync(dal.p, al.data(), np * sizeof(E), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
+  // Error-free sharings first (k_recover_c_clean, one thread each); only the others need the elimination.
+  // Needs pairwise distinct nodes (else the reference's own behaviour is the e = 0 oddity handled by k_recover_c).
+  bool distinct = true;
+  for (uint32_t i = 0; i < np && distinct; ++i)
+    for (uint32_t j = i + 1; j < np; ++j)
+      if (F::eq(al[i], al[j])) distinct = false;
+  struct AsyncBuf {  // freed in stream order after the kernels that use it
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit AsyncBuf(cudaStream_t s) : st(s) {}
+    ~AsyncBuf() {
+      if (p) cudaFreeAsync(p, st);
+    }
+  } dpending(st);
+  DevBuf dcoef;
+  uint32_t* d_pending = nullptr;
+  unsigned long long* d_n_pending = nullptr;
+  std::vector<E> coef;
+  if (distinct && t <= kRecoverCMaxT && N < (1ull << 32) && getenv("SCLGPU_RECOVER_C_FULL") == nullptr) {
+    const uint32_t m = t + 1;
+    const E* d_check = nullptr;
+    if (t > 0) RET(basis_rows<F>(ctx, st, al.data(), m, al.data() + m, 2 * t, &d_check));
+    // coef[k][i] = coefficient of x^k in the Lagrange basis polynomial of node a_i among a_0..a_t
+    coef.assign((size_t)m * m, F::zero());
+    std::vector<E> poly(m + 1);
+    for (uint32_t i = 0; i < m; ++i) {
+      std::fill(poly.begin(), poly.end(), F::zero());
+      poly[0] = F::one();
+      uint32_t deg = 0;
+      E den = F::one();
+      for (uint32_t j = 0; j < m; ++j) {
+        if (j == i) continue;
+        for (uint32_t d = deg + 1; d >= 1; --d) poly[d] = F::sub(poly[d - 1], F::mul(al[j], poly[d]));
+        poly[0] = F::neg(F::mul(al[j], poly[0]));
+        ++deg;
+        den = F::mul(den, F::sub(al[i], al[j]));
+      }
+      const E inv = F::inv(den);
+      for (uint32_t k = 0; k < m; ++k) coef[(size_t)k * m + i] = F::mul(poly[k], inv);
+    }
+    CK(dcoef.alloc(coef.size() * sizeof(E)));
+    CK(cudaMemcpyAsync(dcoef.p, coef.data(), coef.size() * sizeof(E), cudaMemcpyHostToDevice, st));
+    // stream-ordered scratch: stays cached in the device's pool between calls (a cudaMalloc / cudaFree pair
+    // would cost milliseconds and a device synchronisation per call)
+    void* pend = nullptr;
+    CK(cudaMallocAsync(&pend, N * sizeof(uint32_t) + sizeof(unsigned long long), st));
+    dpending.p = pend;
+    d_n_pending = static_cast<unsigned long long*>(pend);  // counter first (8-byte aligned), then the index list
+    d_pending = reinterpret_cast<uint32_t*>(d_n_pending + 1);
+    CK(cudaMemsetAsync(d_n_pending, 0, sizeof(unsigned long long), st));
+    const size_t csm = (size_t)(3 * t + 1) * m * sizeof(E);
+    k_recover_c_clean<F><<<grid_for(ctx, N, 256, 4), 256, csm, st>>>(d_shares, N, si, sj, t, d_check, dcoef.as<E>(), d_f,
+                                                                    d_e, d_status, d_pending, d_n_pending);
+    CKL();
+  }
   const int warps_per_cta = 8;
   const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 2 * np) * sizeof(E);
   CK(cudaFuncSetAttribute(k_recover_c<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<uint64_t>((N + warps_per_cta - 1) / warps_per_cta, (uint64_t)ctx->sm_count * 4);
   k_recover_c<F><<<grid, 32 * warps_per_cta, smem, st>>>(d_shares, N, si, sj, t, dal.as<E>(), d_f, d_e, d_status,
-                                                         ctx->d_count);
+                                                         ctx->d_count, d_pending, d_n_pending);
   CKL();
   unsigned long long bad = 0;
   CK(cudaMemcpyAsync(&bad, ctx->d_count, sizeof(bad), cudaMemcpyDeviceToHost, st));

@@ -24,6 +24,16 @@ for field, W, t, n, N in [(61, 2, 15, 32, 1500), (61, 4, 2, 5, 301), (127, 2, 7,
     sh = ctx.shamir_share_array(field, sec, t, n, "knobs", 5)
     assert np.array_equal(sh, port.shamir_share_array(field, sec, t, n, "knobs", 5)), ("share_array", field, W, t, n)
     assert np.array_equal(ctx.recover_p_array(field, sh), sec), ("recover_p_array", field, W, n)
+for field, n, N in [(61, 16, 600), (127, 7, 200)]:   # shamirRecoverC: 0..t corrupted shares per sharing
+    t = (n - 1) // 3
+    sec = port.vector_random(field, "secrets", 0, N)
+    sh = port.shamir_share(field, sec, t, n, "rc", 3).copy()
+    flat = sh.reshape(N, n, -1)
+    for j in range(N):
+        for i in range(j % (t + 1)):
+            flat[j, (5 * i + j) % (3 * t + 1), 0] ^= np.uint64(1 + j)
+    g, w = ctx.recover_c(field, sh), port.recover_c(field, sh)
+    assert all(np.array_equal(a, b) for a, b in zip(g[:3], w[:3])) and g[3] == w[3] == 0, ("recover_c", field, n)
 for field, rows, inner, cols in [(61, 300, 520, 70), (61, 129, 4100, 33), (61, 257, 130, 257), (127, 130, 520, 40), (127, 64, 2100, 20)]:
     shp = () if field == 61 else (2,)
     A = port.vector_random(field, "mat A", 0, rows * inner).reshape((rows, inner) + shp)

@@ -757,10 +757,12 @@ def test_share_kernel_paths_vs_oracle(tc):
     assert r.returncode == 0 and "TC_CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC"])
+@pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC",
+                                  "SCLGPU_RECOVER_C_FULL", "SCLGPU_NO_KNOB"])
 def test_selectable_kernels_vs_oracle(knob):
     """tests/knob_check.py with one kernel-selection knob set: the first GEMM form, the
-    integer-pipe GEMM, the integer-pipe reconstruction kernels, the staged share path."""
+    integer-pipe GEMM, the integer-pipe reconstruction kernels, the staged share path, Berlekamp-Welch without the
+    error-free fast path; SCLGPU_NO_KNOB is the same sweep on the defaults."""
     import os
     import subprocess
     import sys

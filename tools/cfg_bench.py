@@ -72,6 +72,12 @@ r = {"field": 61, "n": nc_, "t": tc_, "N": Nc}
 r["recover_c_ms"] = timeit(lambda: ctx.recover_c_dev(61, shc, Nc, nc_, fo, eo, sto, B.PARTY_MAJOR))
 r["ok"] = bool(torch.equal(fo[:, 0], sec)) and int(sto.sum().item()) == 0
 r["sharings_per_s"] = Nc / (r["recover_c_ms"] * 1e-3)
+shc[3, ::2] ^= 5   # undo: every sharing error-free (the k_recover_c_clean path alone)
+r["recover_c_error_free_ms"] = timeit(lambda: ctx.recover_c_dev(61, shc, Nc, nc_, fo, eo, sto, B.PARTY_MAJOR))
+r["ok_error_free"] = bool(torch.equal(fo[:, 0], sec)) and int(sto.sum().item()) == 0
+shc[3, ::64] ^= 5  # one sharing in 64 with a corrupted share
+r["recover_c_1_in_64_ms"] = timeit(lambda: ctx.recover_c_dev(61, shc, Nc, nc_, fo, eo, sto, B.PARTY_MAJOR))
+r["ok_1_in_64"] = bool(torch.equal(fo[:, 0], sec)) and int(sto.sum().item()) == 0
 res["recoverC_fp61_n16_t5_2^20"] = r
 del sec, shc, fo, eo, sto; torch.cuda.empty_cache()
 
