@@ -433,21 +433,23 @@ k_recover_c_clean(const typename F::E* __restrict__ in, uint64_t N, uint64_t str
 // lane, all lanes in parallel.  Then Q / E by long division, lanes over the divisor terms.
 // Outputs per sharing: f (np coefficients, zero padded), err (t+1, monic, zero padded),
 // status 1 where the reference throws "could not correct shares" (f, err zeroed).
+// quick != 0: first try the verified one-elimination shortcut described in the loop body.
 template <class F>
 __global__ void __launch_bounds__(256)
 k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i, uint64_t stride_j,
             uint32_t t, const typename F::E* __restrict__ alphas, typename F::E* __restrict__ f_out,
             typename F::E* __restrict__ e_out, uint8_t* __restrict__ status,
             unsigned long long* __restrict__ n_failed, const uint32_t* __restrict__ pending,
-            const unsigned long long* __restrict__ n_pending) {
+            const unsigned long long* __restrict__ n_pending, int quick) {
   typedef typename F::E E;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const uint32_t np = 3u * t + 1u, cols = np + 1u;
-  const uint32_t per_warp = np * cols + 2u * np;            // matrix, x, division remainder
+  const uint32_t per_warp = np * cols + 3u * np;            // matrix, x, division remainder, quotient
   const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   E* M = reinterpret_cast<E*>(dyn_smem) + (size_t)wib * per_warp;
   E* X = M + np * cols;
   E* R = X + np;
+  E* Qt = R + np;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const E minus1 = F::neg(F::one());
@@ -459,6 +461,106 @@ k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i,
   for (uint64_t q = warp; q < n_work; q += warps) {
     const uint64_t j = pending ? pending[q] : q;
     const E s_i = row ? in[(uint64_t)lane * stride_i + j * stride_j] : F::zero();
+    if (quick && t > 0) {
+      // ---- one elimination instead of up to t+1.  ANY solution (E, Q) of the e = t system gives the decoded
+      // polynomial f = Q / E when the word is within t errors of a codeword (Berlekamp-Welch).  So: rank-revealing
+      // fraction-free Gauss-Jordan without row exchanges, free unknowns := 0, divide, and VERIFY: if f has degree
+      // <= t and disagrees with the shares in d <= t places, unique decoding makes the reference's answer the
+      // unique solution of its e = d system (every e > d system has many solutions and is rejected), namely f and
+      // the locator prod_{bad i} (x - a_i) -- written here directly.  Anything else falls through to the
+      // reference's own sequence below.
+      if (row) {
+        E* mr = M + lane * cols;
+        E v = s_i;
+        for (uint32_t c = 0; c < t; ++c) {
+          mr[c] = v;
+          v = F::mul(v, a_i);
+        }
+        mr[np] = F::neg(v);
+        E u = minus1;
+        for (uint32_t c = t; c < np; ++c) {
+          mr[c] = u;
+          u = F::mul(u, a_i);
+        }
+        X[lane] = F::zero();
+      }
+      __syncwarp();
+      int my_col = -1;  // pivot column of this lane's row
+      for (uint32_t c = 0; c < np; ++c) {
+        const bool nz = row && my_col < 0 && !F::is_zero(M[lane * cols + c]);
+        const unsigned mask = __ballot_sync(0xffffffffu, nz);
+        if (mask == 0) continue;  // free unknown
+        const uint32_t piv = (uint32_t)__ffs(mask) - 1u;
+        if (lane == piv) my_col = (int)c;
+        const E p = M[piv * cols + c];
+        if (row && lane != piv) {
+          E* mr = M + lane * cols;
+          const E f = mr[c];
+          if (!F::is_zero(f)) {
+            for (uint32_t q = c + 1; q < cols; ++q) mr[q] = F::sub(F::mul(mr[q], p), F::mul(f, M[piv * cols + q]));
+            mr[c] = F::zero();
+            if (my_col >= 0) mr[my_col] = F::mul(mr[my_col], p);
+          }
+        }
+        __syncwarp();
+      }
+      // rows without a pivot read 0 = b: consistent iff b == 0
+      bool good = __ballot_sync(0xffffffffu, row && my_col < 0 && !F::is_zero(M[lane * cols + np])) == 0;
+      if (good) {
+        if (row && my_col >= 0) X[my_col] = F::mul(M[lane * cols + np], F::inv(M[lane * cols + my_col]));
+        __syncwarp();
+        const uint32_t qn = np - t;  // Q = x[t..np-1], E = (x_0..x_{t-1}, 1)
+        if (lane < qn) R[lane] = X[t + lane];
+        if (lane < np) Qt[lane] = F::zero();
+        __syncwarp();
+        const unsigned nzq = __ballot_sync(0xffffffffu, lane < qn && !F::is_zero(R[lane]));
+        const uint32_t deg = nzq ? 31u - (uint32_t)__clz(nzq) : 0u;
+        if (deg >= t) {
+          for (int d = (int)deg; d >= (int)t; --d) {
+            const E c = R[d];
+            __syncwarp();
+            if (lane < t) R[d - t + lane] = F::sub(R[d - t + lane], F::mul(c, X[lane]));
+            if (lane == 0) {
+              Qt[d - t] = c;
+              R[d] = F::zero();
+            }
+            __syncwarp();
+          }
+          good = __ballot_sync(0xffffffffu, lane < t && !F::is_zero(R[lane])) == 0;
+        } else {
+          good = nzq == 0;
+        }
+        // f = Qt has degree <= deg - t <= t by construction; count the disagreements with the shares
+        E y = F::zero();
+        if (row) {
+          for (int k = (int)t; k >= 0; --k) y = F::add(F::mul(y, a_i), Qt[k]);
+        }
+        const unsigned badm = __ballot_sync(0xffffffffu, row && !F::eq(y, s_i));
+        const uint32_t d_err = (uint32_t)__popc(badm);
+        if (good && d_err <= t) {
+          E* fo = f_out + j * np;
+          E* eo = e_out + j * (uint64_t)(t + 1);
+          if (lane < np) fo[lane] = Qt[lane];
+          // locator, built in R by lane 0: prod over the bad positions of (x - a_i), low coefficient first
+          if (lane == 0) {
+            R[0] = F::one();
+            uint32_t dg = 0;
+            for (unsigned mm = badm; mm; mm &= mm - 1u) {
+              const E a = alphas[__ffs(mm) - 1];
+              R[dg + 1] = R[dg];
+              for (uint32_t q = dg; q >= 1; --q) R[q] = F::sub(R[q - 1], F::mul(a, R[q]));
+              R[0] = F::neg(F::mul(a, R[0]));
+              ++dg;
+            }
+            for (uint32_t q = 0; q <= t; ++q) eo[q] = q <= dg ? R[q] : F::zero();
+            status[j] = 0;
+          }
+          __syncwarp();
+          continue;
+        }
+      }
+      __syncwarp();
+    }
     int e = (int)t;
     for (;; --e) {
       if (row) {

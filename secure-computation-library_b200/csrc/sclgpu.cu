@@ -1715,11 +1715,12 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     CKL();
   }
   const int warps_per_cta = 8;
-  const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 2 * np) * sizeof(E);
+  const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 3 * np) * sizeof(E);
+  const int quick = (distinct && getenv("SCLGPU_RECOVER_C_FULL") == nullptr) ? 1 : 0;
   CK(cudaFuncSetAttribute(k_recover_c<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<uint64_t>((N + warps_per_cta - 1) / warps_per_cta, (uint64_t)ctx->sm_count * 4);
   k_recover_c<F><<<grid, 32 * warps_per_cta, smem, st>>>(d_shares, N, si, sj, t, dal.as<E>(), d_f, d_e, d_status,
-                                                         ctx->d_count, d_pending, d_n_pending);
+                                                         ctx->d_count, d_pending, d_n_pending, quick);
   CKL();
   unsigned long long bad = 0;
   CK(cudaMemcpyAsync(&bad, ctx->d_count, sizeof(bad), cudaMemcpyDeviceToHost, st));
