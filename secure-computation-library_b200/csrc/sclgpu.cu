@@ -1097,6 +1097,7 @@ static int share_array_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, u
   if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
   int rc;
   if (!array_args_ok(ctx, N, W, n, rc)) return rc;
+  if (W == 1) return share_dev<F>(ctx, d_secrets, N, t, n, seed, first_block, d_shares, layout);  // plain shamirSecretShare
   CK(cudaSetDevice(ctx->device));
   if (N == 0 || n == 0) return SCLGPU_OK;
   const AesKey key = aes_expand(seed);
@@ -1125,6 +1126,7 @@ static int share_array_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, ui
   if (!ctx || !seed || ((!secrets || !shares) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   int rc;
   if (!array_args_ok(ctx, N, W, n, rc)) return rc;
+  if (W == 1) return share_host<F>(ctx, secrets, N, t, n, seed, first_block, shares);  // plain shamirSecretShare
   CK(cudaSetDevice(ctx->device));
   if (N == 0 || n == 0) return SCLGPU_OK;
   const AesKey key = aes_expand(seed);
