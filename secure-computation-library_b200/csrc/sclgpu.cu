@@ -301,6 +301,23 @@ struct DevBuf {
   T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Stream-ordered scratch of the device-pointer entry points: allocated and freed in stream order from the
+// device's default pool, whose release threshold sclgpu_init raises, so that repeated calls reuse the same memory
+// and no call pays a cudaMalloc / cudaFree pair (milliseconds, and a device-wide synchronisation).
+struct StreamBuf {
+  void* p = nullptr;
+  cudaStream_t st;
+  explicit StreamBuf(cudaStream_t s) : st(s) {}
+  StreamBuf(const StreamBuf&) = delete;
+  StreamBuf& operator=(const StreamBuf&) = delete;
+  ~StreamBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
 // Scratch from the context's pool: same interface as DevBuf, nothing freed on return.  A host entry
 // point opens a PoolScope (calls on one context are serialised and end synchronised, so buffers handed
 // out in one call are free again in the next).
@@ -572,7 +589,7 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   uint64_t chunk = (1ull << 30) / ((uint64_t)(t + 1) * sizeof(E));
   if (chunk < 1024) chunk = 1024;
   if (chunk > N) chunk = N;
-  DevBuf planes;
+  StreamBuf planes(st);
   CK(planes.alloc(chunk * (uint64_t)(t + 1) * sizeof(E)));
   RET(aes_opt_in(ctx, k_expand_coeffs<F>));
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
@@ -582,8 +599,7 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
     CKL();
     RET(share_coeffs_on<F>(ctx, st, planes.as<E>(), nc, t, n, d_out + c0 * sj, si, sj));
   }
-  CK(cudaStreamSynchronize(st));  // planes is freed on return
-  return SCLGPU_OK;
+  return SCLGPU_OK;  // planes goes back to the pool in stream order
 }
 
 template <class E>
@@ -941,7 +957,7 @@ static int share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_
   const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
   uint64_t chunk = std::max<uint64_t>((512ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
   if (chunk > N) chunk = N;
-  DevBuf tmp;
+  StreamBuf tmp(ctx->stream);
   CK(tmp.alloc(chunk * n * sizeof(E)));
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
     const uint64_t nc = std::min(chunk, N - c0);
@@ -949,8 +965,7 @@ static int share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_
                             tmp.as<E>(), nc, 1));
     RET(transpose_on<E>(ctx, ctx->stream, tmp.as<E>(), n, nc, out + c0 * n));
   }
-  CK(cudaStreamSynchronize(ctx->stream));  // tmp is freed on return
-  return SCLGPU_OK;
+  return SCLGPU_OK;  // tmp goes back to the pool in stream order
 }
 
 // Host pipeline: two streams, chunked; H2D secrets -> share (party-major) ->
@@ -1105,7 +1120,7 @@ static int share_array_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, u
   const bool sm = layout == SCLGPU_SECRET_MAJOR;
   const bool fused = share_array_fused<F>(W, t, n);
   const uint64_t chunk = (fused && !sm) ? N : share_array_chunk_len<F>(N, W, t, n, 512ull << 20);
-  DevBuf planes, tmp;
+  StreamBuf planes(ctx->stream), tmp(ctx->stream);
   if (!fused) CK(planes.alloc(chunk * W * (uint64_t)(t + 1) * sizeof(E)));
   if (sm) CK(tmp.alloc(chunk * W * (uint64_t)n * sizeof(E)));
   const E* sec = reinterpret_cast<const E*>(d_secrets);
@@ -1115,8 +1130,7 @@ static int share_array_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, u
     RET(share_array_chunk<F>(ctx, ctx->stream, key, first_block + c0 * B, sec + c0 * W, nc, W, t, n, planes.as<E>(),
                              tmp.as<E>(), sm ? out + c0 * n * W : out + c0 * W, N * W, sm));
   }
-  CK(cudaStreamSynchronize(ctx->stream));  // scratch is freed on return
-  return SCLGPU_OK;
+  return SCLGPU_OK;  // scratch goes back to the pool in stream order
 }
 
 template <class F>
@@ -1510,14 +1524,13 @@ static int recover_p_array_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N
     return recover_p_on<F>(ctx, ctx->stream, in, N * W, n, N * W, 1, d_basis, out);
   uint64_t chunk = std::max<uint64_t>((512ull << 20) / ((uint64_t)n * W * sizeof(E)), 256);
   chunk = std::min(chunk, N);
-  DevBuf tmp;
+  StreamBuf tmp(ctx->stream);
   CK(tmp.alloc(chunk * n * W * sizeof(E)));
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
     const uint64_t nc = std::min(chunk, N - c0);
     RET(transpose_wide_on<E>(ctx, ctx->stream, in + c0 * n * W, nc, n, W, tmp.as<E>()));
     RET(recover_p_on<F>(ctx, ctx->stream, tmp.as<E>(), nc * W, n, nc * W, 1, d_basis, out + c0 * W));
   }
-  CK(cudaStreamSynchronize(ctx->stream));
   return SCLGPU_OK;
 }
 
@@ -1667,14 +1680,7 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   for (uint32_t i = 0; i < np && distinct; ++i)
     for (uint32_t j = i + 1; j < np; ++j)
       if (F::eq(al[i], al[j])) distinct = false;
-  struct AsyncBuf {  // freed in stream order after the kernels that use it
-    void* p = nullptr;
-    cudaStream_t st;
-    explicit AsyncBuf(cudaStream_t s) : st(s) {}
-    ~AsyncBuf() {
-      if (p) cudaFreeAsync(p, st);
-    }
-  } dpending(st);
+  StreamBuf dpending(st);
   DevBuf dcoef;
   uint32_t* d_pending = nullptr;
   unsigned long long* d_n_pending = nullptr;
@@ -1705,10 +1711,8 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     CK(cudaMemcpyAsync(dcoef.p, coef.data(), coef.size() * sizeof(E), cudaMemcpyHostToDevice, st));
     // stream-ordered scratch: stays cached in the device's pool between calls (a cudaMalloc / cudaFree pair
     // would cost milliseconds and a device synchronisation per call)
-    void* pend = nullptr;
-    CK(cudaMallocAsync(&pend, N * sizeof(uint32_t) + sizeof(unsigned long long), st));
-    dpending.p = pend;
-    d_n_pending = static_cast<unsigned long long*>(pend);  // counter first (8-byte aligned), then the index list
+    CK(dpending.alloc(N * sizeof(uint32_t) + sizeof(unsigned long long)));
+    d_n_pending = dpending.as<unsigned long long>();  // counter first (8-byte aligned), then the index list
     d_pending = reinterpret_cast<uint32_t*>(d_n_pending + 1);
     CK(cudaMemsetAsync(d_n_pending, 0, sizeof(unsigned long long), st));
     const size_t csm = (size_t)(3 * t + 1) * m * sizeof(E);

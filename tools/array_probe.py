@@ -26,3 +26,13 @@ for rnd in range(2):
     print("plain  ", timeit(lambda: ctx.shamir_share_dev(61, sec, N, t, n, "x", 0, sh, B.PARTY_MAJOR)))
     for W in (2, 4, 8):
         print("array W=%d" % W, timeit(lambda: ctx.shamir_share_array_dev(61, sec, N // W, W, t, n, "x", 0, sh, B.PARTY_MAJOR)))
+
+# secret-major ([N][n][W], SCL's layout): chunked share + wide transposition
+W = 2
+sm = torch.empty((N // W) * n * W, dtype=torch.int64, device="cuda")
+out = torch.empty(N, dtype=torch.int64, device="cuda")
+for lg in (22, 25):
+    Np = 1 << lg
+    a = timeit(lambda: ctx.shamir_share_array_dev(61, sec, Np, W, t, n, "x", 0, sm, B.SECRET_MAJOR), reps=3)
+    b = timeit(lambda: ctx.recover_p_array_dev(61, sm, Np, W, n, out, B.SECRET_MAJOR), reps=3)
+    print(f"secret-major 2^{lg} pairs: share {a:.2f} ms, recover {b:.2f} ms, ok={bool(torch.equal(out[:Np * W], sec[:Np * W]))}")
