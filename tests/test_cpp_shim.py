@@ -55,3 +55,13 @@ def test_plain_c_consumer_of_the_abi():
     r = subprocess.run([C_BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "C_EXAMPLE_OK" in r.stdout, r.stdout + r.stderr
     assert "error detected during recovery" in r.stdout
+
+
+def test_copy_team_of_the_pageable_stager():
+    """csrc/host_stage.h: the copy-thread team (non-temporal stores, 0..7 helpers) on the CPU -- thousands of
+    back-to-back copies of random sizes and alignments, every byte and both neighbours checked."""
+    exe = os.path.join(REPO, "tests", "cpp", "_build", "test_copy_team")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_build/test_copy_team not built (run __graft_entry__.build())")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "COPY_TEAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
