@@ -449,6 +449,42 @@ def test_full_size_c2_properties(ctx, pkg, orc):
     assert torch.equal(d_sum, d_want)
 
 
+def test_full_size_array_sharing_properties(ctx, pkg, port):
+    """Pedersen's sharing step at C2's volume: 2^25 pairs (math::Array<Fp61, 2>), n=32, t=15 = 2^26 component
+    polynomials, 16 GiB of shares.  (i) share -> recoverP returns every pair in both layouts, (ii) a prefix and two
+    far-away slices equal the (seekable) oracle bit for bit, (iii) party-major and secret-major hold the same shares."""
+    import torch
+
+    ctx.use_torch_stream()
+    B = pkg.binding
+    W, t, n, N = 2, 15, 32, 1 << 25
+    blocks = pkg.api.blocks_per_array_share_call(61, W, t)
+    d_sec = torch.empty((N, W), dtype=torch.int64, device="cuda")
+    ctx.random_dev(61, "pairs", 0, N * W, d_sec)
+    d_pm = torch.empty((n, N, W), dtype=torch.int64, device="cuda")
+    d_out = torch.empty((N, W), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_array_dev(61, d_sec, N, W, t, n, "pedersen", 0, d_pm, B.PARTY_MAJOR)
+    ctx.recover_p_array_dev(61, d_pm, N, W, n, d_out, B.PARTY_MAJOR)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, d_sec)
+    K = 1024
+    for lo in (0, N // 2 - 3, N - K):
+        sec_h = d_sec[lo:lo + K].cpu().numpy().view(np.uint64)
+        want = port.shamir_share_array(61, sec_h, t, n, "pedersen", lo * blocks)          # [K, n, W]
+        got = d_pm[:, lo:lo + K, :].permute(1, 0, 2).contiguous().cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, want), lo
+    # secret-major = SCL's own layout: same shares, and it reconstructs
+    Nh = N // 2                                                                             # 8 GiB more
+    d_sm = torch.empty((Nh, n, W), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_array_dev(61, d_sec, Nh, W, t, n, "pedersen", 0, d_sm, B.SECRET_MAJOR)
+    d_out.zero_()
+    ctx.recover_p_array_dev(61, d_sm, Nh, W, n, d_out, B.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out[:Nh], d_sec[:Nh])
+    for lo in (0, Nh - 4096):
+        assert torch.equal(d_sm[lo:lo + 4096], d_pm[:, lo:lo + 4096, :].permute(1, 0, 2))
+
+
 # ------------------------------------------------------------------ shamirRecoverC (SURVEY 8f.3)
 def test_recover_c_golden(ctx, port, golden):
     for c in golden["recover_c"]:
