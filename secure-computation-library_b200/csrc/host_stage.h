@@ -178,8 +178,8 @@ class HostStager {
   }
 
   cudaError_t h2d(cudaStream_t st, void* dev, const void* host, size_t bytes) {
-    if (bytes < kMinStaged || !pageable(host)) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
-    cudaError_t e = prepare();
+    if (bytes < kMinStaged || !pageable(host) || !ready()) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaSuccess;
     for (size_t off = 0; off < bytes && e == cudaSuccess; off += kPiece) {
       const size_t len = bytes - off < kPiece ? bytes - off : kPiece;
       const int s = next_slot();
@@ -194,8 +194,8 @@ class HostStager {
   }
 
   cudaError_t d2h(cudaStream_t st, void* host, const void* dev, size_t bytes) {
-    if (bytes < kMinStaged || !pageable(host)) return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = prepare();
+    if (bytes < kMinStaged || !pageable(host) || !ready()) return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
     for (size_t off = 0; off < bytes && e == cudaSuccess; off += kPiece) {
       const size_t len = bytes - off < kPiece ? bytes - off : kPiece;
       const int s = next_slot();
@@ -253,6 +253,16 @@ class HostStager {
     next_ = (next_ + 1) % kSlots;
     return s;
   }
+  // ring, events, callback stream and copy team exist (created on first use); if they cannot be created -- e.g. no
+  // pinned memory left -- the transfer is left to the driver's own pageable path
+  bool ready() {
+    if (hs_) return true;
+    if (failed_) return false;
+    if (prepare() == cudaSuccess) return true;
+    cudaGetLastError();
+    failed_ = true;
+    return false;
+  }
   cudaError_t prepare() {
     if (hs_) return cudaSuccess;
     cudaError_t e = cudaStreamCreateWithFlags(&hs_, cudaStreamNonBlocking);
@@ -275,6 +285,7 @@ class HostStager {
   void* slot_[kSlots] = {};
   cudaEvent_t mid_[kSlots] = {}, done_[kSlots] = {};
   int next_ = 0;
+  bool failed_ = false;
   CopyTeam* team_ = nullptr;
   std::deque<Task> tasks_;
 };
