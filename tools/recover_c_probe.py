@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""shamirRecoverC alone (Fp61, n=16, t=5, 2^20 sharings; every second / every 64th / no sharing with a corrupted
+share), for timing and for ncu.  Development tool."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as entry
+
+pkg = entry.load_package(); B = pkg.binding
+ctx = pkg.Context(0); ctx.use_torch_stream()
+N, n, t = 1 << 20, 16, 5
+sec = torch.empty(N, dtype=torch.int64, device="cuda")
+sh = torch.empty((n, N), dtype=torch.int64, device="cuda")
+ctx.random_dev(61, "secrets", 0, N, sec)
+ctx.shamir_share_dev(61, sec, N, t, n, "rc", 0, sh, B.PARTY_MAJOR)
+fo = torch.empty((N, 3 * t + 1), dtype=torch.int64, device="cuda")
+eo = torch.empty((N, t + 1), dtype=torch.int64, device="cuda")
+st = torch.empty(N, dtype=torch.uint8, device="cuda")
+
+def timeit(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+for every in (2, 64, 0):
+    if every: sh[3, ::every] ^= 5
+    ms = timeit(lambda: ctx.recover_c_dev(61, sh, N, n, fo, eo, st, B.PARTY_MAJOR))
+    ok = bool(torch.equal(fo[:, 0], sec)) and int(st.sum().item()) == 0
+    print(f"corrupted share in every {every or 'no'} sharing: {ms:.3f} ms  {N / ms / 1e3:.1f} M sharings/s  ok={ok}")
+    if every: sh[3, ::every] ^= 5
