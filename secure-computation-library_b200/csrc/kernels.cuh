@@ -497,7 +497,13 @@ k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i,
           E* mr = M + lane * cols;
           const E f = mr[c];
           if (!F::is_zero(f)) {
-            for (uint32_t q = c + 1; q < cols; ++q) mr[q] = F::sub(F::mul(mr[q], p), F::mul(f, M[piv * cols + q]));
+            const E nf = F::neg(f);  // row*p - f*pivot_row as ONE lazily reduced two-term sum
+            for (uint32_t q = c + 1; q < cols; ++q) {
+              typename F::Acc acc = F::acc_zero();
+              F::mac(acc, mr[q], p);
+              F::mac(acc, nf, M[piv * cols + q]);
+              mr[q] = F::acc_reduce(acc);
+            }
             mr[c] = F::zero();
             if (my_col >= 0) mr[my_col] = F::mul(mr[my_col], p);
           }
@@ -600,7 +606,13 @@ k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i,
           E* mr = M + lane * cols;
           const E f = mr[c];
           if (!F::is_zero(f)) {
-            for (uint32_t q = c + 1; q < cols; ++q) mr[q] = F::sub(F::mul(mr[q], p), F::mul(f, M[c * cols + q]));
+            const E nf = F::neg(f);
+            for (uint32_t q = c + 1; q < cols; ++q) {
+              typename F::Acc acc = F::acc_zero();
+              F::mac(acc, mr[q], p);
+              F::mac(acc, nf, M[c * cols + q]);
+              mr[q] = F::acc_reduce(acc);
+            }
             mr[c] = F::zero();
             if (lane < c) mr[lane] = F::mul(mr[lane], p);  // keep the diagonal of finished rows consistent
           }
