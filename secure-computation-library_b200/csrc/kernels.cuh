@@ -485,25 +485,31 @@ k_recover_c(const typename F::E* __restrict__ in, uint64_t N, uint64_t stride_i,
         X[lane] = F::zero();
       }
       __syncwarp();
+      // np <= 16: two lanes per row (lane and lane + 16), each updating every other column
+      const bool two = np <= 16u;
+      const uint32_t sub = two ? (lane >> 4) : 0u, rl = two ? (lane & 15u) : lane, qs = two ? 2u : 1u;
+      const bool row2 = rl < np;
       int my_col = -1;  // pivot column of this lane's row
       for (uint32_t c = 0; c < np; ++c) {
         const bool nz = row && my_col < 0 && !F::is_zero(M[lane * cols + c]);
         const unsigned mask = __ballot_sync(0xffffffffu, nz);
         if (mask == 0) continue;  // free unknown
         const uint32_t piv = (uint32_t)__ffs(mask) - 1u;
-        if (lane == piv) my_col = (int)c;
+        if (row2 && rl == piv) my_col = (int)c;
         const E p = M[piv * cols + c];
-        if (row && lane != piv) {
-          E* mr = M + lane * cols;
-          const E f = mr[c];
-          if (!F::is_zero(f)) {
-            const E nf = F::neg(f);  // row*p - f*pivot_row as ONE lazily reduced two-term sum
-            for (uint32_t q = c + 1; q < cols; ++q) {
-              typename F::Acc acc = F::acc_zero();
-              F::mac(acc, mr[q], p);
-              F::mac(acc, nf, M[piv * cols + q]);
-              mr[q] = F::acc_reduce(acc);
-            }
+        const bool upd = row2 && rl != piv;
+        E* mr = M + rl * cols;
+        const E f = upd ? mr[c] : F::zero();
+        __syncwarp();  // both lanes of a row have read column c before it is cleared
+        if (upd && !F::is_zero(f)) {
+          const E nf = F::neg(f);  // row*p - f*pivot_row as ONE lazily reduced two-term sum
+          for (uint32_t q = c + 1 + sub; q < cols; q += qs) {
+            typename F::Acc acc = F::acc_zero();
+            F::mac(acc, mr[q], p);
+            F::mac(acc, nf, M[piv * cols + q]);
+            mr[q] = F::acc_reduce(acc);
+          }
+          if (sub == 0) {
             mr[c] = F::zero();
             if (my_col >= 0) mr[my_col] = F::mul(mr[my_col], p);
           }
