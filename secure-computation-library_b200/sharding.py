@@ -58,6 +58,18 @@ def share_first_block(field: int, t: int, first_block: int, shard: Shard) -> int
     return first_block + shard.lo * blocks_per_share_call(field, t)
 
 
+def array_share_first_block(field: int, width: int, t: int, first_block: int, shard: Shard) -> int:
+    """PRG counter at which a rank starts its slice of a batch of array-valued sharings
+    (shamirSecretShare on math::Array<FF, width>: ceil((t+1)*width*byteSize/16) blocks per sharing)."""
+    bs = 8 if field == 61 else 16
+    return first_block + shard.lo * (((t + 1) * width * bs + 15) // 16)
+
+
+def additive_share_first_block(n: int, first_block: int, shard: Shard) -> int:
+    """PRG counter for a rank's slice of a batch additiveShare: n-1 FF::random draws (one block each) per secret."""
+    return first_block + shard.lo * (n - 1)
+
+
 def random_first_block(field: int, first_block: int, shard: Shard, one_per_block: bool = False) -> int:
     """PRG counter for a rank's slice of Vector::random / FF::random x n.
     For Fp61 Vector::random the slice must start on an even element (align=2)."""

@@ -103,6 +103,31 @@ def test_sharded_share_equals_unsharded_single_process(pkg, port):
         assert np.array_equal(np.concatenate(parts, axis=0), full)
 
 
+def test_sharded_array_and_additive_share_equal_unsharded(pkg, port):
+    """The same host arithmetic for array-valued sharings (ceil((t+1)*W*bs/16) blocks each) and additive
+    sharings (n-1 blocks each)."""
+    sh = pkg.sharding
+    for field, W, t, n, N in [(61, 2, 15, 32, 45), (61, 3, 2, 5, 33), (127, 2, 7, 16, 21)]:
+        es = () if field == 61 else (2,)
+        secrets = port.vector_random(field, "pairs", 0, N * W).reshape((N, W) + es)
+        full = port.shamir_share_array(field, secrets, t, n, "pedersen", 7)
+        for world in (2, 5):
+            parts = []
+            for r in range(world):
+                s = sh.shard_range(N, world, r)
+                parts.append(port.shamir_share_array(field, secrets[s.lo:s.hi], t, n, "pedersen",
+                                                     sh.array_share_first_block(field, W, t, 7, s)))
+            assert np.array_equal(np.concatenate(parts, axis=0), full)
+    for field, n, N in [(61, 4, 50), (127, 3, 17)]:
+        secrets = port.vector_random(field, "secrets", 0, N)
+        full = port.additive_share(field, secrets, n, "additive", 9)
+        parts = []
+        for r in range(3):
+            s = sh.shard_range(N, 3, r)
+            parts.append(port.additive_share(field, secrets[s.lo:s.hi], n, "additive", sh.additive_share_first_block(n, 9, s)))
+        assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
 def test_gloo_world2_sharded_share_recover():
     """world_size-2 gloo run of the sharded driver (tests/dist_worker.py)."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
