@@ -2,6 +2,7 @@
 oracle on rank 0:
   * batch-sharded shamirSecretShare / shamirRecoverP with the PRG counter offset per rank, secrets gathered;
   * recoverD error counts summed over ranks;
+  * batch-sharded sharing of math::Array<Fp61, 2> pairs (Pedersen's sharing step), shares gathered;
   * C5: row-sharded Fp61 mat-vec with the all-gather of the y slices (sharding.matvec_row_sharded).
 Run by tests/test_gpu_parity.py::test_multi_gpu_nccl when at least two GPUs are visible."""
 import os
@@ -55,6 +56,24 @@ def main():
         want[last.lo + 5, 20] ^= np.uint64(1)
         assert np.array_equal(got, want), "gathered shares differ from the one-PRG batch"
         assert total_bad == 1, total_bad
+
+    # ---- array-valued sharings (Pedersen's sharing step), batch-sharded the same way
+    W, Na = 2, 30011
+    sa = sh.shard_range(Na, world, rank)
+    d_pairs = torch.empty((sa.count, W), dtype=torch.int64, device=dev)
+    ctx.random_dev(61, "pairs", sa.lo * W // 2, sa.count * W, d_pairs)      # W even: every sharing starts on a block
+    d_ash = torch.empty((sa.count, n, W), dtype=torch.int64, device=dev)
+    ctx.shamir_share_array_dev(61, d_pairs, sa.count, W, t, n, "pedersen", sh.array_share_first_block(61, W, t, 5, sa),
+                               d_ash, B.SECRET_MAJOR)
+    d_arec = torch.empty((sa.count, W), dtype=torch.int64, device=dev)
+    ctx.recover_p_array_dev(61, d_ash, sa.count, W, n, d_arec, B.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    assert torch.equal(d_arec, d_pairs), "array sharing does not reconstruct on rank %d" % rank
+    g_ash = sh.gather_shards(d_ash.reshape(sa.count, n * W), sa, Na)
+    if rank == 0:
+        pairs = port.vector_random(61, "pairs", 0, Na * W).reshape(Na, W)
+        want = port.shamir_share_array(61, pairs, t, n, "pedersen", 5)
+        assert np.array_equal(g_ash.cpu().numpy().view(np.uint64).reshape(want.shape), want), "gathered array shares differ"
 
     # ---- C5: row-sharded mat-vec + all-gather
     rows, cols = 2048, 1024
