@@ -772,9 +772,16 @@ k_expand_coeffs(const __grid_constant__ AesKey key, const uint32_t* __restrict__
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
     for (uint32_t w = 0; w < W; ++w) coeffs[j * W + w] = secrets[j * W + w];
     const uint64_t ctr0 = first_block + j * B;
+    PrgGroup grp;  // rounds 1-2 of the 256-block group of the counter, cached (aes_ctr.cuh)
+    uint64_t gid = ~0ull;
     for (uint64_t b = (F::BYTES == 16 ? W : W / 2); b < B; ++b) {
       uint32_t o0, o1, o2, o3;
-      prg_block(key, lanebase, ctr0 + b, o0, o1, o2, o3);
+      const uint64_t ctr = ctr0 + b;
+      if ((ctr >> 8) != gid) {
+        gid = ctr >> 8;
+        prg_group(key, lanebase, ctr, grp);
+      }
+      prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
       const uint64_t w0 = (uint64_t)o0 | ((uint64_t)o1 << 32), w1 = (uint64_t)o2 | ((uint64_t)o3 << 32);
       if constexpr (F::BYTES == 16) {
         put(j, b, F127::from_raw(E127{w0, w1}));
