@@ -70,16 +70,14 @@ inline void stream_copy(void* dst, const void* src, size_t bytes) {
 class CopyTeam {
  public:
   explicit CopyTeam(int helpers) {
-    for (int i = 0; i < helpers; ++i) threads_.emplace_back([this] { loop(); });
-  }
-  ~CopyTeam() {
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      stop_ = true;
+    try {
+      for (int i = 0; i < helpers; ++i) threads_.emplace_back([this] { loop(); });
+    } catch (...) {
+      shutdown();
+      throw;
     }
-    cv_.notify_all();
-    for (auto& t : threads_) t.join();
   }
+  ~CopyTeam() { shutdown(); }
   // memcpy split into 1 MiB parts over the caller and the helpers; returns when every byte is copied.
   // One copy at a time (the stager's callbacks are serialised by their stream).  Job fields change only
   // while no helper is registered (active_ == 0); helpers register under the lock before reading them.
@@ -109,6 +107,15 @@ class CopyTeam {
 
  private:
   static constexpr size_t kPart = 1u << 20;
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+    threads_.clear();
+  }
   size_t work() {
     size_t n = 0;
     for (;;) {
@@ -275,7 +282,11 @@ class HostStager {
       unsigned hw = std::thread::hardware_concurrency();
       int helpers = hw >= 16 ? 7 : hw >= 8 ? 5 : hw >= 4 ? 2 : 1;  // + the callback thread; measured flat from 8 to 16 threads
       if (const char* v = getenv("SCLGPU_COPY_THREADS")) helpers = std::max(0, atoi(v) - 1);
-      team_ = new CopyTeam(helpers);
+      try {
+        team_ = new CopyTeam(helpers);
+      } catch (...) {  // no threads to be had: the callback thread copies alone
+        team_ = new CopyTeam(0);
+      }
     } else {
       release();
     }
