@@ -12,8 +12,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <mutex>
+#include <new>
 #include <set>
 #include <string>
 #include <vector>
@@ -64,6 +66,21 @@ static int cuda_fail(sclgpu_ctx* ctx, cudaError_t e, const char* what) {
   return fail(ctx, e == cudaErrorMemoryAllocation ? SCLGPU_ENOMEM : SCLGPU_ECUDA,
               std::string(what) + ": " + cudaGetErrorString(e));
 }
+// No C++ exception crosses the C ABI: allocation failures of the host-side containers and anything else
+// thrown below an entry point come back as an error code with a message.
+template <class Fn>
+static int guarded(sclgpu_ctx* ctx, Fn&& fn) {
+  try {
+    return fn();
+  } catch (const std::bad_alloc&) {
+    return fail(ctx, SCLGPU_ENOMEM, "host allocation failed");
+  } catch (const std::exception& e) {
+    return fail(ctx, SCLGPU_ECUDA, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return fail(ctx, SCLGPU_ECUDA, "internal error");
+  }
+}
+
 #define CK(call)                                                   \
   do {                                                             \
     cudaError_t e__ = (call);                                      \
@@ -917,16 +934,16 @@ static int from_bytes_host(sclgpu_ctx* ctx, const uint8_t* bytes, uint64_t n, vo
   return op.down(out, dout, n * sizeof(E));
 }
 
-extern "C" int sclgpu_fp61_from_bytes(sclgpu_ctx* c, const uint8_t* b, uint64_t n, uint64_t* o) { return from_bytes_host<F61>(c, b, n, o); }
-extern "C" int sclgpu_fp127_from_bytes(sclgpu_ctx* c, const uint8_t* b, uint64_t n, void* o) { return from_bytes_host<F127>(c, b, n, o); }
-extern "C" int sclgpu_fp61_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_host<F61, false>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp127_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_host<F127, false>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp61_ff_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_host<F61, true>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp127_ff_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_host<F127, true>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp61_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_dev<F61, false>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp127_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_dev<F127, false>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp61_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return random_dev<F61, true>(c, s, fb, n, o); }
-extern "C" int sclgpu_fp127_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return random_dev<F127, true>(c, s, fb, n, o); }
+extern "C" int sclgpu_fp61_from_bytes(sclgpu_ctx* c, const uint8_t* b, uint64_t n, uint64_t* o) { return guarded(c, [&] { return from_bytes_host<F61>(c, b, n, o); }); }
+extern "C" int sclgpu_fp127_from_bytes(sclgpu_ctx* c, const uint8_t* b, uint64_t n, void* o) { return guarded(c, [&] { return from_bytes_host<F127>(c, b, n, o); }); }
+extern "C" int sclgpu_fp61_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return guarded(c, [&] { return random_host<F61, false>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp127_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return guarded(c, [&] { return random_host<F127, false>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp61_ff_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return guarded(c, [&] { return random_host<F61, true>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp127_ff_random(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return guarded(c, [&] { return random_host<F127, true>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp61_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return guarded(c, [&] { return random_dev<F61, false>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp127_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return guarded(c, [&] { return random_dev<F127, false>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp61_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return guarded(c, [&] { return random_dev<F61, true>(c, s, fb, n, o); }); }
+extern "C" int sclgpu_fp127_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return guarded(c, [&] { return random_dev<F127, true>(c, s, fb, n, o); }); }
 extern "C" int sclgpu_fp61_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, uint64_t* o) {
   if (!ctx || ((!b || !o) && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
@@ -1008,10 +1025,10 @@ static int share_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t
   return SCLGPU_OK;
 }
 
-extern "C" int sclgpu_fp61_shamir_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return share_host<F61>(c, s, N, t, n, seed, fb, o); }
-extern "C" int sclgpu_fp127_shamir_share(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return share_host<F127>(c, s, N, t, n, seed, fb, o); }
-extern "C" int sclgpu_fp61_shamir_share_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return share_dev<F61>(c, s, N, t, n, seed, fb, o, layout); }
-extern "C" int sclgpu_fp127_shamir_share_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return share_dev<F127>(c, s, N, t, n, seed, fb, o, layout); }
+extern "C" int sclgpu_fp61_shamir_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return guarded(c, [&] { return share_host<F61>(c, s, N, t, n, seed, fb, o); }); }
+extern "C" int sclgpu_fp127_shamir_share(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return guarded(c, [&] { return share_host<F127>(c, s, N, t, n, seed, fb, o); }); }
+extern "C" int sclgpu_fp61_shamir_share_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return guarded(c, [&] { return share_dev<F61>(c, s, N, t, n, seed, fb, o, layout); }); }
+extern "C" int sclgpu_fp127_shamir_share_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return guarded(c, [&] { return share_dev<F127>(c, s, N, t, n, seed, fb, o, layout); }); }
 
 template <class F>
 static int share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, uint32_t t, uint32_t n,
@@ -1025,8 +1042,8 @@ static int share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, u
   strides_for(layout, N, n, si, sj);
   return share_coeffs_on<F>(ctx, ctx->stream, (const E*)d_coeffs, N, t, n, (E*)d_shares, si, sj);
 }
-extern "C" int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, uint32_t n, uint64_t* o, int layout) { return share_coeffs_dev<F61>(c, k, N, t, n, o, layout); }
-extern "C" int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, uint32_t n, void* o, int layout) { return share_coeffs_dev<F127>(c, k, N, t, n, o, layout); }
+extern "C" int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, uint32_t n, uint64_t* o, int layout) { return guarded(c, [&] { return share_coeffs_dev<F61>(c, k, N, t, n, o, layout); }); }
+extern "C" int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, uint32_t n, void* o, int layout) { return guarded(c, [&] { return share_coeffs_dev<F127>(c, k, N, t, n, o, layout); }); }
 
 // ------------------------------------------------------------------ array-valued secrets
 // shamirSecretShare on math::Array<FF, W> (shamir.h:52-68 with T = Array; pedersenSecretShare's sharing
@@ -1173,10 +1190,10 @@ static int share_array_host(sclgpu_ctx* ctx, const void* secrets, uint64_t N, ui
   return SCLGPU_OK;
 }
 
-extern "C" int sclgpu_fp61_shamir_share_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return share_array_host<F61>(c, s, N, W, t, n, seed, fb, o); }
-extern "C" int sclgpu_fp127_shamir_share_array(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return share_array_host<F127>(c, s, N, W, t, n, seed, fb, o); }
-extern "C" int sclgpu_fp61_shamir_share_array_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return share_array_dev<F61>(c, s, N, W, t, n, seed, fb, o, layout); }
-extern "C" int sclgpu_fp127_shamir_share_array_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return share_array_dev<F127>(c, s, N, W, t, n, seed, fb, o, layout); }
+extern "C" int sclgpu_fp61_shamir_share_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return guarded(c, [&] { return share_array_host<F61>(c, s, N, W, t, n, seed, fb, o); }); }
+extern "C" int sclgpu_fp127_shamir_share_array(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return guarded(c, [&] { return share_array_host<F127>(c, s, N, W, t, n, seed, fb, o); }); }
+extern "C" int sclgpu_fp61_shamir_share_array_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return guarded(c, [&] { return share_array_dev<F61>(c, s, N, W, t, n, seed, fb, o, layout); }); }
+extern "C" int sclgpu_fp127_shamir_share_array_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return guarded(c, [&] { return share_array_dev<F127>(c, s, N, W, t, n, seed, fb, o, layout); }); }
 extern "C" uint64_t sclgpu_share_array_blocks(uint32_t element_bytes, uint32_t W, uint32_t t) { return ((uint64_t)(t + 1) * W * element_bytes + 15) / 16; }
 
 // ------------------------------------------------------------------ per-party packets
@@ -1337,14 +1354,14 @@ static int additive_recover_host(sclgpu_ctx* ctx, const void* shares, uint64_t N
   CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
-extern "C" int sclgpu_fp61_additive_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return additive_share_host<F61>(c, s, N, n, seed, fb, o); }
-extern "C" int sclgpu_fp127_additive_share(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return additive_share_host<F127>(c, s, N, n, seed, fb, o); }
-extern "C" int sclgpu_fp61_additive_share_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return additive_share_dev<F61>(c, s, N, n, seed, fb, o, layout); }
-extern "C" int sclgpu_fp127_additive_share_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return additive_share_dev<F127>(c, s, N, n, seed, fb, o, layout); }
-extern "C" int sclgpu_fp61_additive_recover(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, uint64_t* o) { return additive_recover_host<F61>(c, s, N, n, o); }
-extern "C" int sclgpu_fp127_additive_recover(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, void* o) { return additive_recover_host<F127>(c, s, N, n, o); }
-extern "C" int sclgpu_fp61_additive_recover_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, uint64_t* o) { return additive_recover_dev<F61>(c, s, N, n, layout, o); }
-extern "C" int sclgpu_fp127_additive_recover_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, void* o) { return additive_recover_dev<F127>(c, s, N, n, layout, o); }
+extern "C" int sclgpu_fp61_additive_share(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o) { return guarded(c, [&] { return additive_share_host<F61>(c, s, N, n, seed, fb, o); }); }
+extern "C" int sclgpu_fp127_additive_share(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o) { return guarded(c, [&] { return additive_share_host<F127>(c, s, N, n, seed, fb, o); }); }
+extern "C" int sclgpu_fp61_additive_share_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* o, int layout) { return guarded(c, [&] { return additive_share_dev<F61>(c, s, N, n, seed, fb, o, layout); }); }
+extern "C" int sclgpu_fp127_additive_share_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const uint8_t seed[16], uint64_t fb, void* o, int layout) { return guarded(c, [&] { return additive_share_dev<F127>(c, s, N, n, seed, fb, o, layout); }); }
+extern "C" int sclgpu_fp61_additive_recover(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, uint64_t* o) { return guarded(c, [&] { return additive_recover_host<F61>(c, s, N, n, o); }); }
+extern "C" int sclgpu_fp127_additive_recover(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, void* o) { return guarded(c, [&] { return additive_recover_host<F127>(c, s, N, n, o); }); }
+extern "C" int sclgpu_fp61_additive_recover_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, uint64_t* o) { return guarded(c, [&] { return additive_recover_dev<F61>(c, s, N, n, layout, o); }); }
+extern "C" int sclgpu_fp127_additive_recover_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, void* o) { return guarded(c, [&] { return additive_recover_dev<F127>(c, s, N, n, layout, o); }); }
 
 // ------------------------------------------------------------------ lagrange
 template <class F>
@@ -1359,8 +1376,8 @@ static int lagrange_host(sclgpu_ctx* ctx, const void* nodes, uint32_t n, const v
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   return SCLGPU_OK;
 }
-extern "C" int sclgpu_fp61_lagrange_basis(sclgpu_ctx* c, const uint64_t* nodes, uint32_t n, const uint64_t* x, uint64_t* o) { return lagrange_host<F61>(c, nodes, n, x, o); }
-extern "C" int sclgpu_fp127_lagrange_basis(sclgpu_ctx* c, const void* nodes, uint32_t n, const void* x, void* o) { return lagrange_host<F127>(c, nodes, n, x, o); }
+extern "C" int sclgpu_fp61_lagrange_basis(sclgpu_ctx* c, const uint64_t* nodes, uint32_t n, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return lagrange_host<F61>(c, nodes, n, x, o); }); }
+extern "C" int sclgpu_fp127_lagrange_basis(sclgpu_ctx* c, const void* nodes, uint32_t n, const void* x, void* o) { return guarded(c, [&] { return lagrange_host<F127>(c, nodes, n, x, o); }); }
 
 // Matrix::hyperInvertible(n, m), matrix.h:462-475: row i = computeLagrangeBasis(range(1, m+1), -i); the
 // int overload (lagrange.h:80-82) makes -i the field element p - i (FF(int), mersenne61.cc:38-40).
@@ -1380,8 +1397,8 @@ static int hyper_invertible_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* 
   CK(cudaStreamSynchronize(ctx->pipe[0]));
   return SCLGPU_OK;
 }
-extern "C" int sclgpu_fp61_hyper_invertible(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return hyper_invertible_host<F61>(c, n, m, o); }
-extern "C" int sclgpu_fp127_hyper_invertible(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return hyper_invertible_host<F127>(c, n, m, o); }
+extern "C" int sclgpu_fp61_hyper_invertible(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return guarded(c, [&] { return hyper_invertible_host<F61>(c, n, m, o); }); }
+extern "C" int sclgpu_fp127_hyper_invertible(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return guarded(c, [&] { return hyper_invertible_host<F127>(c, n, m, o); }); }
 
 // ------------------------------------------------------------------ recover P
 template <class F>
@@ -1494,15 +1511,15 @@ static int recover_p_packets_host(sclgpu_ctx* ctx, const uint8_t* const* packets
   CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
-extern "C" int sclgpu_fp61_shamir_share_packets(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return share_packets_host<F61>(c, s, N, t, n, seed, fb, p); }
-extern "C" int sclgpu_fp127_shamir_share_packets(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return share_packets_host<F127>(c, s, N, t, n, seed, fb, p); }
-extern "C" int sclgpu_fp61_recover_p_packets(sclgpu_ctx* c, const uint8_t* const* p, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_packets_host<F61>(c, p, N, n, a, x, o); }
-extern "C" int sclgpu_fp127_recover_p_packets(sclgpu_ctx* c, const uint8_t* const* p, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return recover_p_packets_host<F127>(c, p, N, n, a, x, o); }
+extern "C" int sclgpu_fp61_shamir_share_packets(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return guarded(c, [&] { return share_packets_host<F61>(c, s, N, t, n, seed, fb, p); }); }
+extern "C" int sclgpu_fp127_shamir_share_packets(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint8_t* const* p) { return guarded(c, [&] { return share_packets_host<F127>(c, s, N, t, n, seed, fb, p); }); }
+extern "C" int sclgpu_fp61_recover_p_packets(sclgpu_ctx* c, const uint8_t* const* p, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return recover_p_packets_host<F61>(c, p, N, n, a, x, o); }); }
+extern "C" int sclgpu_fp127_recover_p_packets(sclgpu_ctx* c, const uint8_t* const* p, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return guarded(c, [&] { return recover_p_packets_host<F127>(c, p, N, n, a, x, o); }); }
 extern "C" uint64_t sclgpu_packet_bytes(uint32_t element_bytes, uint64_t n_elements) { return kPacketHeader + (uint64_t)element_bytes * n_elements; }
-extern "C" int sclgpu_fp61_recover_p(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_host<F61>(c, s, N, n, a, x, o); }
-extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return recover_p_host<F127>(c, s, N, n, a, x, o); }
-extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }
-extern "C" int sclgpu_fp127_recover_p_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, const void* x, void* o) { return recover_p_dev<F127>(c, s, N, n, layout, a, x, o); }
+extern "C" int sclgpu_fp61_recover_p(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return recover_p_host<F61>(c, s, N, n, a, x, o); }); }
+extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, const void* x, void* o) { return guarded(c, [&] { return recover_p_host<F127>(c, s, N, n, a, x, o); }); }
+extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }); }
+extern "C" int sclgpu_fp127_recover_p_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, const void* x, void* o) { return guarded(c, [&] { return recover_p_dev<F127>(c, s, N, n, layout, a, x, o); }); }
 
 // shamirRecoverP on Vector<Array<FF, W>> (shamir.h:100-104 with T = Array): the basis of nodes 1..n at 0
 // applied component-wise, i.e. the plane kernel on N*W columns.
@@ -1571,10 +1588,10 @@ static int recover_p_array_host(sclgpu_ctx* ctx, const void* shares, uint64_t N,
   CK(ctx->stager.drain());
   return SCLGPU_OK;
 }
-extern "C" int sclgpu_fp61_recover_p_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, uint64_t* o) { return recover_p_array_host<F61>(c, s, N, W, n, o); }
-extern "C" int sclgpu_fp127_recover_p_array(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t n, void* o) { return recover_p_array_host<F127>(c, s, N, W, n, o); }
-extern "C" int sclgpu_fp61_recover_p_array_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, int layout, uint64_t* o) { return recover_p_array_dev<F61>(c, s, N, W, n, layout, o); }
-extern "C" int sclgpu_fp127_recover_p_array_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t n, int layout, void* o) { return recover_p_array_dev<F127>(c, s, N, W, n, layout, o); }
+extern "C" int sclgpu_fp61_recover_p_array(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, uint64_t* o) { return guarded(c, [&] { return recover_p_array_host<F61>(c, s, N, W, n, o); }); }
+extern "C" int sclgpu_fp127_recover_p_array(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t n, void* o) { return guarded(c, [&] { return recover_p_array_host<F127>(c, s, N, W, n, o); }); }
+extern "C" int sclgpu_fp61_recover_p_array_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t W, uint32_t n, int layout, uint64_t* o) { return guarded(c, [&] { return recover_p_array_dev<F61>(c, s, N, W, n, layout, o); }); }
+extern "C" int sclgpu_fp127_recover_p_array_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t W, uint32_t n, int layout, void* o) { return guarded(c, [&] { return recover_p_array_dev<F127>(c, s, N, W, n, layout, o); }); }
 
 // ------------------------------------------------------------------ recover D
 static int finish_detect(sclgpu_ctx* ctx, cudaStream_t st, uint64_t* n_detected) {
@@ -1651,10 +1668,10 @@ static int recover_d_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   CK(ctx->stager.drain());
   return rc;
 }
-extern "C" int sclgpu_fp61_recover_d(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F61>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
-extern "C" int sclgpu_fp127_recover_d(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_host<F127>(c, s, N, ng, t, a, na, d, x, o, e, nd); }
-extern "C" int sclgpu_fp61_recover_d_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return recover_d_dev<F61>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }
-extern "C" int sclgpu_fp127_recover_d_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return recover_d_dev<F127>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }
+extern "C" int sclgpu_fp61_recover_d(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return guarded(c, [&] { return recover_d_host<F61>(c, s, N, ng, t, a, na, d, x, o, e, nd); }); }
+extern "C" int sclgpu_fp127_recover_d(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return guarded(c, [&] { return recover_d_host<F127>(c, s, N, ng, t, a, na, d, x, o, e, nd); }); }
+extern "C" int sclgpu_fp61_recover_d_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const uint64_t* a, uint32_t na, uint32_t d, const uint64_t* x, uint64_t* o, uint8_t* e, uint64_t* nd) { return guarded(c, [&] { return recover_d_dev<F61>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }); }
+extern "C" int sclgpu_fp127_recover_d_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t ng, int layout, uint32_t t, const void* a, uint32_t na, uint32_t d, const void* x, void* o, uint8_t* e, uint64_t* nd) { return guarded(c, [&] { return recover_d_dev<F127>(c, s, N, ng, layout, t, a, na, d, x, o, e, nd); }); }
 
 // ------------------------------------------------------------------ recover C
 // alphas stay HOST pointers (n values); d_* are device pointers
@@ -1775,10 +1792,10 @@ static int recover_c_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   }
   return rc;
 }
-extern "C" int sclgpu_fp61_recover_c(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, uint64_t* f, uint64_t* e, uint8_t* st, uint64_t* nf) { return recover_c_host<F61>(c, s, N, n, a, f, e, st, nf); }
-extern "C" int sclgpu_fp127_recover_c(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, void* f, void* e, uint8_t* st, uint64_t* nf) { return recover_c_host<F127>(c, s, N, n, a, f, e, st, nf); }
-extern "C" int sclgpu_fp61_recover_c_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, uint64_t* f, uint64_t* e, uint8_t* st, uint64_t* nf) { return recover_c_dev<F61>(c, s, N, n, layout, a, f, e, st, nf); }
-extern "C" int sclgpu_fp127_recover_c_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, void* f, void* e, uint8_t* st, uint64_t* nf) { return recover_c_dev<F127>(c, s, N, n, layout, a, f, e, st, nf); }
+extern "C" int sclgpu_fp61_recover_c(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, uint64_t* f, uint64_t* e, uint8_t* st, uint64_t* nf) { return guarded(c, [&] { return recover_c_host<F61>(c, s, N, n, a, f, e, st, nf); }); }
+extern "C" int sclgpu_fp127_recover_c(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, const void* a, void* f, void* e, uint8_t* st, uint64_t* nf) { return guarded(c, [&] { return recover_c_host<F127>(c, s, N, n, a, f, e, st, nf); }); }
+extern "C" int sclgpu_fp61_recover_c_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, uint64_t* f, uint64_t* e, uint8_t* st, uint64_t* nf) { return guarded(c, [&] { return recover_c_dev<F61>(c, s, N, n, layout, a, f, e, st, nf); }); }
+extern "C" int sclgpu_fp127_recover_c_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, void* f, void* e, uint8_t* st, uint64_t* nf) { return guarded(c, [&] { return recover_c_dev<F127>(c, s, N, n, layout, a, f, e, st, nf); }); }
 
 // ------------------------------------------------------------------ vector ops
 template <class F, int OP>
@@ -1935,10 +1952,10 @@ static int vec_equal_host(sclgpu_ctx* ctx, const void* a, const void* b, uint64_
   RET(hop.up(b, n * sizeof(E), &db));
   return vec_equal_on<F>(ctx, hop.st, (const E*)da, (const E*)db, n, equal);
 }
-extern "C" int sclgpu_fp61_vec_equal(sclgpu_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n, int* eq) { return vec_equal_host<F61>(c, a, b, n, eq); }
-extern "C" int sclgpu_fp127_vec_equal(sclgpu_ctx* c, const void* a, const void* b, uint64_t n, int* eq) { return vec_equal_host<F127>(c, a, b, n, eq); }
-extern "C" int sclgpu_fp61_vec_equal_dev(sclgpu_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n, int* eq) { return vec_equal_dev<F61>(c, a, b, n, eq); }
-extern "C" int sclgpu_fp127_vec_equal_dev(sclgpu_ctx* c, const void* a, const void* b, uint64_t n, int* eq) { return vec_equal_dev<F127>(c, a, b, n, eq); }
+extern "C" int sclgpu_fp61_vec_equal(sclgpu_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n, int* eq) { return guarded(c, [&] { return vec_equal_host<F61>(c, a, b, n, eq); }); }
+extern "C" int sclgpu_fp127_vec_equal(sclgpu_ctx* c, const void* a, const void* b, uint64_t n, int* eq) { return guarded(c, [&] { return vec_equal_host<F127>(c, a, b, n, eq); }); }
+extern "C" int sclgpu_fp61_vec_equal_dev(sclgpu_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t n, int* eq) { return guarded(c, [&] { return vec_equal_dev<F61>(c, a, b, n, eq); }); }
+extern "C" int sclgpu_fp127_vec_equal_dev(sclgpu_ctx* c, const void* a, const void* b, uint64_t n, int* eq) { return guarded(c, [&] { return vec_equal_dev<F127>(c, a, b, n, eq); }); }
 
 SCLGPU_VEC_API(fp61, F61, uint64_t*, const uint64_t*)
 SCLGPU_VEC_API(fp127, F127, void*, const void*)
@@ -2048,15 +2065,15 @@ static int matmul_host(sclgpu_ctx* ctx, const void* A, uint32_t rows, uint32_t i
   RET(matmul_on<F>(ctx, hop.st, (const E*)dA, rows, inner, (const E*)dB, cols, (E*)dC));
   return hop.down(C, dC, (size_t)rows * cols * sizeof(E));
 }
-extern "C" int sclgpu_fp61_matmul(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* B, uint32_t n, uint64_t* C) { return matmul_host<F61>(c, A, r, k, B, n, C); }
-extern "C" int sclgpu_fp127_matmul(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* B, uint32_t n, void* C) { return matmul_host<F127>(c, A, r, k, B, n, C); }
-extern "C" int sclgpu_fp61_matmul_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* B, uint32_t n, uint64_t* C) { return matmul_dev<F61>(c, A, r, k, B, n, C); }
-extern "C" int sclgpu_fp127_matmul_dev(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* B, uint32_t n, void* C) { return matmul_dev<F127>(c, A, r, k, B, n, C); }
+extern "C" int sclgpu_fp61_matmul(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* B, uint32_t n, uint64_t* C) { return guarded(c, [&] { return matmul_host<F61>(c, A, r, k, B, n, C); }); }
+extern "C" int sclgpu_fp127_matmul(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* B, uint32_t n, void* C) { return guarded(c, [&] { return matmul_host<F127>(c, A, r, k, B, n, C); }); }
+extern "C" int sclgpu_fp61_matmul_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* B, uint32_t n, uint64_t* C) { return guarded(c, [&] { return matmul_dev<F61>(c, A, r, k, B, n, C); }); }
+extern "C" int sclgpu_fp127_matmul_dev(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* B, uint32_t n, void* C) { return guarded(c, [&] { return matmul_dev<F127>(c, A, r, k, B, n, C); }); }
 
-extern "C" int sclgpu_fp61_matvec(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return matvec_host<F61>(c, A, r, k, x, y); }
-extern "C" int sclgpu_fp127_matvec(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return matvec_host<F127>(c, A, r, k, x, y); }
-extern "C" int sclgpu_fp61_matvec_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return matvec_dev<F61>(c, A, r, k, x, y); }
-extern "C" int sclgpu_fp127_matvec_dev(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return matvec_dev<F127>(c, A, r, k, x, y); }
+extern "C" int sclgpu_fp61_matvec(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return guarded(c, [&] { return matvec_host<F61>(c, A, r, k, x, y); }); }
+extern "C" int sclgpu_fp127_matvec(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return guarded(c, [&] { return matvec_host<F127>(c, A, r, k, x, y); }); }
+extern "C" int sclgpu_fp61_matvec_dev(sclgpu_ctx* c, const uint64_t* A, uint32_t r, uint32_t k, const uint64_t* x, uint64_t* y) { return guarded(c, [&] { return matvec_dev<F61>(c, A, r, k, x, y); }); }
+extern "C" int sclgpu_fp127_matvec_dev(sclgpu_ctx* c, const void* A, uint32_t r, uint32_t k, const void* x, void* y) { return guarded(c, [&] { return matvec_dev<F127>(c, A, r, k, x, y); }); }
 
 template <class F>
 static int vandermonde_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out) {
@@ -2072,8 +2089,8 @@ static int vandermonde_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out) 
   CKL();
   return hop.down(out, dv, (size_t)n * m * sizeof(E));
 }
-extern "C" int sclgpu_fp61_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return vandermonde_host<F61>(c, n, m, o); }
-extern "C" int sclgpu_fp127_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return vandermonde_host<F127>(c, n, m, o); }
+extern "C" int sclgpu_fp61_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return guarded(c, [&] { return vandermonde_host<F61>(c, n, m, o); }); }
+extern "C" int sclgpu_fp127_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return guarded(c, [&] { return vandermonde_host<F127>(c, n, m, o); }); }
 
 extern "C" int sclgpu_fp61_transpose_dev(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
   if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");
