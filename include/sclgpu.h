@@ -143,6 +143,24 @@ int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const uint64_t* d_coeff
 int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N,
                                          uint32_t t, uint32_t n, void* d_shares, int layout);
 
+/* ---- the C2 step in one launch: N x { ss::shamirSecretShare (shamir.h:52-68),
+ * ss::shamirRecoverP (shamir.h:82-104) } on party-major planes ([n][N]; plane i = what
+ * party i holds).  The share groups of the tcgen05 share kernel (limited by the
+ * shared-memory pipe of the fused AES-CTR) and reconstruction warps (FMA pipe + memory)
+ * run in the same persistent CTAs.
+ *   d_rec_shares == d_shares : the sharings produced by THIS call are reconstructed, each
+ *       128-secret tile as soon as it is stored (d_out[j] == d_secrets[j] afterwards);
+ *   otherwise d_rec_shares is ANOTHER batch of N sharings ([n][N]) -- e.g. the batch a
+ *       previous call produced and the parties returned -- reconstructed concurrently.
+ * alphas == NULL: nodes 1..n, x = 0 (shamir.h:100-104); else n nodes and x as in
+ * sclgpu_fp61_recover_p.  Any (t, n): shapes outside the fused kernel (t > 15 or
+ * n > 32) run as sclgpu_fp61_shamir_share_dev followed by sclgpu_fp61_recover_p_dev. */
+int sclgpu_fp61_shamir_share_recover_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N,
+                                         uint32_t t, uint32_t n, const uint8_t seed[16],
+                                         uint64_t first_block, uint64_t* d_shares,
+                                         const uint64_t* d_rec_shares, const uint64_t* alphas,
+                                         const uint64_t* x, uint64_t* d_out);
+
 /* ---- ss::shamirRecoverC (shamir.h:203-258, Berlekamp-Welch) on N sharings ---------
  * t = (n-1)/3 and the first np = 3t+1 shares of each sharing are used, as in the
  * reference; alphas == NULL means 1..n (shamir.h:256-258).  Per sharing j:

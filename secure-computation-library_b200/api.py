@@ -226,6 +226,16 @@ class Context:
                          layout: int = B.PARTY_MAJOR):
         self._check(self._f(field, "shamir_share_dev")(self._ctx, _dp(secrets), N, t, n, seed16(seed), first_block, _dp(shares), layout))
 
+    def shamir_share_recover_dev(self, secrets, N: int, t: int, n: int, seed, first_block: int, shares, out,
+                                 rec_shares=None, alphas=None, x: int | None = None):
+        """Fp61, party-major planes: shamirSecretShare of `secrets` into `shares` AND shamirRecoverP of
+        `rec_shares` (default: the sharings just produced) into `out`, in one launch."""
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], 61)
+        rs = shares if rec_shares is None else rec_shares
+        self._check(self.lib.sclgpu_fp61_shamir_share_recover_dev(self._ctx, _dp(secrets), N, t, n, seed16(seed), first_block,
+                                                                  _dp(shares), _dp(rs), _p(A), _p(X), _dp(out)))
+
     def shamir_share_coeffs_dev(self, field: int, coeffs, N: int, t: int, n: int, shares, layout: int = B.PARTY_MAJOR):
         self._check(self._f(field, "shamir_share_coeffs_dev")(self._ctx, _dp(coeffs), N, t, n, _dp(shares), layout))
 

@@ -110,6 +110,7 @@ def load() -> C.CDLL:
              _vp, _vp, _vp, C.POINTER(_u64))
         _sig(lib, f"sclgpu_{f}_vandermonde", _int, _vp, _u32, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_transpose_dev", _int, _vp, _vp, _u64, _u64, _vp)
+    _sig(lib, "sclgpu_fp61_shamir_share_recover_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp)
     _sig(lib, "sclgpu_packet_bytes", _u64, _u32, _u64)
     _sig(lib, "sclgpu_share_array_blocks", _u64, _u32, _u32, _u32)
     _sig(lib, "sclgpu_pipe_microbench", _int, _vp, _int, _u32, C.POINTER(C.c_double))

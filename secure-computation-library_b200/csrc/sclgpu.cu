@@ -46,7 +46,9 @@ struct sclgpu_ctx {
   std::map<std::string, void*> basis_cache;  // (field, nodes, xs) -> device matrix
   std::map<uint32_t, void*> tc_bmat_cache;   // (t, n) -> Vandermonde limb image of k_share61_tc
   std::map<const void*, void*> rd_bmat_cache;  // Lagrange check matrix (device) -> its limb image for k_recover_d_tc
+  std::map<const void*, RecBasis61> rec_basis_cache;  // Lagrange basis (device) -> 21-bit limbs for k_share_recover61
   bool tc_prepared = false;
+  bool sr_prepared = false;
   // device scratch of the host-pointer entry points (chunk buffers), kept across calls: a cudaMalloc /
   // cudaFree pair per buffer per call costs milliseconds and a device synchronisation
   std::vector<std::pair<void*, size_t>> pool;
@@ -144,6 +146,32 @@ static AesKey aes_expand(const uint8_t seed[16]) {
   k.k16 = 1u << 16;
   k.k24 = 1u << 24;
   return k;
+}
+
+// ------------------------------------------------------------ environment knobs
+// Measurement / test switches.  Every variable is read ONCE per process, at its first use, and the
+// answer is kept: no getenv on the dispatch paths.
+static bool env_flag(const char* name) {
+  static std::mutex mu;
+  static std::map<std::string, bool> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = seen.find(name);
+  if (it != seen.end()) return it->second;
+  const bool v = getenv(name) != nullptr;
+  seen.emplace(name, v);
+  return v;
+}
+
+static int env_int(const char* name, int dflt) {
+  static std::mutex mu;
+  static std::map<std::string, int> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = seen.find(name);
+  if (it != seen.end()) return it->second;
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  seen.emplace(name, v);
+  return v;
 }
 
 // ------------------------------------------------------------ launch helpers
@@ -488,7 +516,8 @@ static int share_tc_on(sclgpu_ctx* ctx, cudaStream_t st, const AesKey& key, uint
   int variant = g_share_tc;
   if (F::BYTES == 16 && variant == 1) variant = 3;  // the shared-memory-A kernel exists for Fp61 only
   const int groups = tc_variant_groups(variant);
-  const int grid = (int)std::min<uint64_t>((tiles + groups - 1) / groups, (uint64_t)ctx->sm_count);
+  const int share_sms = std::min(ctx->sm_count, std::max(1, env_int("SCLGPU_SHARE_SMS", ctx->sm_count)));
+  const int grid = (int)std::min<uint64_t>((tiles + groups - 1) / groups, (uint64_t)share_sms);
   ctx->launches++;
   cudaError_t e;
   if constexpr (F::BYTES == 8) {
@@ -544,7 +573,7 @@ static int share_coeffs_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E
                            uint32_t t, uint32_t n, typename F::E* d_out, uint64_t si, uint64_t sj) {
   if (N == 0 || n == 0) return SCLGPU_OK;
   const bool fits = F::BYTES == 8 ? (t <= kTcMaxT && n <= kTcMaxParties) : (t <= kTcMaxT127 && n <= kTcMaxParties127);
-  if (fits && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr) {
+  if (fits && share_tc_enabled() && !env_flag("SCLGPU_SHARE_GENERIC")) {
     const void* d_bmat = nullptr;
     RET(share_tc_bmat<F>(ctx, st, t, n, &d_bmat));
     ctx->launches++;
@@ -571,9 +600,9 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   if (N == 0 || n == 0) return SCLGPU_OK;
   const AesKey key = aes_expand(seed);
   if constexpr (F::BYTES == 8) {
-    if (t <= kTcMaxT && n <= kTcMaxParties && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr)
+    if (t <= kTcMaxT && n <= kTcMaxParties && share_tc_enabled() && !env_flag("SCLGPU_SHARE_GENERIC"))
       return share_tc_on<F61>(ctx, st, key, first_block, d_secrets, N, t, n, d_out, si, sj);
-    if (t <= 15 && n <= 0xFFFFu && getenv("SCLGPU_SHARE_GENERIC") == nullptr) {
+    if (t <= 15 && n <= 0xFFFFu && !env_flag("SCLGPU_SHARE_GENERIC")) {
 #define SCLGPU_CASE61(TT) \
   case TT: return share61_mode<TT>(ctx, st, key, first_block, d_secrets, N, n, d_out, si, sj);
       switch (t) {
@@ -586,7 +615,7 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
     }
   }
   if constexpr (F::BYTES == 16) {
-    if (t <= kTcMaxT127 && n <= kTcMaxParties127 && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr)
+    if (t <= kTcMaxT127 && n <= kTcMaxParties127 && share_tc_enabled() && !env_flag("SCLGPU_SHARE_GENERIC"))
       return share_tc_on<F127>(ctx, st, key, first_block, d_secrets, N, t, n, d_out, si, sj);
   }
 #define SCLGPU_CASE(TT) \
@@ -683,6 +712,7 @@ static int basis_rows(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* nod
     ctx->basis_cache.clear();
     for (auto& kv : ctx->rd_bmat_cache) cudaFree(kv.second);  // keyed by the pointers just freed
     ctx->rd_bmat_cache.clear();
+    ctx->rec_basis_cache.clear();
   }
   ctx->basis_cache[key] = dm;
   *d_mat = reinterpret_cast<const E*>(dm);
@@ -701,12 +731,14 @@ static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   if (N == 0) return SCLGPU_OK;
   if constexpr (F::BYTES == 8) {
     // party-major planes, the device-native layout: HBM-bound kernel
-    if (sj == 1 && n >= 1 && n <= 2048 && getenv("SCLGPU_RECOVER_GENERIC") == nullptr) {
+    if (env_flag("SCLGPU_RECOVER61_TC") && recover_d_tc_fits<F>(n, 0))
+      return recover_d_on<F>(ctx, st, d_shares, N, si, sj, n, 0, d_basis, d_out, nullptr);
+    if (sj == 1 && n >= 1 && n <= 2048 && !env_flag("SCLGPU_RECOVER_GENERIC")) {
       const bool vec2 = (N % 2 == 0) && (si % 2 == 0) &&
                         ((reinterpret_cast<uintptr_t>(d_shares) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
       const size_t lsm = (size_t)n * 16;
       if (vec2) {
-        k_recover61_pm<2><<<grid_for(ctx, N / 2, 256, 3), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
+        k_recover61_pm<2><<<std::min(grid_for(ctx, N / 2, 256, 3), 3 * std::max(1, env_int("SCLGPU_RECOVER_SMS", ctx->sm_count))), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
       } else {
         k_recover61_pm<1><<<grid_for(ctx, N, 256, 4), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
       }
@@ -716,7 +748,7 @@ static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   }
   if constexpr (F::BYTES == 16) {
     // Fp127: the inner product as a one-row limb product on the tensor cores (k_recover_d_tc without checks)
-    if (recover_d_tc_fits<F>(n, 0) && getenv("SCLGPU_RECOVER_GENERIC") == nullptr)
+    if (recover_d_tc_fits<F>(n, 0) && !env_flag("SCLGPU_RECOVER_GENERIC"))
       return recover_d_on<F>(ctx, st, d_shares, N, si, sj, n, 0, d_basis, d_out, nullptr);
   }
   const size_t smem = (size_t)n * sizeof(typename F::E);
@@ -759,7 +791,7 @@ static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
                         uint64_t si, uint64_t sj, uint32_t m, uint32_t n_checks,
                         const typename F::E* d_mat, typename F::E* d_out, uint8_t* d_err) {
   if (N == 0) return SCLGPU_OK;
-  if (recover_d_tc_fits<F>(m, n_checks) && getenv("SCLGPU_RECOVER_GENERIC") == nullptr) {
+  if (recover_d_tc_fits<F>(m, n_checks) && !env_flag("SCLGPU_RECOVER_GENERIC")) {
     // tensor-core kernel: limb image of the (n_checks+1) x m matrix, row r*BYTES+s, column k*BYTES+a
     typedef typename F::E E;
     constexpr uint32_t EB = F::BYTES;
@@ -795,7 +827,7 @@ static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     ctx->launches++;
     cudaError_t e;
     if constexpr (EB == 8) {
-      e = recover_d61_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, d_err ? ctx->d_count : nullptr);
+      e = recover_d61_tc_launch(st, std::min(ctx->sm_count, std::max(1, env_int("SCLGPU_RECOVER_SMS", ctx->sm_count))), d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, d_err ? ctx->d_count : nullptr);
     } else {
       e = recover_d127_tc_launch(st, ctx->sm_count, d_img, d_shares, N, si, sj, m, n_checks, d_out, d_err, d_err ? ctx->d_count : nullptr);
     }
@@ -1078,7 +1110,7 @@ static bool array_args_ok(sclgpu_ctx* ctx, uint64_t N, uint32_t W, uint32_t n, i
 template <class F>
 static bool share_array_fused(uint32_t W, uint32_t t, uint32_t n) {
   const bool fits = F::BYTES == 8 ? (t <= kTcMaxT && n <= kTcMaxParties && W % 2 == 0) : (t <= kTcMaxT127 && n <= kTcMaxParties127);
-  return fits && share_tc_enabled() && getenv("SCLGPU_SHARE_GENERIC") == nullptr;
+  return fits && share_tc_enabled() && !env_flag("SCLGPU_SHARE_GENERIC");
 }
 
 // one chunk of nc sharings, secrets and output on the device; planes: (t+1)*nc*W elements of scratch,
@@ -1521,6 +1553,60 @@ extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, 
 extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }); }
 extern "C" int sclgpu_fp127_recover_p_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, const void* x, void* o) { return guarded(c, [&] { return recover_p_dev<F127>(c, s, N, n, layout, a, x, o); }); }
 
+// ------------------------------------------------------------------ share + recover P in one launch
+// N x { shamirSecretShare (shamir.h:52-68), shamirRecoverP (shamir.h:82-104) } on party-major planes.  With
+// d_rec_shares == d_shares the sharings produced by this call are reconstructed (the round trip of one batch);
+// otherwise d_rec_shares is another batch of N sharings, reconstructed under the share work of this one.
+// Shapes the fused kernel does not take (t > 15, n > 32, another field) run as the two kernels back to back.
+static int share_recover61_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
+                               const uint8_t seed[16], uint64_t first_block, uint64_t* d_shares,
+                               const uint64_t* d_rec_shares, const uint64_t* alphas, const uint64_t* x,
+                               uint64_t* d_out) {
+  if (!ctx || !seed || ((!d_secrets || !d_shares || !d_rec_shares || !d_out) && N && n))
+    return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n too large");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  cudaStream_t st = ctx->stream;
+  const uint64_t* d_basis = nullptr;
+  RET(recover_p_basis<F61>(ctx, st, n, alphas, x, &d_basis));
+  // the reconstruction warps use 128-bit accesses (two secrets per thread): even N, 16-byte aligned planes and output
+  const bool fused = t <= kTcMaxT && n <= kTcMaxParties && share_tc_enabled() && !env_flag("SCLGPU_SHARE_GENERIC") &&
+                     !env_flag("SCLGPU_NO_FUSED_STEP") && N % 2 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(d_rec_shares) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+  if (!fused) {
+    RET(share_strided_on<F61>(ctx, st, d_secrets, N, t, n, seed, first_block, d_shares, N, 1));
+    return recover_p_on<F61>(ctx, st, d_rec_shares, N, n, N, 1, d_basis, d_out);
+  }
+  auto it = ctx->rec_basis_cache.find(d_basis);
+  if (it == ctx->rec_basis_cache.end()) {
+    uint64_t hb[kTcMaxParties];
+    CK(cudaMemcpyAsync(hb, d_basis, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    RecBasis61 rb;
+    std::memset(&rb, 0, sizeof(rb));
+    for (uint32_t i = 0; i < n; ++i) {
+      rb.l[i][0] = (uint32_t)(hb[i] & 0x1FFFFFu);
+      rb.l[i][1] = (uint32_t)((hb[i] >> 21) & 0x1FFFFFu);
+      rb.l[i][2] = (uint32_t)(hb[i] >> 42);
+    }
+    it = ctx->rec_basis_cache.emplace(d_basis, rb).first;
+  }
+  if (!ctx->sr_prepared) {
+    CK(share_recover61_prepare());
+    ctx->sr_prepared = true;
+  }
+  const void* d_bmat = nullptr;
+  RET(share_tc_bmat<F61>(ctx, st, t, n, &d_bmat));
+  const AesKey key = aes_expand(seed);
+  ctx->launches++;
+  cudaError_t e = share_recover61_launch(st, ctx->sm_count, key, it->second, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n,
+                                         d_shares, d_rec_shares, d_out);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_shamir_share_recover_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* sh, const uint64_t* rs, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return share_recover61_dev(c, s, N, t, n, seed, fb, sh, rs, a, x, o); }); }
+
 // shamirRecoverP on Vector<Array<FF, W>> (shamir.h:100-104 with T = Array): the basis of nodes 1..n at 0
 // applied component-wise, i.e. the plane kernel on N*W columns.
 template <class F>
@@ -1702,7 +1788,7 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   uint32_t* d_pending = nullptr;
   unsigned long long* d_n_pending = nullptr;
   std::vector<E> coef;
-  if (distinct && t <= kRecoverCMaxT && N < (1ull << 32) && getenv("SCLGPU_RECOVER_C_FULL") == nullptr) {
+  if (distinct && t <= kRecoverCMaxT && N < (1ull << 32) && !env_flag("SCLGPU_RECOVER_C_FULL")) {
     const uint32_t m = t + 1;
     const E* d_check = nullptr;
     if (t > 0) RET(basis_rows<F>(ctx, st, al.data(), m, al.data() + m, 2 * t, &d_check));
@@ -1739,7 +1825,7 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   }
   const int warps_per_cta = 8;
   const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 3 * np) * sizeof(E);
-  const int quick = (distinct && getenv("SCLGPU_RECOVER_C_FULL") == nullptr) ? 1 : 0;
+  const int quick = (distinct && !env_flag("SCLGPU_RECOVER_C_FULL")) ? 1 : 0;
   CK(cudaFuncSetAttribute(k_recover_c<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<uint64_t>((N + warps_per_cta - 1) / warps_per_cta, (uint64_t)ctx->sm_count * 4);
   k_recover_c<F><<<grid, 32 * warps_per_cta, smem, st>>>(d_shares, N, si, sj, t, dal.as<E>(), d_f, d_e, d_status,
@@ -2014,8 +2100,8 @@ static int matmul_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, u
   ctx->launches++;
   cudaError_t e;
   const uint64_t work = (uint64_t)rows * cols * inner;
-  const bool big = work >= (F::BYTES == 8 ? (1ull << 18) : (1ull << 16)) && getenv("SCLGPU_MATMUL_GENERIC") == nullptr;
-  const bool v1 = getenv("SCLGPU_MATMUL_V1") != nullptr;  // the cp.async form (Fp61: even inner dimension, aligned A)
+  const bool big = work >= (F::BYTES == 8 ? (1ull << 18) : (1ull << 16)) && !env_flag("SCLGPU_MATMUL_GENERIC");
+  const bool v1 = env_flag("SCLGPU_MATMUL_V1");  // the cp.async form (Fp61: even inner dimension, aligned A)
   if (big && !(v1 && F::BYTES == 8 && ((inner & 1) || (reinterpret_cast<uintptr_t>(A) & 15)))) {
     void* scratch = nullptr;
     size_t bytes;

@@ -30,6 +30,20 @@ static inline uint32_t tc_bmat_offset(uint32_t r, uint32_t kk) {
   return (r >> 3) * 1024u + (r & 7u) * 128u + (((kk >> 4) ^ (r & 7u)) << 4) + (kk & 15u);
 }
 
+// shamirSecretShare + shamirRecoverP in one persistent launch (share_recover.cu).  Lagrange coefficients of the
+// reconstruction as three 21-bit limbs each (l0 + l1*2^21 + l2*2^42), zero beyond n: a kernel parameter, read
+// from the constant bank.
+struct RecBasis61 {
+  uint32_t l[32][3];
+};
+cudaError_t share_recover61_prepare();
+// d_rec_in == d_shares: reconstruct the sharings produced by this launch (tile by tile, as they are stored);
+// otherwise d_rec_in holds another batch of N sharings in the same party-major [n][N] layout.
+cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, const AesKey& key, const RecBasis61& basis,
+                                   const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
+                                   const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
+                                   const uint64_t* d_rec_in, uint64_t* d_rec_out);
+
 cudaError_t share_tc_prepare();
 // variant 1: A in shared memory, 3 groups; variants >= 2: A in tensor memory with
 // (groups, accumulators per group, columns per MMA pass) as listed in share_tc.cu

@@ -103,6 +103,40 @@ def test_survey_sum_of_1023_calls(ctx, port, golden):
     assert sum(ints(port, sh[1:], 61)) % P[61] == int(golden["survey_sum_1023"], 16) == 0x44672D90DD13206
 
 
+@pytest.mark.parametrize("t,n,N", [(15, 32, 1 << 16), (15, 32, 1000), (2, 5, (1 << 15) + 77), (0, 1, 7), (1, 3, 33),
+                                   (7, 16, 129), (15, 31, 4097), (6, 13, 100000), (16, 33, 257)])
+def test_fused_share_recover_vs_oracle(ctx, orc, t, n, N):
+    """sclgpu_fp61_shamir_share_recover_dev (k_share_recover61: share groups + reconstruction warps in one persistent
+    launch): the share planes and the reconstructed secrets against the oracle, in the dependent mode (the tiles this
+    launch stores are read back by the same CTA) and in the independent mode (another batch's planes)."""
+    import torch
+    secrets = orc.vector_random(61, "secrets", 3, N)
+    first = 77
+    want = orc.shamir_share(61, secrets, t, n, "shamir bench", first)          # [N][n]
+    d_sec = torch.from_numpy(secrets.view(np.int64)).cuda()
+    d_sh = torch.zeros((n, N), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros(N, dtype=torch.int64, device="cuda")
+    ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", first, d_sh, d_out)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, want)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), orc.recover_p(61, want))
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), secrets)
+    # independent mode: reconstruct ANOTHER batch (arbitrary canonical words, not a sharing) while sharing this one
+    other = orc.vector_random(61, "other planes", 0, N * n).reshape(N, n)
+    d_other = torch.from_numpy(np.ascontiguousarray(other.T).view(np.int64)).cuda()
+    d_sh.zero_()
+    d_out.zero_()
+    ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", first, d_sh, d_out, rec_shares=d_other)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, want)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), orc.recover_p(61, other))
+    # custom nodes / evaluation point
+    alphas = orc.from_ints([3 * i + 2 for i in range(n)], 61)
+    ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", first, d_sh, d_out, rec_shares=d_other, alphas=alphas, x=5)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), orc.recover_p(61, other, alphas=alphas, x=5))
+
+
 @pytest.mark.parametrize("field,t,n,N", [
     (61, 2, 5, 1 << 16), (61, 15, 32, 1 << 14), (61, 15, 32, 1000), (61, 0, 1, 7), (61, 1, 3, 33),
     (61, 16, 33, 257), (61, 17, 40, 129), (61, 31, 64, 65), (61, 3, 70000 // 1000, 100),

@@ -28,6 +28,14 @@ def main():
     res["share_ms"] = timeit(lambda: ctx.shamir_share_dev(61, d_sec, N, t, n, "shamir bench", 0, d_sh, B.PARTY_MAJOR))
     res["recover_ms"] = timeit(lambda: ctx.recover_p_dev(61, d_sh, N, n, d_out, B.PARTY_MAJOR))
     res["ok"] = bool(torch.equal(d_out, d_sec))
+    d_out.zero_()
+    res["fused_step_ms"] = timeit(lambda: ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", 0, d_sh, d_out))
+    res["fused_ok"] = bool(torch.equal(d_out, d_sec))
+    d_sh2 = d_sh.clone()
+    d_out.zero_()
+    res["fused_indep_ms"] = timeit(lambda: ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", 0, d_sh, d_out, rec_shares=d_sh2))
+    res["fused_indep_ok"] = bool(torch.equal(d_out, d_sec))
+    del d_sh2
     res["random_ms"] = timeit(lambda: ctx.random_dev(61, "prg bench", 0, N, d_out))
     print(json.dumps(res))
 main()
