@@ -143,6 +143,26 @@ int sclgpu_fp61_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const uint64_t* d_coeff
 int sclgpu_fp127_shamir_share_coeffs_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N,
                                          uint32_t t, uint32_t n, void* d_shares, int layout);
 
+/* ---- shamirRecoverP fused with the all-gather of its result (batch sharded over the
+ * GPUs of a box, "gather reconstructed values").  This rank reconstructs its N sharings
+ * (party-major planes [n][N]) and the kernel stores secret j into EVERY destination:
+ * d_dsts[r][offset + j], r < n_dsts <= 8, where d_dsts[r] is rank r's copy of the gathered
+ * vector as addressable from this device (own memory or peer memory over NVLink).  No
+ * collective call, no staging buffer: the stores are posted while the planes are read.
+ * Completion: when every rank's stream has finished its call (barrier + sclgpu_sync). */
+int sclgpu_fp61_recover_p_gather_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N, uint32_t n,
+                                     const uint64_t* alphas, const uint64_t* x, uint64_t* const* d_dsts,
+                                     uint32_t n_dsts, uint64_t offset);
+/* Peer-memory plumbing.  One process per GPU: sclgpu_ipc_export the 64-byte handle of a
+ * sclgpu_malloc'ed buffer, hand it to the other processes, sclgpu_ipc_open it there
+ * (cudaIpcOpenMemHandle with lazy peer access), sclgpu_ipc_close when done.  One process
+ * driving several GPUs: sclgpu_enable_peer(ctx, other_device). */
+int sclgpu_memcpy_d2d(sclgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes); /* stream-ordered, peer memory included */
+int sclgpu_ipc_export(sclgpu_ctx* ctx, void* d_ptr, uint8_t handle[64]);
+int sclgpu_ipc_open(sclgpu_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int sclgpu_ipc_close(sclgpu_ctx* ctx, void* d_ptr);
+int sclgpu_enable_peer(sclgpu_ctx* ctx, int peer_device);
+
 /* ---- the C2 step in one launch: N x { ss::shamirSecretShare (shamir.h:52-68),
  * ss::shamirRecoverP (shamir.h:82-104) } on party-major planes ([n][N]; plane i = what
  * party i holds).  The share groups of the tcgen05 share kernel (limited by the
@@ -411,6 +431,61 @@ int sclgpu_fp127_transpose_dev(sclgpu_ctx* ctx, const void* d_in, uint64_t rows,
  * LOP3 (kind 2), IADD3 (kind 3) or LDS.32 (kind 4) warp instructions per warp on every SM and
  * returns the achieved thread-level operations per second in *ops_per_s. */
 int sclgpu_pipe_microbench(sclgpu_ctx* ctx, int kind, uint32_t iters, double* ops_per_s);
+
+/* ---- several GPUs behind one handle (SCL is one process, one thread:
+ * coro/runtime.h:126-163).  A batch call cuts [0, N) into contiguous slices, one per device,
+ * slice g starting its PRG at first_block + lo_g * B with the same seed, so the results are
+ * what N calls on ONE scl::util::PRG return; one worker thread per device runs the
+ * single-device host pipeline on its slice of the caller's buffers.  devices == NULL means
+ * 0..n_devices-1.  Fails as a whole (no partial device set, no CPU fallback). */
+typedef struct sclgpu_mctx sclgpu_mctx;
+int sclgpu_multi_init(const int* devices, int n_devices, sclgpu_mctx** mctx);
+void sclgpu_multi_destroy(sclgpu_mctx* mctx);
+int sclgpu_multi_device_count(const sclgpu_mctx* mctx);
+sclgpu_ctx* sclgpu_multi_context(sclgpu_mctx* mctx, int index); /* the per-device context (borrowed) */
+const char* sclgpu_multi_last_error(const sclgpu_mctx* mctx);
+/* same contracts as the single-device host entry points of the same name */
+int sclgpu_multi_fp61_shamir_share(sclgpu_mctx* mctx, const uint64_t* secrets, uint64_t N, uint32_t t,
+                                   uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                   uint64_t* shares);
+int sclgpu_multi_fp127_shamir_share(sclgpu_mctx* mctx, const void* secrets, uint64_t N, uint32_t t,
+                                    uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                    void* shares);
+int sclgpu_multi_fp61_recover_p(sclgpu_mctx* mctx, const uint64_t* shares, uint64_t N, uint32_t n,
+                                const uint64_t* alphas, const uint64_t* x, uint64_t* out);
+int sclgpu_multi_fp127_recover_p(sclgpu_mctx* mctx, const void* shares, uint64_t N, uint32_t n,
+                                 const void* alphas, const void* x, void* out);
+int sclgpu_multi_fp61_recover_d(sclgpu_mctx* mctx, const uint64_t* shares, uint64_t N, uint32_t n_given,
+                                uint32_t t, const uint64_t* alphas, uint32_t n_alphas, uint32_t d,
+                                const uint64_t* x, uint64_t* out, uint8_t* err, uint64_t* n_detected);
+int sclgpu_multi_fp127_recover_d(sclgpu_mctx* mctx, const void* shares, uint64_t N, uint32_t n_given,
+                                 uint32_t t, const void* alphas, uint32_t n_alphas, uint32_t d,
+                                 const void* x, void* out, uint8_t* err, uint64_t* n_detected);
+int sclgpu_multi_fp61_random(sclgpu_mctx* mctx, const uint8_t seed[16], uint64_t first_block, uint64_t n,
+                             uint64_t* out);
+
+/* ---- asynchronous host calls.  The host entry points return when their last device-to-host
+ * copy has landed; these run the same pipeline on a companion context (own streams and
+ * scratch, same device) from a worker thread and return at once.  One asynchronous call is in
+ * flight per context (a second one first completes the first); sclgpu_wait -- or sclgpu_sync
+ * -- completes it and returns its status.  The caller's buffers must stay valid until then.
+ * Typical use: share_async(batch k) then recover_p(batch k-1) on the same context: shares
+ * travel device-to-host while the previous batch travels host-to-device (PCIe is full duplex). */
+int sclgpu_fp61_shamir_share_async(sclgpu_ctx* ctx, const uint64_t* secrets, uint64_t N, uint32_t t,
+                                   uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                   uint64_t* shares);
+int sclgpu_fp127_shamir_share_async(sclgpu_ctx* ctx, const void* secrets, uint64_t N, uint32_t t,
+                                    uint32_t n, const uint8_t seed[16], uint64_t first_block,
+                                    void* shares);
+int sclgpu_fp61_recover_p_async(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t n,
+                                const uint64_t* alphas, const uint64_t* x, uint64_t* out);
+int sclgpu_fp127_recover_p_async(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint32_t n,
+                                 const void* alphas, const void* x, void* out);
+int sclgpu_wait(sclgpu_ctx* ctx);
+/* the CUDA device index of a context; set the message sclgpu_last_error returns (used by the
+ * layers above the single-device ABI) */
+int sclgpu_device_index(const sclgpu_ctx* ctx, int* device);
+void sclgpu_set_error(sclgpu_ctx* ctx, const char* message);
 
 #ifdef __cplusplus
 }

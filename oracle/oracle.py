@@ -27,6 +27,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("SCL_REFERENCE_ROOT", "/root/reference")
 PORT_SO = os.path.join(HERE, "libscloracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsclref.so")
+REF_SO_V3 = os.path.join(HERE, "_ref", "libsclref_v3.so")  # same sources, -march=x86-64-v3
+REF_FLAGS = {REF_SO: "-O3 -maes -msse4.1", REF_SO_V3: "-O3 -march=x86-64-v3 -maes -mpclmul"}
+
+
+def _cpu_has_v3() -> bool:
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return False
+    return all(f in flags for f in ("avx2", "bmi2", "fma", "aes"))
 
 P61 = (1 << 61) - 1
 P127 = (1 << 127) - 1
@@ -50,7 +60,8 @@ def build_ref(force: bool = False) -> str | None:
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "scl")):
         return REF_SO if os.path.exists(REF_SO) else None
     drv = os.path.join(HERE, "ref_driver.cc")
-    if force or not os.path.exists(REF_SO) or os.path.getmtime(drv) > os.path.getmtime(REF_SO):
+    if (force or not os.path.exists(REF_SO) or not os.path.exists(REF_SO_V3)
+            or os.path.getmtime(drv) > min(os.path.getmtime(REF_SO), os.path.getmtime(REF_SO_V3))):
         subprocess.check_call(["make", "-C", HERE, "ref", f"REF={REFERENCE_ROOT}"], stdout=subprocess.DEVNULL)
     return REF_SO
 
@@ -341,10 +352,13 @@ class RefOracle(_Base):
 
     kind = "reference"
 
-    def __init__(self):
+    def __init__(self, prefer_v3: bool = True):
         so = build_ref()
         if so is None or not os.path.exists(so):
             raise FileNotFoundError("oracle/_ref/libsclref.so not built and /root/reference absent")
+        if prefer_v3 and os.path.exists(REF_SO_V3) and _cpu_has_v3():
+            so = REF_SO_V3
+        self.build_flags = REF_FLAGS.get(so, "?")
         self.lib = C.CDLL(so)
         L = self.lib
         L.sclref_prg_next.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]

@@ -14,4 +14,4 @@ The directory name contains a hyphen, so it is loaded through
 There is no CPU fallback anywhere in this package.
 """
 from . import api, binding, sharding  # noqa: F401
-from .api import Context, CudaError, InvalidArgument, LogicError  # noqa: F401
+from .api import Context, CudaError, InvalidArgument, LogicError, MultiContext  # noqa: F401

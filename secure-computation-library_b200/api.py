@@ -367,6 +367,58 @@ class Context:
         X = from_ints([x or 0], field)
         self._check(self._f(field, "recover_p_dev")(self._ctx, _dp(shares), N, n, layout, _p(A), _p(X), _dp(out)))
 
+    def recover_p_gather_dev(self, shares, N: int, n: int, dst_ptrs, offset: int, alphas=None, x: int | None = None):
+        """Fp61 shamirRecoverP of this rank's N sharings (party-major planes), result j stored to dst_ptrs[r] + 8*(offset + j)
+        for every r: the all-gather over peer memory happens inside the reconstruction kernel.  dst_ptrs: device
+        addresses (ints) valid on this device -- own memory or peer memory (malloc / ipc_export / ipc_open)."""
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], 61)
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+        self._check(self.lib.sclgpu_fp61_recover_p_gather_dev(self._ctx, _dp(shares), N, n, _p(A), _p(X), arr, len(dst_ptrs), offset))
+
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.sclgpu_malloc(self._ctx, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def free(self, ptr: int):
+        self._check(self.lib.sclgpu_free(self._ctx, C.c_void_p(ptr)))
+
+    def memcpy_d2d(self, dst: int, src: int, nbytes: int):
+        self._check(self.lib.sclgpu_memcpy_d2d(self._ctx, C.c_void_p(dst), C.c_void_p(src), nbytes))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._check(self.lib.sclgpu_ipc_export(self._ctx, C.c_void_p(ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.lib.sclgpu_ipc_open(self._ctx, h, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self.lib.sclgpu_ipc_close(self._ctx, C.c_void_p(ptr)))
+
+    def enable_peer(self, peer_device: int):
+        self._check(self.lib.sclgpu_enable_peer(self._ctx, int(peer_device)))
+
+    # ------------------------------------------------------------ asynchronous host calls
+    def shamir_share_async(self, field: int, secrets: np.ndarray, t: int, n: int, seed, first_block: int, out: np.ndarray):
+        """sclgpu_*_shamir_share_async: returns at once; `secrets` / `out` (caller-owned, e.g. pinned) must stay alive
+        until wait() / sync()."""
+        N = _nelem(secrets, field)
+        self._check(self._f(field, "shamir_share_async")(self._ctx, _p(secrets), N, t, n, seed16(seed), first_block, _p(out)))
+
+    def recover_p_async(self, field: int, shares: np.ndarray, N: int, n: int, out: np.ndarray, alphas=None, x: int | None = None):
+        A = None if alphas is None else _c(alphas)
+        X = None if alphas is None else from_ints([x or 0], field)
+        self._check(self._f(field, "recover_p_async")(self._ctx, _p(shares), N, n, _p(A), _p(X), _p(out)))
+
+    def wait(self):
+        self._check(self.lib.sclgpu_wait(self._ctx))
+
     def recover_d(self, field: int, shares, t: int, alphas=None, d: int | None = None, x: int | None = None):
         """-> (secrets, err uint8[N], rc) with rc = -1 for "not enough shares provided to
         detect errors", else the number of secrets flagged (oracle-compatible)."""
@@ -475,3 +527,82 @@ class Context:
 
     def transpose_dev(self, field: int, src, rows: int, cols: int, dst):
         self._check(self._f(field, "transpose_dev")(self._ctx, _dp(src), rows, cols, _dp(dst)))
+
+
+class MultiContext:
+    """sclgpu_mctx: several GPUs of one box behind one handle, for a single-process caller.  Host arrays in SCL's
+    layout; [0, N) is cut into contiguous slices, one per device, PRG counters offset to match."""
+
+    def __init__(self, devices):
+        self.lib = B.load()
+        devs = list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        self._m = C.c_void_p()
+        rc = self.lib.sclgpu_multi_init(arr, len(devs), C.byref(self._m))
+        if rc != B.OK:
+            self._m = None
+            raise CudaError(f"sclgpu_multi_init({devs}) failed: {self.lib.sclgpu_strerror(rc).decode()} (no CPU fallback)")
+        self.devices = devs
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self.lib.sclgpu_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow=()):
+        if rc == B.OK or rc in allow:
+            return rc
+        msg = self.lib.sclgpu_multi_last_error(self._m).decode(errors="replace")
+        if rc == B.EINVAL:
+            raise InvalidArgument(msg)
+        if rc in (B.ELOGIC, B.EDETECT, B.ECORRECT):
+            raise LogicError(msg)
+        raise CudaError(f"{self.lib.sclgpu_strerror(rc).decode()}: {msg}")
+
+    def _f(self, field: int, name: str):
+        return getattr(self.lib, f"sclgpu_multi_{_SUF[field]}_{name}")
+
+    def random(self, seed, first_block: int, n: int) -> np.ndarray:
+        out = empty(61, n)
+        self._check(self.lib.sclgpu_multi_fp61_random(self._m, seed16(seed), first_block, n, _p(out)))
+        return out
+
+    def shamir_share(self, field: int, secrets, t: int, n: int, seed, first_block: int = 0, out=None) -> np.ndarray:
+        secrets = _c(secrets)
+        N = _nelem(secrets, field)
+        if out is None:
+            out = empty(field, N, n)
+        self._check(self._f(field, "shamir_share")(self._m, _p(secrets), N, t, n, seed16(seed), first_block, _p(out)))
+        return out
+
+    def recover_p(self, field: int, shares, alphas=None, x: int | None = None, out=None) -> np.ndarray:
+        shares = _c(shares)
+        N, n = shares.shape[0], shares.shape[1]
+        if out is None:
+            out = empty(field, N)
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], field)
+        self._check(self._f(field, "recover_p")(self._m, _p(shares), N, n, _p(A), _p(X), _p(out)))
+        return out
+
+    def recover_d(self, field: int, shares, t: int, alphas=None, d: int | None = None, x: int | None = None):
+        shares = _c(shares)
+        N, n_given = shares.shape[0], shares.shape[1]
+        out = empty(field, N)
+        err = np.zeros(N, dtype=np.uint8)
+        A = None if alphas is None else _c(alphas)
+        n_alphas = 0 if A is None else _nelem(A, field)
+        X = from_ints([x or 0], field)
+        nd = C.c_uint64(0)
+        rc = self._f(field, "recover_d")(self._m, _p(shares), N, n_given, t, _p(A), n_alphas, d if d is not None else t,
+                                          _p(X), _p(out), _p(err), C.byref(nd))
+        if rc == B.ELOGIC:
+            return out, err, -1
+        self._check(rc, allow=(B.EDETECT,))
+        return out, err, int(nd.value)

@@ -111,6 +111,27 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_vandermonde", _int, _vp, _u32, _u32, _vp)
         _sig(lib, f"sclgpu_{f}_transpose_dev", _int, _vp, _vp, _u64, _u64, _vp)
     _sig(lib, "sclgpu_fp61_shamir_share_recover_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp)
+    _sig(lib, "sclgpu_fp61_recover_p_gather_dev", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _u32, _u64)
+    _sig(lib, "sclgpu_memcpy_d2d", _int, _vp, _vp, _vp, C.c_size_t)
+    _sig(lib, "sclgpu_ipc_export", _int, _vp, _vp, _vp)
+    _sig(lib, "sclgpu_ipc_open", _int, _vp, _vp, C.POINTER(_vp))
+    _sig(lib, "sclgpu_ipc_close", _int, _vp, _vp)
+    _sig(lib, "sclgpu_enable_peer", _int, _vp, _int)
+    _sig(lib, "sclgpu_multi_init", _int, _vp, _int, C.POINTER(_vp))
+    _sig(lib, "sclgpu_multi_destroy", None, _vp)
+    _sig(lib, "sclgpu_multi_device_count", _int, _vp)
+    _sig(lib, "sclgpu_multi_context", _vp, _vp, _int)
+    _sig(lib, "sclgpu_multi_last_error", C.c_char_p, _vp)
+    _sig(lib, "sclgpu_multi_fp61_random", _int, _vp, _vp, _u64, _u64, _vp)
+    for f in ("fp61", "fp127"):
+        _sig(lib, f"sclgpu_multi_{f}_shamir_share", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
+        _sig(lib, f"sclgpu_multi_{f}_recover_p", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp)
+        _sig(lib, f"sclgpu_multi_{f}_recover_d", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u64))
+        _sig(lib, f"sclgpu_{f}_shamir_share_async", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp)
+        _sig(lib, f"sclgpu_{f}_recover_p_async", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp)
+    _sig(lib, "sclgpu_wait", _int, _vp)
+    _sig(lib, "sclgpu_device_index", _int, _vp, C.POINTER(_int))
+    _sig(lib, "sclgpu_set_error", None, _vp, C.c_char_p)
     _sig(lib, "sclgpu_packet_bytes", _u64, _u32, _u64)
     _sig(lib, "sclgpu_share_array_blocks", _u64, _u32, _u32, _u32)
     _sig(lib, "sclgpu_pipe_microbench", _int, _vp, _int, _u32, C.POINTER(C.c_double))

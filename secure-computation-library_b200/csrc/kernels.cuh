@@ -890,10 +890,18 @@ __device__ __forceinline__ uint64_t f61_rot(uint64_t acc, int s) {  // acc * 2^s
   return s == 0 ? x : (((x << s) & F61::P) | (x >> (61 - s)));
 }
 
+// Destinations of the reconstructed secrets when the result is gathered while it is produced: dst[r] is where THIS
+// rank's slice starts inside rank r's copy of the gathered vector (dst[self] = local memory, the others peer memory
+// mapped over NVLink: cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess).  count == 0: plain `out`.
+struct GatherDst {
+  uint64_t* dst[8];
+  uint32_t count;
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_recover61_pm(const uint64_t* __restrict__ in, uint64_t N, uint32_t n, uint64_t stride_i,
-               const uint64_t* __restrict__ basis, uint64_t* __restrict__ out) {
+               const uint64_t* __restrict__ basis, uint64_t* __restrict__ out, const __grid_constant__ GatherDst gather) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   uint4* lb = reinterpret_cast<uint4*>(dyn_smem);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -955,10 +963,24 @@ k_recover61_pm(const uint64_t* __restrict__ in, uint64_t N, uint32_t n, uint64_t
                          f61_rot(acc[s][3], 32) + f61_rot(acc[s][4], 53) + f61_rot(acc[s][5], 13);  // < 2^64
       r[s] = F61::from_raw(t);
     }
-    if constexpr (VEC == 2) {
-      reinterpret_cast<ulonglong2*>(out)[u] = make_ulonglong2(r[0], r[1]);
+    if (gather.count == 0) {
+      if constexpr (VEC == 2) {
+        reinterpret_cast<ulonglong2*>(out)[u] = make_ulonglong2(r[0], r[1]);
+      } else {
+        out[u] = r[0];
+      }
     } else {
-      out[u] = r[0];
+      // all-gather fused into the reconstruction: the result goes to every rank's copy (posted stores over NVLink)
+#pragma unroll
+      for (uint32_t g = 0; g < 8u; ++g) {
+        if (g < gather.count) {
+          if constexpr (VEC == 2) {
+            reinterpret_cast<ulonglong2*>(gather.dst[g])[u] = make_ulonglong2(r[0], r[1]);
+          } else {
+            gather.dst[g][u] = r[0];
+          }
+        }
+      }
     }
   }
 }

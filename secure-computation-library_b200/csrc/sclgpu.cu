@@ -237,8 +237,13 @@ extern "C" int sclgpu_init(int device, sclgpu_ctx** out) {
   return SCLGPU_OK;
 }
 
+// multi.cu: completion / teardown of this context's asynchronous call, if any
+int sclgpu_async_complete(sclgpu_ctx* ctx, const char** error);
+void sclgpu_async_release(sclgpu_ctx* ctx);
+
 extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
   if (!ctx) return;
+  sclgpu_async_release(ctx);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
@@ -263,9 +268,20 @@ extern "C" int sclgpu_set_stream(sclgpu_ctx* ctx, void* s) {
 }
 extern "C" int sclgpu_sync(sclgpu_ctx* ctx) {
   if (!ctx) return SCLGPU_EINVAL;
+  const char* aerr = nullptr;
+  const int arc = sclgpu_async_complete(ctx, &aerr);  // a pending *_async call finishes here
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (arc != SCLGPU_OK) return fail(ctx, arc, aerr ? aerr : "asynchronous call failed");
   return SCLGPU_OK;
+}
+extern "C" int sclgpu_device_index(const sclgpu_ctx* ctx, int* device) {
+  if (!ctx || !device) return SCLGPU_EINVAL;
+  *device = ctx->device;
+  return SCLGPU_OK;
+}
+extern "C" void sclgpu_set_error(sclgpu_ctx* ctx, const char* msg) {
+  if (ctx) ctx->last_error = msg ? msg : "";
 }
 extern "C" const char* sclgpu_last_error(const sclgpu_ctx* ctx) {
   return ctx ? ctx->last_error.c_str() : "no context";
@@ -332,6 +348,13 @@ extern "C" int sclgpu_memcpy_d2h(sclgpu_ctx* ctx, void* h, const void* d, size_t
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return SCLGPU_OK;
+}
+
+extern "C" int sclgpu_memcpy_d2d(sclgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));  // also peer memory (UVA)
   return SCLGPU_OK;
 }
 
@@ -727,25 +750,30 @@ static int recover_d_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
 template <class F>
 static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_shares, uint64_t N,
                         uint32_t n, uint64_t si, uint64_t sj, const typename F::E* d_basis,
-                        typename F::E* d_out) {
+                        typename F::E* d_out, const GatherDst* gather = nullptr) {
   if (N == 0) return SCLGPU_OK;
+  GatherDst gd;
+  std::memset(&gd, 0, sizeof(gd));
+  if (gather) gd = *gather;
   if constexpr (F::BYTES == 8) {
     // party-major planes, the device-native layout: HBM-bound kernel
     if (env_flag("SCLGPU_RECOVER61_TC") && recover_d_tc_fits<F>(n, 0))
       return recover_d_on<F>(ctx, st, d_shares, N, si, sj, n, 0, d_basis, d_out, nullptr);
     if (sj == 1 && n >= 1 && n <= 2048 && !env_flag("SCLGPU_RECOVER_GENERIC")) {
-      const bool vec2 = (N % 2 == 0) && (si % 2 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(d_shares) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+      uintptr_t align = reinterpret_cast<uintptr_t>(d_shares) | reinterpret_cast<uintptr_t>(d_out);
+      for (uint32_t g = 0; g < gd.count; ++g) align |= reinterpret_cast<uintptr_t>(gd.dst[g]);
+      const bool vec2 = (N % 2 == 0) && (si % 2 == 0) && (align & 15) == 0;
       const size_t lsm = (size_t)n * 16;
       if (vec2) {
-        k_recover61_pm<2><<<std::min(grid_for(ctx, N / 2, 256, 3), 3 * std::max(1, env_int("SCLGPU_RECOVER_SMS", ctx->sm_count))), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
+        k_recover61_pm<2><<<std::min(grid_for(ctx, N / 2, 256, 3), 3 * std::max(1, env_int("SCLGPU_RECOVER_SMS", ctx->sm_count))), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out, gd);
       } else {
-        k_recover61_pm<1><<<grid_for(ctx, N, 256, 4), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out);
+        k_recover61_pm<1><<<grid_for(ctx, N, 256, 4), 256, lsm, st>>>(d_shares, N, n, si, d_basis, d_out, gd);
       }
       CKL();
       return SCLGPU_OK;
     }
   }
+  if (gd.count) return fail(ctx, SCLGPU_EINVAL, "gathered reconstruction needs party-major Fp61 planes");
   if constexpr (F::BYTES == 16) {
     // Fp127: the inner product as a one-row limb product on the tensor cores (k_recover_d_tc without checks)
     if (recover_d_tc_fits<F>(n, 0) && !env_flag("SCLGPU_RECOVER_GENERIC"))
@@ -1553,6 +1581,72 @@ extern "C" int sclgpu_fp127_recover_p(sclgpu_ctx* c, const void* s, uint64_t N, 
 extern "C" int sclgpu_fp61_recover_p_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, int layout, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return recover_p_dev<F61>(c, s, N, n, layout, a, x, o); }); }
 extern "C" int sclgpu_fp127_recover_p_dev(sclgpu_ctx* c, const void* s, uint64_t N, uint32_t n, int layout, const void* a, const void* x, void* o) { return guarded(c, [&] { return recover_p_dev<F127>(c, s, N, n, layout, a, x, o); }); }
 
+// ------------------------------------------------------------------ recover P + all-gather over peer memory
+// shamirRecoverP of this rank's slice of a batch, the result written straight into EVERY rank's copy of the
+// gathered vector ("gather reconstructed values"): d_dsts[r] = base of rank r's gathered buffer as
+// mapped on this device (its own cudaMalloc memory for r = self, peer memory for the others, sclgpu_ipc_open /
+// sclgpu_enable_peer), and element j of the slice goes to d_dsts[r][offset + j].  One kernel: the NVLink stores
+// are posted while the planes are still being read -- no separate collective, no staging copy.
+static int recover_p_gather61_dev(sclgpu_ctx* ctx, const uint64_t* d_shares, uint64_t N, uint32_t n, const uint64_t* alphas,
+                                  const uint64_t* x, uint64_t* const* d_dsts, uint32_t n_dsts, uint64_t offset) {
+  if (!ctx || (!d_shares && n && N) || !d_dsts) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (n_dsts < 1 || n_dsts > 8) return fail(ctx, SCLGPU_EINVAL, "1..8 gather destinations");
+  for (uint32_t r = 0; r < n_dsts; ++r)
+    if (!d_dsts[r]) return fail(ctx, SCLGPU_EINVAL, "null gather destination");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0) return SCLGPU_OK;
+  const uint64_t* d_basis = nullptr;
+  RET(recover_p_basis<F61>(ctx, ctx->stream, n, alphas, x, &d_basis));
+  GatherDst gd;
+  std::memset(&gd, 0, sizeof(gd));
+  gd.count = n_dsts;
+  for (uint32_t r = 0; r < n_dsts; ++r) gd.dst[r] = d_dsts[r] + offset;
+  return recover_p_on<F61>(ctx, ctx->stream, d_shares, N, n, N, 1, d_basis, gd.dst[0], &gd);
+}
+extern "C" int sclgpu_fp61_recover_p_gather_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t n, const uint64_t* a, const uint64_t* x, uint64_t* const* d, uint32_t nd, uint64_t off) { return guarded(c, [&] { return recover_p_gather61_dev(c, s, N, n, a, x, d, nd, off); }); }
+
+// Peer memory plumbing for the call above.  One process per GPU: export the handle of a sclgpu_malloc'ed buffer,
+// pass the 64 bytes to the other ranks by any means (torch.distributed, MPI, a socket), open it there.
+extern "C" int sclgpu_ipc_export(sclgpu_ctx* ctx, void* d_ptr, uint8_t handle[64]) {
+  if (!ctx || !d_ptr || !handle) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, d_ptr));
+  std::memcpy(handle, &h, 64);
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_ipc_open(sclgpu_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+  if (!ctx || !d_ptr || !handle) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_ipc_close(sclgpu_ctx* ctx, void* d_ptr) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaIpcCloseMemHandle(d_ptr));
+  return SCLGPU_OK;
+}
+// Single process driving several GPUs: let this context's device address memory of `peer_device` directly.
+extern "C" int sclgpu_enable_peer(sclgpu_ctx* ctx, int peer_device) {
+  if (!ctx) return SCLGPU_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (peer_device == ctx->device) return SCLGPU_OK;
+  int can = 0;
+  CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+  if (!can) return fail(ctx, SCLGPU_ECUDA, "devices cannot access each other's memory");
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return SCLGPU_OK;
+  }
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaDeviceEnablePeerAccess");
+  return SCLGPU_OK;
+}
+
 // ------------------------------------------------------------------ share + recover P in one launch
 // N x { shamirSecretShare (shamir.h:52-68), shamirRecoverP (shamir.h:82-104) } on party-major planes.  With
 // d_rec_shares == d_shares the sharings produced by this call are reconstructed (the round trip of one batch);
@@ -1600,7 +1694,7 @@ static int share_recover61_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint6
   RET(share_tc_bmat<F61>(ctx, st, t, n, &d_bmat));
   const AesKey key = aes_expand(seed);
   ctx->launches++;
-  cudaError_t e = share_recover61_launch(st, ctx->sm_count, key, it->second, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n,
+  cudaError_t e = share_recover61_launch(st, ctx->sm_count, env_int("SCLGPU_SR_WARPS", 4), key, it->second, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n,
                                          d_shares, d_rec_shares, d_out);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
   return SCLGPU_OK;

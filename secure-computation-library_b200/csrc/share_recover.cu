@@ -282,23 +282,30 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
   }
 }
 
-static constexpr int kSrGroups = 5, kSrWarps = 8;
+static constexpr int kSrGroups = 5;
 
 cudaError_t share_recover61_prepare() {
-  return cudaFuncSetAttribute(k_share_recover61<kSrGroups, kSrWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)kSrDynSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_share_recover61<kSrGroups, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_share_recover61<kSrGroups, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
+  return e;
 }
 
-cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, const AesKey& key, const RecBasis61& basis,
+cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int rec_warps, const AesKey& key, const RecBasis61& basis,
                                    const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
                                    const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
                                    const uint64_t* d_rec_in, uint64_t* d_rec_out) {
   const uint64_t tiles = (N + 127) / 128;
   const int grid = (int)std::min<uint64_t>((tiles + kSrGroups - 1) / kSrGroups, (uint64_t)sm_count);
   const uint32_t dependent = (d_rec_in == d_shares) ? 1u : 0u;
-  k_share_recover61<kSrGroups, kSrWarps><<<grid, 128 * kSrGroups + 32 * kSrWarps, kSrDynSmem, st>>>(
-      key, basis, d_t0, reinterpret_cast<const uint4*>(d_bmat), first_block, d_secrets, N, t, n, d_shares, d_rec_in,
-      d_rec_out, dependent);
+  const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
+  if (rec_warps == 4) {
+    k_share_recover61<kSrGroups, 4><<<grid, 128 * kSrGroups + 128, kSrDynSmem, st>>>(
+        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent);
+  } else {
+    k_share_recover61<kSrGroups, 8><<<grid, 128 * kSrGroups + 256, kSrDynSmem, st>>>(
+        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent);
+  }
   return cudaGetLastError();
 }
 

@@ -3,7 +3,9 @@ oracle on rank 0:
   * batch-sharded shamirSecretShare / shamirRecoverP with the PRG counter offset per rank, secrets gathered;
   * recoverD error counts summed over ranks;
   * batch-sharded sharing of math::Array<Fp61, 2> pairs (Pedersen's sharing step), shares gathered;
-  * C5: row-sharded Fp61 mat-vec with the all-gather of the y slices (sharding.matvec_row_sharded).
+  * C5: row-sharded Fp61 mat-vec with the all-gather of the y slices (sharding.matvec_row_sharded);
+  * shamirRecoverP with the all-gather fused into the kernel (stores to peer memory, sclgpu_ipc_*), every rank's copy;
+  * the multi-device handle (sclgpu_mctx) driven by one process over all the GPUs.
 Run by tests/test_gpu_parity.py::test_multi_gpu_nccl when at least two GPUs are visible."""
 import os
 import sys
@@ -87,6 +89,52 @@ def main():
         A = port.vector_random(61, "mat A", 0, rows * cols).reshape(rows, cols)
         x = port.vector_random(61, "vec x", 0, cols)
         assert np.array_equal(y.cpu().numpy().view(np.uint64), port.matvec(61, A, x)), "row-sharded mat-vec differs"
+    # ---- shamirRecoverP fused with the all-gather of its result: stores to every rank's buffer over peer memory
+    Ng = 40000
+    sg = sh.shard_range(Ng, world, rank, align=2)
+    d_gsec = torch.empty(sg.count, dtype=torch.int64, device=dev)
+    ctx.random_dev(61, "secrets", sh.random_first_block(61, 0, sg), sg.count, d_gsec)
+    d_gsh = torch.empty((n, sg.count), dtype=torch.int64, device=dev)
+    ctx.shamir_share_dev(61, d_gsec, sg.count, t, n, "shamir bench", sh.share_first_block(61, t, 0, sg), d_gsh, B.PARTY_MAJOR)
+    buf = ctx.malloc(8 * Ng)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.ipc_export(buf))
+    peers = [buf if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
+    ctx.recover_p_gather_dev(d_gsh, sg.count, n, peers, sg.lo)
+    torch.cuda.synchronize()
+    dist.barrier()
+    mine = torch.empty(Ng, dtype=torch.int64, device=dev)
+    ctx.memcpy_d2d(mine.data_ptr(), buf, 8 * Ng)
+    torch.cuda.synchronize()
+    assert np.array_equal(mine.cpu().numpy().view(np.uint64), port.vector_random(61, "secrets", 0, Ng)), \
+        "gathered reconstruction differs on rank %d" % rank
+    dist.barrier()
+    for r in range(world):
+        if r != rank:
+            ctx.ipc_close(peers[r])
+    dist.barrier()
+    ctx.free(buf)
+
+    # ---- one process, one handle over all the GPUs (sclgpu_mctx): rank 0 drives, the others wait
+    dist.barrier()
+    if rank == 0:
+        m = pkg.MultiContext(list(range(world)))
+        Nm = 50001
+        secrets = port.vector_random(61, "secrets", 0, Nm)
+        assert np.array_equal(m.random("secrets", 0, Nm), secrets)
+        shm = m.shamir_share(61, secrets, t, n, "shamir bench", 9)
+        want = port.shamir_share(61, secrets, t, n, "shamir bench", 9)
+        assert np.array_equal(shm, want), "multi-device share differs from the one-PRG batch"
+        assert np.array_equal(m.recover_p(61, shm), secrets)
+        s127 = port.vector_random(127, "secrets127", 0, 3001)
+        sh127 = m.shamir_share(127, s127, 7, 16, "m127", 2)
+        assert np.array_equal(sh127, port.shamir_share(127, s127, 7, 16, "m127", 2))
+        sh127[17, 3, 0] ^= np.uint64(1)
+        sh127[2900, 13, 0] ^= np.uint64(1)
+        out, err, nd = m.recover_d(127, sh127, 7)
+        w_out, w_err, w_nd = port.recover_d(127, sh127, 7)
+        assert nd == w_nd == 2 and np.array_equal(err, w_err) and np.array_equal(out, w_out)
+        m.close()
     dist.barrier()
     if rank == 0:
         print(f"DIST_GPU_OK world={world}")

@@ -952,6 +952,78 @@ def test_full_size_c5_matvec_and_muladd(ctx, pkg, port):
     assert torch.equal(lhs, t1)
 
 
+# ------------------------------------------------------------------ gather / multi-device / async on whatever is visible
+@pytest.mark.parametrize("N,n", [(4096, 32), (1001, 5), (2, 3), (100000, 16)])
+def test_recover_p_gather_destinations(ctx, orc, N, n):
+    """sclgpu_fp61_recover_p_gather_dev: the reconstructed secrets land in every destination buffer at the given offset
+    (here: several buffers of the same device; the peer-memory case runs in tests/dist_gpu_worker.py)."""
+    import torch
+    t = (n - 1) // 2
+    secrets = orc.vector_random(61, "secrets", 0, N)
+    want = orc.shamir_share(61, secrets, t, n, "g", 4)
+    d_sh = torch.from_numpy(np.ascontiguousarray(want.T).view(np.int64)).cuda()
+    off = 6
+    bufs = [torch.zeros(N + 16, dtype=torch.int64, device="cuda") for _ in range(3)]
+    ctx.recover_p_gather_dev(d_sh, N, n, [b_.data_ptr() for b_ in bufs], off)
+    torch.cuda.synchronize()
+    for b_ in bufs:
+        h = b_.cpu().numpy().view(np.uint64)
+        assert np.array_equal(h[off:off + N], secrets)
+        assert not h[:off].any() and not h[off + N:].any()
+
+
+def test_multi_context_vs_oracle(pkg, orc):
+    """sclgpu_mctx over every visible GPU (one is enough: the slicing and the PRG offsets are the same code): share,
+    recoverP, recoverD and Vector::random equal the one-PRG batch of the oracle."""
+    import torch
+    g = max(1, min(torch.cuda.device_count(), 8))
+    devs = list(range(g)) if g > 1 else [0, 0, 0]   # one GPU: three slices on the same device
+    m = pkg.MultiContext(devs)
+    try:
+        for N in (0, 1, 2, 5, 1000, 77777):
+            secrets = orc.vector_random(61, "secrets", 0, N)
+            assert np.array_equal(m.random("secrets", 0, N), secrets)
+            sh = m.shamir_share(61, secrets, 15, 32, "shamir bench", 11)
+            assert np.array_equal(sh, orc.shamir_share(61, secrets, 15, 32, "shamir bench", 11))
+            assert np.array_equal(m.recover_p(61, sh), secrets)
+        s127 = orc.vector_random(127, "secrets127", 0, 2049)
+        sh127 = m.shamir_share(127, s127, 7, 16, "m127", 1)
+        assert np.array_equal(sh127, orc.shamir_share(127, s127, 7, 16, "m127", 1))
+        sh127[5, 2, 1] ^= np.uint64(4)
+        sh127[2048, 13, 0] ^= np.uint64(1)
+        sh127[1000, 15, 0] ^= np.uint64(1)   # unchecked index (shamir.h:129)
+        out, err, nd = m.recover_d(127, sh127, 7)
+        w_out, w_err, w_nd = orc.recover_d(127, sh127, 7)
+        assert nd == w_nd == 2 and np.array_equal(err, w_err) and np.array_equal(out, w_out)
+    finally:
+        m.close()
+
+
+def test_async_host_calls(ctx, orc):
+    """share_async(batch k) overlapping recover_p(batch k-1) on one context; results equal the synchronous calls."""
+    N, t, n = 50000, 15, 32
+    secrets = orc.vector_random(61, "secrets", 0, N)
+    want = [orc.shamir_share(61, secrets, t, n, "shamir bench", 100 * k) for k in range(3)]
+    bufs = [np.zeros((N, n), dtype=np.uint64) for _ in range(2)]
+    out = np.zeros(N, dtype=np.uint64)
+    ctx.shamir_share_async(61, secrets, t, n, "shamir bench", 0, bufs[0])
+    ctx.wait()
+    assert np.array_equal(bufs[0], want[0])
+    for k in (1, 2):
+        ctx.shamir_share_async(61, secrets, t, n, "shamir bench", 100 * k, bufs[k & 1])
+        rec = ctx.recover_p(61, bufs[(k - 1) & 1])       # synchronous call on the same context, other batch
+        ctx.wait()
+        assert np.array_equal(rec, secrets)
+        assert np.array_equal(bufs[k & 1], want[k])
+    ctx.recover_p_async(61, bufs[0], N, n, out)
+    ctx.sync()                                            # sync completes the pending asynchronous call too
+    assert np.array_equal(out, secrets)
+    # an error inside the asynchronous call surfaces at wait()
+    with pytest.raises(Exception):
+        ctx.recover_p_async(61, bufs[0], N, n, out, alphas=np.zeros(n, dtype=np.uint64), x=0)   # equal nodes: not invertible
+        ctx.wait()
+
+
 # ------------------------------------------------------------------ several GPUs, NCCL
 def test_multi_gpu_nccl():
     """tests/dist_gpu_worker.py under torchrun, one process per visible GPU (needs >= 2): batch-sharded
