@@ -211,10 +211,17 @@ template <class FF>
 scl::math::Vector<FF> shamirRecoverP(Context& ctx, const std::vector<scl::net::Packet>& packets) {
   using A = detail::Abi<FF>;
   if (packets.empty()) return scl::math::Vector<FF>();
+  if (packets[0].size() < sizeof(std::uint32_t)) throw std::invalid_argument("packet without an element count");
   std::uint32_t count = 0;
   std::memcpy(&count, packets[0].get(), sizeof(count));
   std::vector<const std::uint8_t*> bufs(packets.size());
-  for (std::size_t i = 0; i < packets.size(); ++i) bufs[i] = packets[i].get();
+  for (std::size_t i = 0; i < packets.size(); ++i) {
+    // a packet from another party: it must actually hold the count + count elements it announces before a byte of it
+    // is handed to the DMA engine (Serializer<Vector<FF>>::read would run off its end, vector.h:612-629)
+    if ((std::size_t)packets[i].size() < sizeof(std::uint32_t) + (std::size_t)count * A::BYTES)
+      throw std::invalid_argument("packet shorter than the Vec it announces");
+    bufs[i] = packets[i].get();
+  }
   std::vector<FF> out(count);
   ctx.check(A::recover_p_packets(ctx.get(), bufs.data(), count, (std::uint32_t)packets.size(), nullptr, nullptr,
                                  detail::raw<FF>(out.data())));

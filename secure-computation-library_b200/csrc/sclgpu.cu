@@ -49,6 +49,7 @@ struct sclgpu_ctx {
   std::map<const void*, RecBasis61> rec_basis_cache;  // Lagrange basis (device) -> 21-bit limbs for k_share_recover61
   bool tc_prepared = false;
   bool sr_prepared = false;
+  cudaMemPool_t mempool = nullptr;    // private stream-ordered pool of the _dev entry points' scratch
   // device scratch of the host-pointer entry points (chunk buffers), kept across calls: a cudaMalloc /
   // cudaFree pair per buffer per call costs milliseconds and a device synchronisation
   std::vector<std::pair<void*, size_t>> pool;
@@ -196,7 +197,12 @@ static int aes_opt_in(sclgpu_ctx* ctx, K kernel) {
 extern "C" int sclgpu_init(int device, sclgpu_ctx** out) {
   if (!out) return SCLGPU_EINVAL;
   *out = nullptr;
-  sclgpu_ctx* ctx = new sclgpu_ctx();
+  sclgpu_ctx* ctx = nullptr;
+  try {
+    ctx = new sclgpu_ctx();
+  } catch (...) {
+    return SCLGPU_ENOMEM;
+  }
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
@@ -213,11 +219,20 @@ extern "C" int sclgpu_init(int device, sclgpu_ctx** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   aes_host_init();
-  {  // stream-ordered scratch (cudaMallocAsync in matmul_on) stays cached in the device's pool between calls
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+  {  // stream-ordered scratch of the _dev entry points: a PRIVATE pool that keeps its memory between calls (the
+     // device's default pool -- shared with every other cudaMallocAsync user of the process -- is left alone)
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&ctx->mempool, &props) == cudaSuccess) {
       uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaMemPoolSetAttribute(ctx->mempool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      ctx->mempool = nullptr;
+      cudaGetLastError();
     }
   }
   bool ok = cudaMalloc(&ctx->d_t0, sizeof(g_t0)) == cudaSuccess &&
@@ -254,6 +269,7 @@ extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
     if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
     if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
   }
+  if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
   cudaFree(ctx->d_t0);
   cudaFree(ctx->d_flag);
   cudaFree(ctx->d_count);
@@ -374,14 +390,18 @@ struct DevBuf {
 // and no call pays a cudaMalloc / cudaFree pair (milliseconds, and a device-wide synchronisation).
 struct StreamBuf {
   void* p = nullptr;
+  sclgpu_ctx* ctx;
   cudaStream_t st;
-  explicit StreamBuf(cudaStream_t s) : st(s) {}
+  StreamBuf(sclgpu_ctx* c, cudaStream_t s) : ctx(c), st(s) {}
   StreamBuf(const StreamBuf&) = delete;
   StreamBuf& operator=(const StreamBuf&) = delete;
   ~StreamBuf() {
     if (p) cudaFreeAsync(p, st);
   }
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+  cudaError_t alloc(size_t bytes) {
+    if (ctx && ctx->mempool) return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, ctx->mempool, st);
+    return cudaMallocAsync(&p, bytes ? bytes : 1, st);
+  }
   template <class T>
   T* as() { return reinterpret_cast<T*>(p); }
 };
@@ -396,7 +416,13 @@ struct PoolScope {
     if (ctx) ctx->pool_next = 0;
   }
   ~PoolScope() {
-    if (g_pool_ctx) g_pool_ctx->stager.drain();  // error paths: no staged copy outlives the call
+    if (g_pool_ctx) {
+      // error paths: nothing enqueued by the call -- kernels, async copies into the caller's buffers, staged copies --
+      // outlives it (on the success path the streams are already idle and this costs nothing)
+      cudaStreamSynchronize(g_pool_ctx->pipe[0]);
+      cudaStreamSynchronize(g_pool_ctx->pipe[1]);
+      g_pool_ctx->stager.drain();
+    }
     g_pool_ctx = nullptr;
   }
 };
@@ -658,7 +684,7 @@ static int share_strided_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::
   uint64_t chunk = (1ull << 30) / ((uint64_t)(t + 1) * sizeof(E));
   if (chunk < 1024) chunk = 1024;
   if (chunk > N) chunk = N;
-  StreamBuf planes(st);
+  StreamBuf planes(ctx, st);
   CK(planes.alloc(chunk * (uint64_t)(t + 1) * sizeof(E)));
   RET(aes_opt_in(ctx, k_expand_coeffs<F>));
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
@@ -779,8 +805,10 @@ static int recover_p_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     if (recover_d_tc_fits<F>(n, 0) && !env_flag("SCLGPU_RECOVER_GENERIC"))
       return recover_d_on<F>(ctx, st, d_shares, N, si, sj, n, 0, d_basis, d_out, nullptr);
   }
+  // basis staged in shared memory: up to 200 KiB (n <= 25600 for Fp61, 12800 for Fp127; documented in sclgpu.h)
   const size_t smem = (size_t)n * sizeof(typename F::E);
-  if (smem > 48 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_p: more than 48 KiB of basis");
+  if (smem > 200 * 1024) return fail(ctx, SCLGPU_EINVAL, "recover_p: more than 200 KiB of Lagrange basis");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_recover_p<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_recover_p<F><<<grid_for(ctx, N, 256, 8), 256, smem, st>>>(d_shares, N, n, si, sj, d_basis, d_out);
   CKL();
   return SCLGPU_OK;
@@ -805,6 +833,10 @@ static int recover_d_matrix(sclgpu_ctx* ctx, cudaStream_t st, uint32_t n_given, 
     if (x) xx = *x;
   }
   if ((uint64_t)n_given < (uint64_t)d + t || (uint64_t)n_alphas < (uint64_t)d + t)
+    return fail(ctx, SCLGPU_ELOGIC, "not enough shares provided to detect errors");
+  // the interpolation reads shares and nodes 0..d: with t = 0 the reference's own check lets d + 1 > n_given through
+  // and reads past the end of both vectors (shamir.h:125-127); here that is an error code
+  if ((uint64_t)n_given < (uint64_t)d + 1 || (uint64_t)n_alphas < (uint64_t)d + 1)
     return fail(ctx, SCLGPU_ELOGIC, "not enough shares provided to detect errors");
   m = d + 1;
   n_checks = (d + t > m) ? d + t - m : 0;
@@ -882,14 +914,14 @@ static void strides_for(int layout, uint64_t N, uint32_t n, uint64_t& si, uint64
 }
 
 // ================================================================ C ABI: PRG
-extern "C" int sclgpu_prg_expand_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+static int sclgpu_prg_expand_dev_impl(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
                                      uint64_t n_bytes, uint8_t* d_out) {
   if (!ctx || !seed || (!d_out && n_bytes)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
   return prg_bytes_on(ctx, ctx->stream, seed, first_block, n_bytes, d_out);
 }
 
-extern "C" int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+static int sclgpu_prg_expand_impl(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
                                  uint64_t n_bytes, uint8_t* out) {
   if (!ctx || !seed || (!out && n_bytes)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
@@ -1004,12 +1036,12 @@ extern "C" int sclgpu_fp61_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64
 extern "C" int sclgpu_fp127_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return guarded(c, [&] { return random_dev<F127, false>(c, s, fb, n, o); }); }
 extern "C" int sclgpu_fp61_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, uint64_t* o) { return guarded(c, [&] { return random_dev<F61, true>(c, s, fb, n, o); }); }
 extern "C" int sclgpu_fp127_ff_random_dev(sclgpu_ctx* c, const uint8_t s[16], uint64_t fb, uint64_t n, void* o) { return guarded(c, [&] { return random_dev<F127, true>(c, s, fb, n, o); }); }
-extern "C" int sclgpu_fp61_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, uint64_t* o) {
+static int sclgpu_fp61_from_bytes_dev_impl(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, uint64_t* o) {
   if (!ctx || ((!b || !o) && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
   return from_bytes_on<F61>(ctx, ctx->stream, b, n, o);
 }
-extern "C" int sclgpu_fp127_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, void* o) {
+static int sclgpu_fp127_from_bytes_dev_impl(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, void* o) {
   if (!ctx || ((!b || !o) && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
   return from_bytes_on<F127>(ctx, ctx->stream, b, n, (E127*)o);
@@ -1034,7 +1066,7 @@ static int share_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, uint32_
   const uint64_t B = ((uint64_t)(t + 1) * F::BYTES + 15) / 16;
   uint64_t chunk = std::max<uint64_t>((512ull << 20) / ((uint64_t)n * sizeof(E)), 1024);
   if (chunk > N) chunk = N;
-  StreamBuf tmp(ctx->stream);
+  StreamBuf tmp(ctx, ctx->stream);
   CK(tmp.alloc(chunk * n * sizeof(E)));
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
     const uint64_t nc = std::min(chunk, N - c0);
@@ -1197,7 +1229,7 @@ static int share_array_dev(sclgpu_ctx* ctx, const void* d_secrets, uint64_t N, u
   const bool sm = layout == SCLGPU_SECRET_MAJOR;
   const bool fused = share_array_fused<F>(W, t, n);
   const uint64_t chunk = (fused && !sm) ? N : share_array_chunk_len<F>(N, W, t, n, 512ull << 20);
-  StreamBuf planes(ctx->stream), tmp(ctx->stream);
+  StreamBuf planes(ctx, ctx->stream), tmp(ctx, ctx->stream);
   if (!fused) CK(planes.alloc(chunk * W * (uint64_t)(t + 1) * sizeof(E)));
   if (sm) CK(tmp.alloc(chunk * W * (uint64_t)n * sizeof(E)));
   const E* sec = reinterpret_cast<const E*>(d_secrets);
@@ -1563,6 +1595,10 @@ static int recover_p_packets_host(sclgpu_ctx* ctx, const uint8_t* const* packets
     cudaStream_t st = ctx->pipe[k];
     for (uint32_t i = 0; i < n; ++i)
       CK(ctx->stager.h2d(st, dsh[k].as<E>() + (uint64_t)i * nc, packets[i] + kPacketHeader + c0 * sizeof(E), nc * sizeof(E)));
+    // wire bytes from other parties: Serializer<Vector<FF>>::read goes through FF::read, i.e. `% p` on every word
+    // (vector.h:623-626, ff.h:63-67, mersenne61.cc:87-90) -- done here in place, so that words in [p, 2^64) /
+    // [p, 2^128) reconstruct to what the reference reconstructs
+    RET(from_bytes_on<F>(ctx, st, reinterpret_cast<const uint8_t*>(dsh[k].p), (uint64_t)n * nc, dsh[k].as<E>()));
     RET(recover_p_on<F>(ctx, st, dsh[k].as<E>(), nc, n, nc, 1, d_basis, dout[k].as<E>()));
     CK(ctx->stager.d2h(st, ho + c0, dout[k].p, nc * sizeof(E)));
   }
@@ -1721,7 +1757,7 @@ static int recover_p_array_dev(sclgpu_ctx* ctx, const void* d_shares, uint64_t N
     return recover_p_on<F>(ctx, ctx->stream, in, N * W, n, N * W, 1, d_basis, out);
   uint64_t chunk = std::max<uint64_t>((512ull << 20) / ((uint64_t)n * W * sizeof(E)), 256);
   chunk = std::min(chunk, N);
-  StreamBuf tmp(ctx->stream);
+  StreamBuf tmp(ctx, ctx->stream);
   CK(tmp.alloc(chunk * n * W * sizeof(E)));
   for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
     const uint64_t nc = std::min(chunk, N - c0);
@@ -1819,7 +1855,7 @@ static int recover_d_host(sclgpu_ctx* ctx, const void* shares, uint64_t N, uint3
   if (n_detected) *n_detected = 0;
   if (N == 0) return SCLGPU_OK;
   if (!shares || !out || !err) return fail(ctx, SCLGPU_EINVAL, "null argument");
-  uint64_t chunk = std::max<uint64_t>((256ull << 20) / ((uint64_t)n_given * sizeof(E)), 1024);
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(n_given, 1) * sizeof(E)), 1024);
   chunk = std::min(chunk, std::min(N, kHostChunk));
   const int nbuf = N > chunk ? 2 : 1;
   PoolScope pool_scope(ctx);
@@ -1877,7 +1913,7 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   for (uint32_t i = 0; i < np && distinct; ++i)
     for (uint32_t j = i + 1; j < np; ++j)
       if (F::eq(al[i], al[j])) distinct = false;
-  StreamBuf dpending(st);
+  StreamBuf dpending(ctx, st);
   DevBuf dcoef;
   uint32_t* d_pending = nullptr;
   unsigned long long* d_n_pending = nullptr;
@@ -2085,20 +2121,20 @@ static int vec_host(sclgpu_ctx* ctx, int op, const void* a, const void* b, const
 }
 
 #define SCLGPU_VEC_API(SUF, F, PTR, CPTR)                                                                                              \
-  extern "C" int sclgpu_##SUF##_vec_add(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 0, a, b, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_sub(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 1, a, b, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_mul(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 2, a, b, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_scale(sclgpu_ctx* c, CPTR a, CPTR s, uint64_t n, PTR o) { return vec_host<F>(c, 3, a, s, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_muladd(sclgpu_ctx* c, CPTR e, CPTR b, CPTR d, CPTR a, CPTR cc, uint64_t n, PTR z) { return vec_host<F>(c, 6, e, b, d, a, cc, n, z); } \
-  extern "C" int sclgpu_##SUF##_dot(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_host<F>(c, 4, a, b, 0, 0, 0, n, o); }     \
-  extern "C" int sclgpu_##SUF##_sum(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return vec_host<F>(c, 5, a, 0, 0, 0, 0, n, o); }             \
-  extern "C" int sclgpu_##SUF##_vec_add_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 0, a, b, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_sub_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 1, a, b, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_mul_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 2, a, b, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_scale_dev(sclgpu_ctx* c, CPTR a, CPTR s, uint64_t n, PTR o) { return vec_dev<F>(c, 3, a, s, 0, 0, 0, n, o); } \
-  extern "C" int sclgpu_##SUF##_vec_muladd_dev(sclgpu_ctx* c, CPTR e, CPTR b, CPTR d, CPTR a, CPTR cc, uint64_t n, PTR z) { return vec_dev<F>(c, 6, e, b, d, a, cc, n, z); } \
-  extern "C" int sclgpu_##SUF##_dot_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return vec_dev<F>(c, 4, a, b, 0, 0, 0, n, o); }  \
-  extern "C" int sclgpu_##SUF##_sum_dev(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return vec_dev<F>(c, 5, a, 0, 0, 0, 0, n, o); }
+  extern "C" int sclgpu_##SUF##_vec_add(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_host<F>(c, 0, a, b, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_sub(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_host<F>(c, 1, a, b, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_mul(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_host<F>(c, 2, a, b, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_scale(sclgpu_ctx* c, CPTR a, CPTR s, uint64_t n, PTR o) { return guarded(c, [&] { return vec_host<F>(c, 3, a, s, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_muladd(sclgpu_ctx* c, CPTR e, CPTR b, CPTR d, CPTR a, CPTR cc, uint64_t n, PTR z) { return guarded(c, [&] { return vec_host<F>(c, 6, e, b, d, a, cc, n, z); }); } \
+  extern "C" int sclgpu_##SUF##_dot(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_host<F>(c, 4, a, b, 0, 0, 0, n, o); }); }     \
+  extern "C" int sclgpu_##SUF##_sum(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return guarded(c, [&] { return vec_host<F>(c, 5, a, 0, 0, 0, 0, n, o); }); }             \
+  extern "C" int sclgpu_##SUF##_vec_add_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_dev<F>(c, 0, a, b, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_sub_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_dev<F>(c, 1, a, b, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_mul_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_dev<F>(c, 2, a, b, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_scale_dev(sclgpu_ctx* c, CPTR a, CPTR s, uint64_t n, PTR o) { return guarded(c, [&] { return vec_dev<F>(c, 3, a, s, 0, 0, 0, n, o); }); } \
+  extern "C" int sclgpu_##SUF##_vec_muladd_dev(sclgpu_ctx* c, CPTR e, CPTR b, CPTR d, CPTR a, CPTR cc, uint64_t n, PTR z) { return guarded(c, [&] { return vec_dev<F>(c, 6, e, b, d, a, cc, n, z); }); } \
+  extern "C" int sclgpu_##SUF##_dot_dev(sclgpu_ctx* c, CPTR a, CPTR b, uint64_t n, PTR o) { return guarded(c, [&] { return vec_dev<F>(c, 4, a, b, 0, 0, 0, n, o); }); }  \
+  extern "C" int sclgpu_##SUF##_sum_dev(sclgpu_ctx* c, CPTR a, uint64_t n, PTR o) { return guarded(c, [&] { return vec_dev<F>(c, 5, a, 0, 0, 0, 0, n, o); }); }
 
 // Vector::equals (vector.h:358-375): *equal = 1 iff all n elements agree (sizes are the caller's check)
 template <class F>
@@ -2272,19 +2308,19 @@ static int vandermonde_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out) 
 extern "C" int sclgpu_fp61_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return guarded(c, [&] { return vandermonde_host<F61>(c, n, m, o); }); }
 extern "C" int sclgpu_fp127_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return guarded(c, [&] { return vandermonde_host<F127>(c, n, m, o); }); }
 
-extern "C" int sclgpu_fp61_transpose_dev(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
+static int sclgpu_fp61_transpose_dev_impl(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
   if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
   return transpose_on<uint64_t>(ctx, ctx->stream, in, rows, cols, out);
 }
-extern "C" int sclgpu_fp127_transpose_dev(sclgpu_ctx* ctx, const void* in, uint64_t rows, uint64_t cols, void* out) {
+static int sclgpu_fp127_transpose_dev_impl(sclgpu_ctx* ctx, const void* in, uint64_t rows, uint64_t cols, void* out) {
   if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");
   CK(cudaSetDevice(ctx->device));
   return transpose_on<E127>(ctx, ctx->stream, (const E127*)in, rows, cols, (E127*)out);
 }
 
 // ------------------------------------------------------------------ microbench
-extern "C" int sclgpu_pipe_microbench(sclgpu_ctx* ctx, int kind, uint32_t iters, double* ops_per_s) {
+static int sclgpu_pipe_microbench_impl(sclgpu_ctx* ctx, int kind, uint32_t iters, double* ops_per_s) {
   if (!ctx || !ops_per_s || kind < 0 || kind > 4) return fail(ctx, SCLGPU_EINVAL, "bad argument");
   CK(cudaSetDevice(ctx->device));
   DevBuf sink;
@@ -2317,3 +2353,13 @@ extern "C" int sclgpu_pipe_microbench(sclgpu_ctx* ctx, int kind, uint32_t iters,
   *ops_per_s = ops / ((double)ms * 1e-3);
   return SCLGPU_OK;
 }
+
+// ------------------------------------------------------------------ guarded wrappers of the entry points above
+// (every extern "C" function goes through guarded(): no C++ exception crosses the ABI)
+extern "C" int sclgpu_prg_expand_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n_bytes, uint8_t* d_out) { return guarded(ctx, [&] { return sclgpu_prg_expand_dev_impl(ctx, seed, first_block, n_bytes, d_out); }); }
+extern "C" int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n_bytes, uint8_t* out) { return guarded(ctx, [&] { return sclgpu_prg_expand_impl(ctx, seed, first_block, n_bytes, out); }); }
+extern "C" int sclgpu_fp61_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, uint64_t* o) { return guarded(ctx, [&] { return sclgpu_fp61_from_bytes_dev_impl(ctx, b, n, o); }); }
+extern "C" int sclgpu_fp127_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, void* o) { return guarded(ctx, [&] { return sclgpu_fp127_from_bytes_dev_impl(ctx, b, n, o); }); }
+extern "C" int sclgpu_fp61_transpose_dev(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) { return guarded(ctx, [&] { return sclgpu_fp61_transpose_dev_impl(ctx, in, rows, cols, out); }); }
+extern "C" int sclgpu_fp127_transpose_dev(sclgpu_ctx* ctx, const void* in, uint64_t rows, uint64_t cols, void* out) { return guarded(ctx, [&] { return sclgpu_fp127_transpose_dev_impl(ctx, in, rows, cols, out); }); }
+extern "C" int sclgpu_pipe_microbench(sclgpu_ctx* ctx, int kind, uint32_t iters, double* ops_per_s) { return guarded(ctx, [&] { return sclgpu_pipe_microbench_impl(ctx, kind, iters, ops_per_s); }); }

@@ -197,6 +197,44 @@ int main() {
     }
     REQUIRE(sclgpu::shamirRecoverP<Fp61>(ctx, packets).equals(secrets));
     REQUIRE(packets[2].read<math::Vector<Fp61>>().equals(math::Vector<Fp61>(cols[2])));  // and SCL can read it
+
+    // ---- packets from OTHER parties may carry non-canonical words (any 8 bytes is a legal wire element:
+    // Serializer<Vector<FF>>::read -> FF::read -> `% p`, vector.h:623-626, ff.h:63-67).  Overwrite words with values in
+    // [p, 2^64) and compare with what SCL itself reconstructs from the same bytes.
+    {
+      const std::uint64_t p61 = 0x1FFFFFFFFFFFFFFFull;
+      std::vector<scl::net::Packet> wire;
+      for (std::size_t i = 0; i < n; ++i) {
+        scl::net::Packet pk;
+        pk.write(math::Vector<Fp61>(cols[i]));
+        unsigned char* bytes = pk.get();
+        for (std::size_t j = i; j < N; j += 5) {   // every fifth word of every packet, staggered
+          std::uint64_t w;
+          std::memcpy(&w, bytes + 4 + 8 * j, 8);
+          std::uint64_t bad = (j % 3 == 0) ? w + p61 : (j % 3 == 1 ? w + 7 * p61 : ~0ull - (j % 97));
+          if (j == i) bad = ~0ull;
+          std::memcpy(bytes + 4 + 8 * j, &bad, 8);
+        }
+        wire.push_back(pk);
+      }
+      std::vector<math::Vector<Fp61>> read_back;
+      for (std::size_t i = 0; i < n; ++i) {
+        scl::net::Packet copy = wire[i];
+        read_back.push_back(copy.read<math::Vector<Fp61>>());   // SCL's deserializer canonicalises
+      }
+      const auto got = sclgpu::shamirRecoverP<Fp61>(ctx, wire);
+      for (std::size_t j = 0; j < N; ++j) {
+        std::vector<Fp61> sh(n);
+        for (std::size_t i = 0; i < n; ++i) sh[i] = read_back[i][j];
+        REQUIRE(got[j] == ss::shamirRecoverP(math::Vector<Fp61>(sh)));
+      }
+      // a packet that announces more elements than it holds is refused before any byte of it is read
+      scl::net::Packet short_pk;
+      short_pk.write((std::uint32_t)N);
+      std::vector<scl::net::Packet> bad_set = wire;
+      bad_set[1] = short_pk;
+      REQUIRE(throwsInvalid([&] { (void)sclgpu::shamirRecoverP<Fp61>(ctx, bad_set); }, "packet shorter than the Vec it announces"));
+    }
   }
 
   // ---- additiveShare (test/scl/ss/test_additive.cc: shares sum to the secret), both fields, PRG state

@@ -663,6 +663,57 @@ def test_share_packets_wire_layout(ctx, pkg, orc, field, t, n, N):
         ctx.recover_p_packets(field, bad, N)
 
 
+@pytest.mark.parametrize("field,t,n,N", [(61, 15, 32, 4098), (61, 2, 5, 1001), (127, 7, 16, 2050), (127, 2, 20, 515), (61, 3, 2100, 40)])
+def test_recover_p_packets_non_canonical_words(ctx, orc, field, t, n, N):
+    """Wire packets come from OTHER parties: any byte string is a legal element, and SCL canonicalises on receive
+    (Serializer<Vector<FF>>::read -> FF::read -> `% p`; vector.h:623-626, ff.h:63-67, mersenne61.cc:87-90).  Words in
+    [p, 2^64) / [p, 2^128) must therefore reconstruct to what the reference reconstructs from the same bytes:
+    FF::read on every word (oracle from_bytes) followed by shamirRecoverP -- on the plane kernel, the tensor-core
+    kernel (Fp127, n <= 16) and the generic kernel (Fp127 n > 16, Fp61 n > 2048)."""
+    import struct
+    rng = np.random.default_rng(field * 1000 + n)
+    w = 1 if field == 61 else 2
+    secrets = orc.vector_random(field, "secrets", 0, N)
+    packets = ctx.shamir_share_packets(field, secrets, min(t, n - 1), n, "wire", 0)
+    p_int = (1 << field) - 1
+    raw = []
+    for i, pk in enumerate(packets):
+        words = pk[4:].view(np.uint64).reshape(N, w).copy()
+        for j in range(i % 3, N, 3):                      # a third of the words of every packet
+            v = int(words[j, 0]) | ((int(words[j, 1]) << 64) if w == 2 else 0)
+            k = int(rng.integers(1, 8 if field == 61 else 2))
+            nv = v + k * p_int if j % 2 else (1 << (64 * w)) - 1 - int(rng.integers(0, 1 << 20))
+            if nv >= 1 << (64 * w):
+                nv = v + p_int
+            words[j, 0] = nv & 0xFFFFFFFFFFFFFFFF
+            if w == 2:
+                words[j, 1] = nv >> 64
+        raw.append(words)
+        pk[4:] = words.reshape(-1).view(np.uint8)
+        assert bytes(pk[:4]) == struct.pack("<I", N)
+    canon = np.stack([orc.from_bytes(field, r.tobytes()).reshape((N,) + ((2,) if w == 2 else ())) for r in raw], axis=1)
+    want = orc.recover_p(field, np.ascontiguousarray(canon))
+    got = ctx.recover_p_packets(field, packets, N)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("field", [61, 127])
+def test_recover_d_degenerate_thresholds(ctx, pkg, port, field):
+    """t = 0: the reference's own size check (n_given >= d + t) lets d + 1 > n_given through and then reads one share
+    past the end (shamir.h:125-127); this ABI returns the reference's logic_error instead of reading out of bounds or
+    dividing by n_given = 0."""
+    s = port.vector_random(field, "secrets", 0, 10)
+    empty_rows = pkg.api.empty(field, 10, 0)
+    out, err, rc = ctx.recover_d(field, empty_rows, 0)       # n_given = 0, t = 0, d = 0
+    assert rc == -1
+    sh = port.shamir_share(field, s, 2, 2, "deg", 0)          # two shares per secret
+    out, err, rc = ctx.recover_d(field, sh, 0, alphas=port.from_ints([1, 2], field), d=2, x=0)   # needs shares 0..2
+    assert rc == -1
+    sh = port.shamir_share(field, s, 0, 3, "deg", 0)          # degree 0, t = 0: one share interpolates, no checks
+    out, err, rc = ctx.recover_d(field, sh, 0)
+    assert rc == 0 and np.array_equal(out, s)
+
+
 # ------------------------------------------------------------------ array-valued secrets, hyperInvertible (SURVEY 8f.4)
 def test_share_array_and_him_golden(ctx, port, golden):
     for c in golden["share_array"]:
