@@ -190,7 +190,9 @@ int sclgpu_fp61_shamir_share_recover_dev(sclgpu_ctx* ctx, const uint64_t* d_secr
  *                  nodes of the corrupted shares), zero padded;
  *   status[j]      1 where the reference throws "could not correct shares" (f, err = 0).
  * Returns SCLGPU_ECORRECT if any status[j] is set (everything is still written),
- * *n_failed (nullable) = how many.  np <= 32, i.e. 1 <= n <= 33 (SCLGPU_EINVAL otherwise).
+ * *n_failed (nullable) = how many.  Any n >= 1 whose (3t+1) x (3t+2) system fits the shared memory
+ * of one SM: np <= 32 runs one warp per sharing, larger np one CTA per sharing (Fp61: n <= 166,
+ * Fp127: n <= 118; SCLGPU_EINVAL beyond -- the reference itself has no limit, shamir.h:203-246).
  * Up to t corrupted shares per sharing are corrected. */
 int sclgpu_fp61_recover_c(sclgpu_ctx* ctx, const uint64_t* shares, uint64_t N, uint32_t n,
                           const uint64_t* alphas, uint64_t* f, uint64_t* err, uint8_t* status,

@@ -22,6 +22,7 @@
 
 #include "../../include/sclgpu.h"
 #include "kernels.cuh"
+#include "recover_c_big.cuh"
 #include "matmul_tc.h"
 #include "share_tc.h"
 #include "host_stage.h"
@@ -1898,7 +1899,10 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   typedef typename F::E E;
   if (n == 0) return fail(ctx, SCLGPU_EINVAL, "shamirRecoverC needs at least one share");
   const uint32_t t = (n - 1) / 3, np = 3 * t + 1;
-  if (np > 32) return fail(ctx, SCLGPU_EINVAL, "recover_c supports n <= 33 (3t+1 <= 32 rows per warp)");
+  // 3t+1 <= 32: a warp per sharing (k_recover_c); larger: a CTA per sharing (k_recover_c_cta), its system in shared memory
+  const bool big = np > 32;
+  if (big && (np > kRecoverCBigMaxPoints || recover_c_big_smem<F>(np) > 227 * 1024))
+    return fail(ctx, SCLGPU_EINVAL, "recover_c: the (3t+1) x (3t+2) system exceeds shared memory (Fp61: n <= 166, Fp127: n <= 118)");
   if (n_failed) *n_failed = 0;
   if (N == 0) return SCLGPU_OK;
   std::vector<E> al(np);
@@ -1918,7 +1922,7 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
   uint32_t* d_pending = nullptr;
   unsigned long long* d_n_pending = nullptr;
   std::vector<E> coef;
-  if (distinct && t <= kRecoverCMaxT && N < (1ull << 32) && !env_flag("SCLGPU_RECOVER_C_FULL")) {
+  if (distinct && N < (1ull << 32) && !env_flag("SCLGPU_RECOVER_C_FULL")) {
     const uint32_t m = t + 1;
     const E* d_check = nullptr;
     if (t > 0) RET(basis_rows<F>(ctx, st, al.data(), m, al.data() + m, 2 * t, &d_check));
@@ -1948,14 +1952,35 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     d_n_pending = dpending.as<unsigned long long>();  // counter first (8-byte aligned), then the index list
     d_pending = reinterpret_cast<uint32_t*>(d_n_pending + 1);
     CK(cudaMemsetAsync(d_n_pending, 0, sizeof(unsigned long long), st));
-    const size_t csm = (size_t)(3 * t + 1) * m * sizeof(E);
-    k_recover_c_clean<F><<<grid_for(ctx, N, 256, 4), 256, csm, st>>>(d_shares, N, si, sj, t, d_check, dcoef.as<E>(), d_f,
-                                                                    d_e, d_status, d_pending, d_n_pending);
+    if (t <= kRecoverCMaxT) {
+      const size_t csm = (size_t)(3 * t + 1) * m * sizeof(E);
+      k_recover_c_clean<F><<<grid_for(ctx, N, 256, 4), 256, csm, st>>>(d_shares, N, si, sj, t, d_check, dcoef.as<E>(), d_f,
+                                                                      d_e, d_status, d_pending, d_n_pending);
+    } else {
+      k_recover_c_clean_any<F><<<grid_for(ctx, N, 256, 4), 256, 0, st>>>(d_shares, N, si, sj, t, d_check, dcoef.as<E>(), d_f,
+                                                                        d_e, d_status, d_pending, d_n_pending);
+    }
     CKL();
+  }
+  const int quick = (distinct && !env_flag("SCLGPU_RECOVER_C_FULL")) ? 1 : 0;
+  if (big) {
+    const size_t bsm = recover_c_big_smem<F>(np);
+    CK(cudaFuncSetAttribute(k_recover_c_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    const int threads = (int)((np + 31u) / 32u * 32u);
+    const int per_sm = std::max(1, std::min((int)((227 * 1024) / bsm), 2048 / threads));
+    const int grid = (int)std::min<uint64_t>(N, (uint64_t)ctx->sm_count * per_sm);
+    k_recover_c_cta<F><<<grid, threads, bsm, st>>>(d_shares, N, si, sj, t, dal.as<E>(), d_f, d_e, d_status, ctx->d_count,
+                                                  d_pending, d_n_pending, quick);
+    CKL();
+    unsigned long long bad_big = 0;
+    CK(cudaMemcpyAsync(&bad_big, ctx->d_count, sizeof(bad_big), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));  // also keeps `dal` alive until the kernel is done
+    if (n_failed) *n_failed = bad_big;
+    if (bad_big) return fail(ctx, SCLGPU_ECORRECT, "could not correct shares");
+    return SCLGPU_OK;
   }
   const int warps_per_cta = 8;
   const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 3 * np) * sizeof(E);
-  const int quick = (distinct && !env_flag("SCLGPU_RECOVER_C_FULL")) ? 1 : 0;
   CK(cudaFuncSetAttribute(k_recover_c<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<uint64_t>((N + warps_per_cta - 1) / warps_per_cta, (uint64_t)ctx->sm_count * 4);
   k_recover_c<F><<<grid, 32 * warps_per_cta, smem, st>>>(d_shares, N, si, sj, t, dal.as<E>(), d_f, d_e, d_status,

@@ -575,9 +575,51 @@ def test_recover_c_vs_oracle(ctx, pkg, orc, field, n, N):
         assert np.array_equal(d_st.cpu().numpy(), got[2])
 
 
+@pytest.mark.parametrize("field,n,N", [(61, 34, 160), (61, 40, 130), (61, 64, 96), (61, 100, 48), (61, 166, 12), (127, 34, 80),
+                                       (127, 64, 40), (127, 118, 8)])
+def test_recover_c_more_than_32_points(ctx, pkg, orc, port, field, n, N):
+    """3t+1 > 32: one CTA per sharing (k_recover_c_cta), error-free sharings settled by k_recover_c_clean_any.  The
+    reference takes any size (shamir.h:203-246, matrix.h:598-828); f, err, status and the count against its
+    shamirRecoverC with 0..t+1 corrupted shares, default and custom nodes, both layouts on the device."""
+    import torch
+
+    rng = np.random.default_rng(n)
+    t = (n - 1) // 3
+    sec = port.vector_random(field, "secrets", 0, N)
+    sh = port.shamir_share(field, sec, t, n, "rc", 3).copy()
+    flat = sh.reshape(N, n, -1)
+    nerr = [0, 1, t, t + 1, t // 2, 2]
+    for j in range(N):
+        k = nerr[j % len(nerr)]
+        for i in (rng.choice(3 * t + 1, size=min(k, 3 * t + 1), replace=False) if k else []):
+            flat[j, i, rng.integers(flat.shape[2])] ^= np.uint64(1 + j)
+    K = min(N, 24)                                           # the unmodified reference on a prefix, the port on everything
+    want_ref = orc.recover_c(field, sh[:K])
+    want = port.recover_c(field, sh)
+    got = ctx.recover_c(field, sh)
+    for g, w, r, name in zip(got[:3], want[:3], want_ref[:3], ("f", "err", "status")):
+        assert np.array_equal(g, w), (field, n, name)
+        assert np.array_equal(g[:K], r), (field, n, name, "reference")
+    assert got[3] == want[3] == int((got[2] != 0).sum())
+    ok = np.array([nerr[j % len(nerr)] <= t for j in range(N)])
+    assert not got[2][ok].any() and np.array_equal(got[0][:, 0][ok], sec[ok])
+    alphas = port.from_ints([5 * i + 3 for i in range(n)], field)
+    w2, g2 = port.recover_c(field, sh[:16], alphas), ctx.recover_c(field, sh[:16], alphas)
+    assert all(np.array_equal(a, b) for a, b in zip(g2[:3], w2[:3])) and g2[3] == w2[3]
+    ctx.use_torch_stream()
+    w = 1 if field == 61 else 2
+    d_pm = torch.from_numpy(np.ascontiguousarray(np.swapaxes(sh.reshape(N, n, w), 0, 1)).view(np.int64)).cuda()
+    d_f = torch.empty((N, 3 * t + 1, w), dtype=torch.int64, device="cuda")
+    d_e = torch.empty((N, t + 1, w), dtype=torch.int64, device="cuda")
+    d_st = torch.empty(N, dtype=torch.uint8, device="cuda")
+    assert ctx.recover_c_dev(field, d_pm, N, n, d_f, d_e, d_st, pkg.binding.PARTY_MAJOR) == got[3]
+    assert np.array_equal(d_f.cpu().numpy().view(np.uint64).reshape(got[0].shape), got[0])
+    assert np.array_equal(d_st.cpu().numpy(), got[2])
+
+
 def test_recover_c_errors(ctx, pkg, port):
     with pytest.raises(pkg.InvalidArgument):
-        ctx.recover_c(61, port.from_ints(list(range(34)), 61).reshape(1, 34))     # 3t+1 = 34 rows > one warp
+        ctx.recover_c(61, port.from_ints(list(range(400)), 61).reshape(1, 400))   # the system no longer fits shared memory
 
 
 # ------------------------------------------------------------------ Polynomial::evaluate from coefficient planes
