@@ -419,6 +419,26 @@ int sclgpu_fp127_matmul_dev(sclgpu_ctx* ctx, const void* d_A, uint32_t rows, uin
                             uint32_t cols, void* d_C);
 int sclgpu_fp61_vandermonde(sclgpu_ctx* ctx, uint32_t n, uint32_t m, uint64_t* out);
 int sclgpu_fp127_vandermonde(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out);
+/* Matrix::vandermonde(n, m, xs) with the caller's nodes (matrix.h:445-460): row i = (1, xs[i], xs[i]^2, ..);
+ * n_xs != n -> SCLGPU_EINVAL "|xs| != number of rows". */
+int sclgpu_fp61_vandermonde_xs(sclgpu_ctx* ctx, uint32_t n, uint32_t m, const uint64_t* xs, uint32_t n_xs, uint64_t* out);
+int sclgpu_fp127_vandermonde_xs(sclgpu_ctx* ctx, uint32_t n, uint32_t m, const void* xs, uint32_t n_xs, void* out);
+/* Polynomial::evaluate (poly.h:56-64: Horner from the top coefficient) of N polynomials of degree <= t at n
+ * caller-chosen points xs (HOST pointer in both forms).  Host form: coeffs [N][t+1], row j = polynomial j's
+ * coefficients, constant term first (Polynomial::coefficients()); out [N][n].  Device form: coefficient planes
+ * [t+1][N] as in *_shamir_share_coeffs_dev, out in `layout`. */
+int sclgpu_fp61_poly_evaluate(sclgpu_ctx* ctx, const uint64_t* coeffs, uint64_t N, uint32_t t, const uint64_t* xs,
+                              uint32_t n, uint64_t* out);
+int sclgpu_fp127_poly_evaluate(sclgpu_ctx* ctx, const void* coeffs, uint64_t N, uint32_t t, const void* xs, uint32_t n,
+                               void* out);
+int sclgpu_fp61_poly_evaluate_dev(sclgpu_ctx* ctx, const uint64_t* d_coeffs, uint64_t N, uint32_t t, const uint64_t* xs,
+                                  uint32_t n, uint64_t* d_out, int layout);
+int sclgpu_fp127_poly_evaluate_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, uint32_t t, const void* xs,
+                                   uint32_t n, void* d_out, int layout);
+/* Matrix::transpose (matrix.h:344-355) of a host matrix [rows][cols] -> [cols][rows];
+ * Matrix::scalarMultiply (matrix.h:325-342) is *_vec_scale on rows*cols elements. */
+int sclgpu_fp61_transpose(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out);
+int sclgpu_fp127_transpose(sclgpu_ctx* ctx, const void* in, uint64_t rows, uint64_t cols, void* out);
 
 /* ---- layout helpers (device) -------------------------------------------------
  * [rows][cols] -> [cols][rows] of 8-byte (fp61) / 16-byte (fp127) elements. */

@@ -28,6 +28,9 @@
 //   Matrix::multiply(Vector)                             matrix.h:498-513
 //   Matrix::multiply(Matrix)                             matrix.h:476-495
 //   Matrix::hyperInvertible(n, m)                        matrix.h:462-475   -> sclgpu::hyperInvertible<FF>(ctx, n, m)
+//   Matrix::vandermonde(n, m, xs)                        matrix.h:445-460   -> sclgpu::vandermonde<FF>(ctx, n, m, xs)
+//   Matrix::scalarMultiply / transpose                   matrix.h:325-355   -> sclgpu::scalarMultiply / transpose(ctx, M)
+//   Polynomial::evaluate, N polynomials at n points      poly.h:56-64       -> sclgpu::evaluate(ctx, polys, xs)
 //   scl::ss::shamirSecretShare(math::Array<FF, W>, t, n, prg)   (pedersen.h:137-138: W = 2, {secret, randomness})
 //     -> sclgpu::shamirSecretShare(ctx, std::vector<math::Array<FF, W>>, t, n, prg) : N Vectors of n Arrays
 //        sclgpu::shamirRecoverP(ctx, std::vector<math::Vector<math::Array<FF, W>>>)  : N Arrays
@@ -37,6 +40,7 @@
 #ifndef SCLGPU_SCL_HPP
 #define SCLGPU_SCL_HPP
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -97,6 +101,9 @@ struct Abi;  // maps an SCL field type onto the fp61 / fp127 entry points
     static constexpr auto share_array = &sclgpu_##SUF##_shamir_share_array;                                   \
     static constexpr auto recover_p_array = &sclgpu_##SUF##_recover_p_array;                                  \
     static constexpr auto hyper_invertible = &sclgpu_##SUF##_hyper_invertible;                                \
+    static constexpr auto vandermonde_xs = &sclgpu_##SUF##_vandermonde_xs;                                    \
+    static constexpr auto poly_evaluate = &sclgpu_##SUF##_poly_evaluate;                                      \
+    static constexpr auto transpose = &sclgpu_##SUF##_transpose;                                              \
   }
 SCLGPU_SCL_ABI(scl::math::ff::Mersenne61, fp61, 8);
 SCLGPU_SCL_ABI(scl::math::ff::Mersenne127, fp127, 16);
@@ -443,6 +450,51 @@ scl::math::Matrix<FF> hyperInvertible(Context& ctx, std::size_t n, std::size_t m
   scl::math::Matrix<FF> him(n, m);
   ctx.check(detail::Abi<FF>::hyper_invertible(ctx.get(), (std::uint32_t)n, (std::uint32_t)m, detail::raw<FF>(&him(0, 0))));
   return him;
+}
+
+// ---- Matrix::vandermonde(n, m, xs), matrix.h:445-460
+template <class FF>
+scl::math::Matrix<FF> vandermonde(Context& ctx, std::size_t n, std::size_t m, const scl::math::Vector<FF>& xs) {
+  if (xs.size() != n) throw std::invalid_argument("|xs| != number of rows");
+  if (n == 0 || m == 0) return scl::math::Matrix<FF>();
+  scl::math::Matrix<FF> v(n, m);
+  ctx.check(detail::Abi<FF>::vandermonde_xs(ctx.get(), (std::uint32_t)n, (std::uint32_t)m, detail::raw<FF>(xs.toStlVector().data()),
+                                            (std::uint32_t)xs.size(), detail::raw<FF>(&v(0, 0))));
+  return v;
+}
+
+// ---- Matrix::scalarMultiply (matrix.h:325-342) and Matrix::transpose (matrix.h:344-355)
+template <class FF>
+scl::math::Matrix<FF> scalarMultiply(Context& ctx, const scl::math::Matrix<FF>& a, const FF& s) {
+  if (a.rows() == 0 || a.cols() == 0) return a;
+  scl::math::Matrix<FF> out(a.rows(), a.cols());
+  ctx.check(detail::Abi<FF>::vec_scale(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(a)(0, 0)), detail::raw<FF>(&s), a.rows() * a.cols(),
+                                       detail::raw<FF>(&out(0, 0))));
+  return out;
+}
+template <class FF>
+scl::math::Matrix<FF> transpose(Context& ctx, const scl::math::Matrix<FF>& a) {
+  if (a.rows() == 0 || a.cols() == 0) return a.transpose();
+  scl::math::Matrix<FF> out(a.cols(), a.rows());
+  ctx.check(detail::Abi<FF>::transpose(ctx.get(), detail::raw<FF>(&const_cast<scl::math::Matrix<FF>&>(a)(0, 0)), a.rows(), a.cols(),
+                                       detail::raw<FF>(&out(0, 0))));
+  return out;
+}
+
+// ---- Polynomial::evaluate (poly.h:56-64) of every polynomial at every point: result(j, i) = polys[j].evaluate(xs[i])
+template <class FF>
+scl::math::Matrix<FF> evaluate(Context& ctx, const std::vector<scl::math::Polynomial<FF>>& polys, const scl::math::Vector<FF>& xs) {
+  const std::size_t N = polys.size(), n = xs.size();
+  if (N == 0 || n == 0) return scl::math::Matrix<FF>();
+  std::size_t m = 1;
+  for (const auto& p : polys) m = std::max<std::size_t>(m, p.degree() + 1);
+  std::vector<FF> coeffs(N * m);  // zero padded to the largest degree
+  for (std::size_t j = 0; j < N; ++j)
+    for (std::size_t k = 0; k <= polys[j].degree(); ++k) coeffs[j * m + k] = polys[j][k];
+  scl::math::Matrix<FF> out(N, n);
+  ctx.check(detail::Abi<FF>::poly_evaluate(ctx.get(), detail::raw<FF>(coeffs.data()), N, (std::uint32_t)(m - 1),
+                                           detail::raw<FF>(xs.toStlVector().data()), (std::uint32_t)n, detail::raw<FF>(&out(0, 0))));
+  return out;
 }
 
 // ---- shamirSecretShare on array-valued secrets (shamir.h:52-68 with T = math::Array<FF, W>; the sharing

@@ -571,6 +571,39 @@ class RefOracle(_Base):
         self._f(field, "vandermonde")(n, m, _p(out))
         return out
 
+    def vandermonde_xs(self, field, n, m, xs):
+        """Matrix::vandermonde(n, m, xs); raises ValueError where the reference throws invalid_argument."""
+        xs = _c(xs)
+        out = empty(field, n, m)
+        f = self._f(field, "vandermonde_xs")
+        f.argtypes = [C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
+        f.restype = C.c_int
+        if f(n, m, _p(xs), xs.size if field == 61 else xs.size // 2, _p(out)):
+            raise ValueError("|xs| != number of rows")
+        return out
+
+    def poly_evaluate(self, field, coeffs, xs):
+        """Polynomial::create(coeffs[j]).evaluate(xs[i]) -> [N, n]."""
+        coeffs, xs = _c(coeffs), _c(xs)
+        N, m = coeffs.shape[0], coeffs.shape[1]
+        n = xs.size if field == 61 else xs.size // 2
+        out = empty(field, N, n)
+        f = self._f(field, "poly_evaluate")
+        f.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, _vp]
+        f.restype = None
+        f(_p(coeffs), N, m, _p(xs), n, _p(out))
+        return out
+
+    def transpose(self, field, A):
+        A = _c(A)
+        rows, cols = A.shape[0], A.shape[1]
+        out = empty(field, cols, rows)
+        f = self._f(field, "transpose")
+        f.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
+        f.restype = None
+        f(_p(A), rows, cols, _p(out))
+        return out
+
     def bench_share_recover(self, field, N, t, n, detect, threads):
         bs = 8 if field == 61 else 16
         blocks = ((t + 1) * bs + 15) // 16

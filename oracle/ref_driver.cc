@@ -37,6 +37,7 @@
 #include "scl/math/fp.h"
 #include "scl/math/lagrange.h"
 #include "scl/math/matrix.h"
+#include "scl/math/poly.h"
 #include "scl/math/vector.h"
 #include "scl/ss/additive.h"
 #include "scl/ss/shamir.h"
@@ -386,6 +387,47 @@ void vandermonde(uint64_t n, uint64_t m, unsigned char* out) {
   }
 }
 
+// Matrix::vandermonde(n, m, xs) (matrix.h:445-460); returns 1 where the reference throws "|xs| != number of rows"
+template <typename T>
+int vandermondeXs(uint64_t n, uint64_t m, const unsigned char* xs, uint64_t n_xs, unsigned char* out) {
+  try {
+    const auto v = scl::math::Matrix<T>::vandermonde(n, m, readVec<T>(xs, n_xs));
+    for (uint64_t i = 0; i < n; ++i) {
+      for (uint64_t j = 0; j < m; ++j) {
+        v(i, j).write(out + (i * m + j) * T::byteSize());
+      }
+    }
+  } catch (const std::invalid_argument&) {
+    return 1;
+  }
+  return 0;
+}
+
+// Polynomial::evaluate (poly.h:56-64): N polynomials (coeffs [N][m], constant term first) at n points -> [N][n]
+template <typename T>
+void polyEvaluate(const unsigned char* coeffs, uint64_t N, uint64_t m, const unsigned char* xs, uint64_t n,
+                  unsigned char* out) {
+  const auto pts = readVec<T>(xs, n);
+  for (uint64_t j = 0; j < N; ++j) {
+    const auto p = scl::math::Polynomial<T>::create(readVec<T>(coeffs + j * m * T::byteSize(), m));
+    for (uint64_t i = 0; i < n; ++i) {
+      p.evaluate(pts[i]).write(out + (j * n + i) * T::byteSize());
+    }
+  }
+}
+
+// Matrix::transpose (matrix.h:344-355)
+template <typename T>
+void transposeM(const unsigned char* in, uint64_t rows, uint64_t cols, unsigned char* out) {
+  const scl::math::Matrix<T> a = scl::math::Matrix<T>::fromVector(rows, cols, readVec<T>(in, rows * cols).toStlVector());
+  const auto tr = a.transpose();
+  for (uint64_t i = 0; i < cols; ++i) {
+    for (uint64_t j = 0; j < rows; ++j) {
+      tr(i, j).write(out + (i * rows + j) * T::byteSize());
+    }
+  }
+}
+
 // op: 0 add 1 sub 2 mul 3 negate(a) 4 inverse(a) 5 divide
 template <typename T>
 int scalarOp(int op, const unsigned char* a, const unsigned char* b,
@@ -550,6 +592,20 @@ double benchShareRecover(uint64_t N, uint64_t t, uint64_t n, int detect,
   void sclref_##SUF##_vandermonde(uint64_t n, uint64_t m,                      \
                                   unsigned char* out) {                        \
     vandermonde<T>(n, m, out);                                                 \
+  }                                                                            \
+  int sclref_##SUF##_vandermonde_xs(uint64_t n, uint64_t m,                    \
+                                    const unsigned char* xs, uint64_t n_xs,    \
+                                    unsigned char* out) {                      \
+    return vandermondeXs<T>(n, m, xs, n_xs, out);                              \
+  }                                                                            \
+  void sclref_##SUF##_poly_evaluate(const unsigned char* coeffs, uint64_t N,   \
+                                    uint64_t m, const unsigned char* xs,       \
+                                    uint64_t n, unsigned char* out) {          \
+    polyEvaluate<T>(coeffs, N, m, xs, n, out);                                 \
+  }                                                                            \
+  void sclref_##SUF##_transpose(const unsigned char* in, uint64_t rows,        \
+                                uint64_t cols, unsigned char* out) {           \
+    transposeM<T>(in, rows, cols, out);                                        \
   }                                                                            \
   int sclref_##SUF##_scalar_op(int op, const unsigned char* a,                 \
                                const unsigned char* b, unsigned char* out) {   \

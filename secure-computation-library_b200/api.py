@@ -525,6 +525,34 @@ class Context:
         self._check(self._f(field, "vandermonde")(self._ctx, n, m, _p(out)))
         return out
 
+    def vandermonde_xs(self, field: int, n: int, m: int, xs) -> np.ndarray:
+        """Matrix::vandermonde(n, m, xs) (matrix.h:445-460)."""
+        xs = _c(xs)
+        out = empty(field, n, m)
+        self._check(self._f(field, "vandermonde_xs")(self._ctx, n, m, _p(xs), _nelem(xs, field), _p(out)))
+        return out
+
+    def poly_evaluate(self, field: int, coeffs, xs) -> np.ndarray:
+        """Polynomial::evaluate (poly.h:56-64): coeffs [N, t+1] (constant term first), xs [n] -> [N, n]."""
+        coeffs, xs = _c(coeffs), _c(xs)
+        N, m = coeffs.shape[0], coeffs.shape[1]
+        n = _nelem(xs, field)
+        out = empty(field, N, n)
+        self._check(self._f(field, "poly_evaluate")(self._ctx, _p(coeffs), N, m - 1, _p(xs), n, _p(out)))
+        return out
+
+    def poly_evaluate_dev(self, field: int, coeffs, N: int, t: int, xs, out, layout: int = B.PARTY_MAJOR):
+        xs = _c(xs)
+        self._check(self._f(field, "poly_evaluate_dev")(self._ctx, _dp(coeffs), N, t, _p(xs), _nelem(xs, field), _dp(out), layout))
+
+    def transpose(self, field: int, A) -> np.ndarray:
+        """Matrix::transpose (matrix.h:344-355)."""
+        A = _c(A)
+        rows, cols = A.shape[0], A.shape[1]
+        out = empty(field, cols, rows)
+        self._check(self._f(field, "transpose")(self._ctx, _p(A), rows, cols, _p(out)))
+        return out
+
     def transpose_dev(self, field: int, src, rows: int, cols: int, dst):
         self._check(self._f(field, "transpose_dev")(self._ctx, _dp(src), rows, cols, _dp(dst)))
 

@@ -109,6 +109,10 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_recover_d_dev", _int, _vp, _vp, _u64, _u32, _int, _u32, _vp, _u32, _u32,
              _vp, _vp, _vp, C.POINTER(_u64))
         _sig(lib, f"sclgpu_{f}_vandermonde", _int, _vp, _u32, _u32, _vp)
+        _sig(lib, f"sclgpu_{f}_vandermonde_xs", _int, _vp, _u32, _u32, _vp, _u32, _vp)
+        _sig(lib, f"sclgpu_{f}_poly_evaluate", _int, _vp, _vp, _u64, _u32, _vp, _u32, _vp)
+        _sig(lib, f"sclgpu_{f}_poly_evaluate_dev", _int, _vp, _vp, _u64, _u32, _vp, _u32, _vp, _int)
+        _sig(lib, f"sclgpu_{f}_transpose", _int, _vp, _vp, _u64, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_transpose_dev", _int, _vp, _vp, _u64, _u64, _vp)
     _sig(lib, "sclgpu_fp61_shamir_share_recover_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp)
     _sig(lib, "sclgpu_fp61_recover_p_gather_dev", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _u32, _u64)

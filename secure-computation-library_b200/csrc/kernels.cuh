@@ -1297,6 +1297,52 @@ k_matvec61_warp(const uint64_t* __restrict__ A, uint32_t rows, uint32_t cols,
   }
 }
 
+// Fp61 mat-vec in two passes for long rows (cols a multiple of 512, 16-byte aligned rows).  Pass 1: the matrix is cut
+// into 4 KiB chunks in MEMORY order (a chunk lies inside one row) and warp w takes chunks w, w + W, ...: the grid
+// sweeps A front to back like the vector kernels do, eight 128-bit loads in flight per lane, no barrier, and writes one
+// partial sum per chunk.  Pass 2: one thread per row adds the row's partials (cols / 512 of them, contiguous).
+// Measured alternatives at 8192 x 8192 (B200): one warp per row 0.107 ms (every concurrent access in another row),
+// two warps per row joined through shared memory 0.116 ms, a 512-thread CTA per row 0.144 ms.
+static constexpr uint32_t kMatvecChunk = 256;  // 16-byte units per chunk: 4 KiB = 512 elements
+
+__global__ void __launch_bounds__(256)
+k_matvec61_chunks(const uint64_t* __restrict__ A, uint64_t n_chunks, uint32_t chunks_per_row,
+                  const uint64_t* __restrict__ x, uint64_t* __restrict__ partial) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const ulonglong2* A2 = reinterpret_cast<const ulonglong2*>(A);
+  const ulonglong2* x2 = reinterpret_cast<const ulonglong2*>(x);
+  for (uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_chunks; q += warps) {
+    const ulonglong2* src = A2 + q * kMatvecChunk + lane;
+    const ulonglong2* xs = x2 + (q % chunks_per_row) * kMatvecChunk + lane;
+    ulonglong2 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a[k].x), "=l"(a[k].y) : "l"(src + 32 * k));
+    F61::Acc acc = F61::acc_zero();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const ulonglong2 xv = __ldg(xs + 32 * k);
+      F61::mac(acc, a[k].x, xv.x);
+      F61::mac(acc, a[k].y, xv.y);
+    }
+    uint64_t s = F61::acc_reduce(acc);  // 16 products: below the 32-term bound of the lazy accumulator
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s = F61::add(s, __shfl_down_sync(0xffffffffu, s, off));
+    if (lane == 0) partial[q] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_matvec61_finish(const uint64_t* __restrict__ partial, uint32_t rows, uint32_t chunks_per_row, uint64_t* __restrict__ y) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const uint64_t* p = partial + (uint64_t)r * chunks_per_row;
+  uint64_t s = 0;
+  for (uint32_t k = 0; k < chunks_per_row; ++k) s = F61::add(s, p[k]);
+  y[r] = s;
+}
+
 // Matrix::vandermonde(n, m), xs = 1..n (matrix.h:445-460): thread = one row
 template <class F>
 __global__ void k_vandermonde(uint32_t n, uint32_t m, typename F::E* __restrict__ out) {
@@ -1307,6 +1353,44 @@ __global__ void k_vandermonde(uint32_t n, uint32_t m, typename F::E* __restrict_
   for (uint32_t j = 0; j < m; ++j) {
     out[(uint64_t)i * m + j] = v;
     v = F::mul(v, x);
+  }
+}
+
+// Matrix::vandermonde(n, m, xs) (matrix.h:445-460): row i = (1, xs[i], xs[i]^2, ...); thread = one row
+template <class F>
+__global__ void k_vandermonde_xs(uint32_t n, uint32_t m, const typename F::E* __restrict__ xs,
+                                 typename F::E* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const typename F::E x = xs[i];
+  typename F::E v = F::one();
+  for (uint32_t j = 0; j < m; ++j) {
+    out[(uint64_t)i * m + j] = v;
+    v = F::mul(v, x);
+  }
+}
+
+// Polynomial::evaluate (poly.h:56-64) of N polynomials at n caller-chosen points: Horner from the top coefficient.
+// coeffs: planes [t+1][N] (coefficient k of polynomial j at k*N + j); value (j, i) at out[i*stride_i + j*stride_j].
+// The points sit in shared memory; thread = one polynomial, its coefficients re-read per point (L1/L2 resident).
+template <class F>
+__global__ void __launch_bounds__(256)
+k_poly_eval(const typename F::E* __restrict__ coeffs, uint64_t N, uint32_t t, const typename F::E* __restrict__ xs,
+            uint32_t n, typename F::E* __restrict__ out, uint64_t stride_i, uint64_t stride_j) {
+  typedef typename F::E E;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  E* sx = reinterpret_cast<E*>(dyn_smem);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sx[i] = xs[i];
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += stride) {
+    E* dst = out + j * stride_j;
+    for (uint32_t i = 0; i < n; ++i) {
+      const E x = sx[i];
+      E r = coeffs[(uint64_t)t * N + j];
+      for (int64_t k = (int64_t)t - 1; k >= 0; --k) r = F::add(coeffs[(uint64_t)k * N + j], F::mul(r, x));
+      dst[(uint64_t)i * stride_i] = r;
+    }
   }
 }
 

@@ -2208,7 +2208,17 @@ static int matvec_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* A, u
   const int grid = (int)std::min<uint64_t>(rows, (uint64_t)ctx->sm_count * 8);
   if constexpr (F::BYTES == 8) {
     if ((cols & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
-      if (cols >= 256) {  // one warp per row
+      if (cols % 512 == 0 && (uint64_t)rows * cols >= (1ull << 22) && !env_flag("SCLGPU_MATVEC_WARP")) {
+        // long rows: chunked sweep in memory order + per-row finish (partials in stream-ordered scratch)
+        const uint32_t cpr = cols / 512;
+        const uint64_t n_chunks = (uint64_t)rows * cpr;
+        StreamBuf part(ctx, st);
+        CK(part.alloc(n_chunks * sizeof(uint64_t)));
+        const int cgrid = (int)std::min<uint64_t>((n_chunks + 7) / 8, (uint64_t)ctx->sm_count * 8);
+        k_matvec61_chunks<<<cgrid, 256, 0, st>>>(A, n_chunks, cpr, x, part.as<uint64_t>());
+        CKL();
+        k_matvec61_finish<<<(rows + 255) / 256, 256, 0, st>>>(part.as<uint64_t>(), rows, cpr, y);
+      } else if (cols >= 256) {  // one warp per row
         const int wgrid = (int)std::min<uint64_t>(((uint64_t)rows + 7) / 8, (uint64_t)ctx->sm_count * 8);
         k_matvec61_warp<<<wgrid, 256, 0, st>>>(A, rows, cols, x, y);
       } else {
@@ -2332,6 +2342,117 @@ static int vandermonde_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, void* out) 
 }
 extern "C" int sclgpu_fp61_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, uint64_t* o) { return guarded(c, [&] { return vandermonde_host<F61>(c, n, m, o); }); }
 extern "C" int sclgpu_fp127_vandermonde(sclgpu_ctx* c, uint32_t n, uint32_t m, void* o) { return guarded(c, [&] { return vandermonde_host<F127>(c, n, m, o); }); }
+
+// Matrix::vandermonde(n, m, xs) with the caller's nodes (matrix.h:445-460)
+template <class F>
+static int vandermonde_xs_host(sclgpu_ctx* ctx, uint32_t n, uint32_t m, const void* xs, uint32_t n_xs, void* out) {
+  typedef typename F::E E;
+  if (!ctx) return SCLGPU_EINVAL;
+  if (n_xs != n) return fail(ctx, SCLGPU_EINVAL, "|xs| != number of rows");
+  if (n == 0 || m == 0) return SCLGPU_OK;  // the reference builds an empty matrix here (no "n or m cannot be 0" check)
+  if (!xs || !out) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  HostOp hop(ctx);
+  void *dx, *dv;
+  RET(hop.up(xs, (size_t)n * sizeof(E), &dx));
+  RET(hop.dev((size_t)n * m * sizeof(E), &dv));
+  k_vandermonde_xs<F><<<(n + 127) / 128, 128, 0, hop.st>>>(n, m, (const E*)dx, (E*)dv);
+  CKL();
+  return hop.down(out, dv, (size_t)n * m * sizeof(E));
+}
+extern "C" int sclgpu_fp61_vandermonde_xs(sclgpu_ctx* c, uint32_t n, uint32_t m, const uint64_t* xs, uint32_t nx, uint64_t* o) { return guarded(c, [&] { return vandermonde_xs_host<F61>(c, n, m, xs, nx, o); }); }
+extern "C" int sclgpu_fp127_vandermonde_xs(sclgpu_ctx* c, uint32_t n, uint32_t m, const void* xs, uint32_t nx, void* o) { return guarded(c, [&] { return vandermonde_xs_host<F127>(c, n, m, xs, nx, o); }); }
+
+// Polynomial::evaluate (poly.h:56-64) of N polynomials at n caller-chosen points.  xs: HOST pointer (n points).
+template <class F>
+static int poly_eval_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d_coeffs, uint64_t N, uint32_t t,
+                        const typename F::E* d_xs, uint32_t n, typename F::E* d_out, uint64_t si, uint64_t sj) {
+  typedef typename F::E E;
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const size_t smem = (size_t)n * sizeof(E);
+  if (smem > 200 * 1024) return fail(ctx, SCLGPU_EINVAL, "poly_evaluate: more than 200 KiB of evaluation points");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_poly_eval<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_poly_eval<F><<<grid_for(ctx, N, 256, 8), 256, smem, st>>>(d_coeffs, N, t, d_xs, n, d_out, si, sj);
+  CKL();
+  return SCLGPU_OK;
+}
+template <class F>
+static int poly_eval_dev(sclgpu_ctx* ctx, const void* d_coeffs, uint64_t N, uint32_t t, const void* xs, uint32_t n,
+                         void* d_out, int layout) {
+  typedef typename F::E E;
+  if (!ctx || ((!d_coeffs || !d_out || !xs) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  if (layout != SCLGPU_PARTY_MAJOR && layout != SCLGPU_SECRET_MAJOR) return fail(ctx, SCLGPU_EINVAL, "bad layout");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  StreamBuf dx(ctx, ctx->stream);
+  CK(dx.alloc((size_t)n * sizeof(E)));
+  CK(cudaMemcpyAsync(dx.p, xs, (size_t)n * sizeof(E), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // xs is the caller's host buffer
+  uint64_t si, sj;
+  strides_for(layout, N, n, si, sj);
+  return poly_eval_on<F>(ctx, ctx->stream, (const E*)d_coeffs, N, t, dx.as<E>(), n, (E*)d_out, si, sj);
+}
+// host form: coeffs [N][t+1] (row j = the coefficients of polynomial j, constant term first, as
+// Polynomial::coefficients() holds them), out [N][n]
+template <class F>
+static int poly_eval_host(sclgpu_ctx* ctx, const void* coeffs, uint64_t N, uint32_t t, const void* xs, uint32_t n, void* out) {
+  typedef typename F::E E;
+  if (!ctx || ((!coeffs || !out || !xs) && N && n)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (N == 0 || n == 0) return SCLGPU_OK;
+  const uint64_t m = (uint64_t)t + 1;
+  uint64_t chunk = std::max<uint64_t>((256ull << 20) / (std::max<uint64_t>(m, n) * sizeof(E)), 1024);
+  chunk = std::min(chunk, std::min(N, kHostChunk));
+  const int nbuf = N > chunk ? 2 : 1;
+  PoolScope pool_scope(ctx);
+  PoolBuf din[2], dpl[2], dpm[2], dsm[2], dx;
+  CK(dx.alloc((size_t)n * sizeof(E)));
+  for (int k = 0; k < nbuf; ++k) {
+    CK(din[k].alloc(chunk * m * sizeof(E)));
+    CK(dpl[k].alloc(chunk * m * sizeof(E)));
+    CK(dpm[k].alloc(chunk * n * sizeof(E)));
+    CK(dsm[k].alloc(chunk * n * sizeof(E)));
+  }
+  CK(ctx->stager.h2d(ctx->pipe[0], dx.p, xs, (size_t)n * sizeof(E)));
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(ctx->stager.drain());
+  const E* hc = reinterpret_cast<const E*>(coeffs);
+  E* ho = reinterpret_cast<E*>(out);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < N; c0 += chunk, k ^= (nbuf - 1)) {
+    const uint64_t nc = std::min(chunk, N - c0);
+    cudaStream_t st = ctx->pipe[k];
+    CK(ctx->stager.h2d(st, din[k].p, hc + c0 * m, nc * m * sizeof(E)));
+    RET(transpose_on<E>(ctx, st, din[k].as<E>(), nc, m, dpl[k].as<E>()));          // [nc][t+1] -> planes [t+1][nc]
+    RET(poly_eval_on<F>(ctx, st, dpl[k].as<E>(), nc, t, dx.as<E>(), n, dpm[k].as<E>(), nc, 1));
+    RET(transpose_on<E>(ctx, st, dpm[k].as<E>(), n, nc, dsm[k].as<E>()));          // [n][nc] -> [nc][n]
+    CK(ctx->stager.d2h(st, ho + c0 * n, dsm[k].p, nc * n * sizeof(E)));
+  }
+  CK(cudaStreamSynchronize(ctx->pipe[0]));
+  CK(cudaStreamSynchronize(ctx->pipe[1]));
+  CK(ctx->stager.drain());
+  return SCLGPU_OK;
+}
+extern "C" int sclgpu_fp61_poly_evaluate(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, const uint64_t* xs, uint32_t n, uint64_t* o) { return guarded(c, [&] { return poly_eval_host<F61>(c, k, N, t, xs, n, o); }); }
+extern "C" int sclgpu_fp127_poly_evaluate(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, const void* xs, uint32_t n, void* o) { return guarded(c, [&] { return poly_eval_host<F127>(c, k, N, t, xs, n, o); }); }
+extern "C" int sclgpu_fp61_poly_evaluate_dev(sclgpu_ctx* c, const uint64_t* k, uint64_t N, uint32_t t, const uint64_t* xs, uint32_t n, uint64_t* o, int layout) { return guarded(c, [&] { return poly_eval_dev<F61>(c, k, N, t, xs, n, o, layout); }); }
+extern "C" int sclgpu_fp127_poly_evaluate_dev(sclgpu_ctx* c, const void* k, uint64_t N, uint32_t t, const void* xs, uint32_t n, void* o, int layout) { return guarded(c, [&] { return poly_eval_dev<F127>(c, k, N, t, xs, n, o, layout); }); }
+
+// Matrix::transpose (matrix.h:344-355) on a host matrix
+template <class E>
+static int transpose_host(sclgpu_ctx* ctx, const void* in, uint64_t rows, uint64_t cols, void* out) {
+  if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (rows == 0 || cols == 0) return SCLGPU_OK;
+  HostOp hop(ctx);
+  void *di, *dout;
+  RET(hop.up(in, rows * cols * sizeof(E), &di));
+  RET(hop.dev(rows * cols * sizeof(E), &dout));
+  RET(transpose_on<E>(ctx, hop.st, (const E*)di, rows, cols, (E*)dout));
+  return hop.down(out, dout, rows * cols * sizeof(E));
+}
+extern "C" int sclgpu_fp61_transpose(sclgpu_ctx* c, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) { return guarded(c, [&] { return transpose_host<uint64_t>(c, in, rows, cols, out); }); }
+extern "C" int sclgpu_fp127_transpose(sclgpu_ctx* c, const void* in, uint64_t rows, uint64_t cols, void* out) { return guarded(c, [&] { return transpose_host<E127>(c, in, rows, cols, out); }); }
 
 static int sclgpu_fp61_transpose_dev_impl(sclgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
   if (!ctx || ((!in || !out) && rows && cols)) return fail(ctx, SCLGPU_EINVAL, "null argument");

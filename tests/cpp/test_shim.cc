@@ -237,6 +237,26 @@ int main() {
     }
   }
 
+  // ---- Matrix::vandermonde(n, m, xs), scalarMultiply, transpose, Polynomial::evaluate at caller points
+  {
+    PRG prg = PRG::create("small surface");
+    const auto xs = math::Vector<Fp61>::random(24, prg);
+    REQUIRE(sclgpu::vandermonde<Fp61>(ctx, 24, 9, xs).equals(math::Matrix<Fp61>::vandermonde(24, 9, xs)));
+    REQUIRE(throwsInvalid([&] { (void)sclgpu::vandermonde<Fp61>(ctx, 25, 9, xs); }, "|xs| != number of rows"));
+    const auto A = math::Matrix<Fp61>::random(37, 19, prg);
+    const Fp61 s = Fp61::random(prg);
+    REQUIRE(sclgpu::scalarMultiply(ctx, A, s).equals(A.scalarMultiply(s)));
+    REQUIRE(sclgpu::transpose(ctx, A).equals(A.transpose()));
+    std::vector<math::Polynomial<Fp61>> polys;
+    for (std::size_t j = 0; j < 300; ++j) polys.push_back(math::Polynomial<Fp61>::create(math::Vector<Fp61>::random(1 + j % 17, prg)));
+    polys.push_back(math::Polynomial<Fp61>());
+    const auto ys = sclgpu::evaluate(ctx, polys, xs);
+    for (std::size_t j = 0; j < polys.size(); ++j)
+      for (std::size_t i = 0; i < xs.size(); ++i) REQUIRE(ys(j, i) == polys[j].evaluate(xs[i]));
+    const auto x127 = math::Vector<Fp127>::random(5, prg);
+    REQUIRE(sclgpu::vandermonde<Fp127>(ctx, 5, 6, x127).equals(math::Matrix<Fp127>::vandermonde(5, 6, x127)));
+  }
+
   // ---- additiveShare (test/scl/ss/test_additive.cc: shares sum to the secret), both fields, PRG state
   {
     for (std::size_t n : {1, 2, 5, 33}) {

@@ -1045,6 +1045,47 @@ def test_full_size_c5_matvec_and_muladd(ctx, pkg, port):
     assert torch.equal(lhs, t1)
 
 
+# ------------------------------------------------------------------ Matrix::vandermonde(xs), Polynomial::evaluate, transpose
+@pytest.mark.parametrize("field", [61, 127])
+def test_vandermonde_xs_poly_evaluate_transpose(ctx, pkg, orc, port, field):
+    """Matrix::vandermonde(n, m, xs) with caller nodes (matrix.h:445-460, "|xs| != number of rows"),
+    Polynomial::evaluate at caller points (poly.h:56-64) in the host and device forms, Matrix::transpose
+    (matrix.h:344-355) -- against the reference's own functions (ref_driver.cc calls them)."""
+    import torch
+    if orc.kind != "reference":
+        pytest.skip("needs oracle/_ref (the unmodified reference)")
+    p_int = (1 << field) - 1
+    for n, m in ((1, 1), (5, 3), (32, 16), (100, 7)):
+        xs = port.from_ints([(i * i * 7919 + 3) % p_int if i % 5 else p_int - i - 1 for i in range(n)], field)
+        assert np.array_equal(ctx.vandermonde_xs(field, n, m, xs), orc.vandermonde_xs(field, n, m, xs))
+    with pytest.raises(pkg.InvalidArgument, match=r"\|xs\| != number of rows"):
+        ctx.vandermonde_xs(field, 4, 3, port.from_ints([1, 2, 3], field))
+    with pytest.raises(ValueError):
+        orc.vandermonde_xs(field, 4, 3, port.from_ints([1, 2, 3], field))
+    w = 1 if field == 61 else 2
+    for N, t, n in ((1, 0, 1), (7, 3, 5), (3000, 15, 32), (1025, 40, 70), (70000, 2, 3)):
+        coeffs = port.vector_random(field, "poly", 0, N * (t + 1)).reshape((N, t + 1) + ((2,) if w == 2 else ()))
+        if N > 5:
+            coeffs[3, t] = 0       # a zero leading coefficient: Polynomial::create strips it, the value is the same
+            coeffs[4] = 0          # the zero polynomial
+        xs = port.from_ints([0, 1, p_int - 1] + [(j * 104729 + 17) % p_int for j in range(n)], field)[:n]
+        want = orc.poly_evaluate(field, coeffs, xs)
+        assert np.array_equal(ctx.poly_evaluate(field, coeffs, xs), want)
+        # device form: coefficient planes [t+1][N], both layouts
+        planes = np.ascontiguousarray(np.swapaxes(coeffs.reshape(N, t + 1, w), 0, 1))
+        d_pl = torch.from_numpy(planes.view(np.int64)).cuda()
+        d_pm = torch.empty((n, N, w), dtype=torch.int64, device="cuda")
+        d_sm = torch.empty((N, n, w), dtype=torch.int64, device="cuda")
+        ctx.poly_evaluate_dev(field, d_pl, N, t, xs, d_pm, pkg.binding.PARTY_MAJOR)
+        ctx.poly_evaluate_dev(field, d_pl, N, t, xs, d_sm, pkg.binding.SECRET_MAJOR)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_sm.cpu().numpy().view(np.uint64).reshape(want.shape), want)
+        assert np.array_equal(np.swapaxes(d_pm.cpu().numpy().view(np.uint64), 0, 1).reshape(want.shape), want)
+    for rows, cols in ((1, 1), (3, 5), (64, 33), (1000, 17)):
+        A = port.vector_random(field, "tr", 0, rows * cols).reshape((rows, cols) + ((2,) if w == 2 else ()))
+        assert np.array_equal(ctx.transpose(field, A), orc.transpose(field, A))
+
+
 # ------------------------------------------------------------------ gather / multi-device / async on whatever is visible
 @pytest.mark.parametrize("N,n", [(4096, 32), (1001, 5), (2, 3), (100000, 16)])
 def test_recover_p_gather_destinations(ctx, orc, N, n):
