@@ -181,6 +181,17 @@ int sclgpu_fp61_shamir_share_recover_dev(sclgpu_ctx* ctx, const uint64_t* d_secr
                                          const uint64_t* d_rec_shares, const uint64_t* alphas,
                                          const uint64_t* x, uint64_t* d_out);
 
+/* The same launch with the all-gather of the reconstructed secrets fused in (see
+ * sclgpu_fp61_recover_p_gather_dev): secret j of this rank's slice is stored to
+ * d_dsts[r][offset + j] for every r < n_dsts <= 8 by the reconstruction warps, i.e. the NVLink
+ * traffic runs under the share groups' work. */
+int sclgpu_fp61_shamir_share_recover_gather_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N,
+                                                uint32_t t, uint32_t n, const uint8_t seed[16],
+                                                uint64_t first_block, uint64_t* d_shares,
+                                                const uint64_t* d_rec_shares, const uint64_t* alphas,
+                                                const uint64_t* x, uint64_t* const* d_dsts,
+                                                uint32_t n_dsts, uint64_t offset);
+
 /* ---- ss::shamirRecoverC (shamir.h:203-258, Berlekamp-Welch) on N sharings ---------
  * t = (n-1)/3 and the first np = 3t+1 shares of each sharing are used, as in the
  * reference; alphas == NULL means 1..n (shamir.h:256-258).  Per sharing j:

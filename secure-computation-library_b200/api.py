@@ -236,6 +236,17 @@ class Context:
         self._check(self.lib.sclgpu_fp61_shamir_share_recover_dev(self._ctx, _dp(secrets), N, t, n, seed16(seed), first_block,
                                                                   _dp(shares), _dp(rs), _p(A), _p(X), _dp(out)))
 
+    def shamir_share_recover_gather_dev(self, secrets, N: int, t: int, n: int, seed, first_block: int, shares, dst_ptrs,
+                                        offset: int, rec_shares=None, alphas=None, x: int | None = None):
+        """shamir_share_recover_dev with the all-gather fused in: reconstructed secret j goes to dst_ptrs[r] + 8*(offset + j)
+        for every r (device addresses valid on this device: own or peer memory)."""
+        A = None if alphas is None else _c(alphas)
+        X = from_ints([x or 0], 61)
+        rs = shares if rec_shares is None else rec_shares
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+        self._check(self.lib.sclgpu_fp61_shamir_share_recover_gather_dev(
+            self._ctx, _dp(secrets), N, t, n, seed16(seed), first_block, _dp(shares), _dp(rs), _p(A), _p(X), arr, len(dst_ptrs), offset))
+
     def shamir_share_coeffs_dev(self, field: int, coeffs, N: int, t: int, n: int, shares, layout: int = B.PARTY_MAJOR):
         self._check(self._f(field, "shamir_share_coeffs_dev")(self._ctx, _dp(coeffs), N, t, n, _dp(shares), layout))
 

@@ -115,6 +115,7 @@ def load() -> C.CDLL:
         _sig(lib, f"sclgpu_{f}_transpose", _int, _vp, _vp, _u64, _u64, _vp)
         _sig(lib, f"sclgpu_{f}_transpose_dev", _int, _vp, _vp, _u64, _u64, _vp)
     _sig(lib, "sclgpu_fp61_shamir_share_recover_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp)
+    _sig(lib, "sclgpu_fp61_shamir_share_recover_gather_dev", _int, _vp, _vp, _u64, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _u64)
     _sig(lib, "sclgpu_fp61_recover_p_gather_dev", _int, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _u32, _u64)
     _sig(lib, "sclgpu_memcpy_d2d", _int, _vp, _vp, _vp, C.c_size_t)
     _sig(lib, "sclgpu_ipc_export", _int, _vp, _vp, _vp)

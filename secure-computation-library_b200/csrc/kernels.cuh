@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "aes_ctr.cuh"
+#include "share_tc.h"
 #include "field.cuh"
 
 namespace sclgpu {
@@ -890,14 +891,7 @@ __device__ __forceinline__ uint64_t f61_rot(uint64_t acc, int s) {  // acc * 2^s
   return s == 0 ? x : (((x << s) & F61::P) | (x >> (61 - s)));
 }
 
-// Destinations of the reconstructed secrets when the result is gathered while it is produced: dst[r] is where THIS
-// rank's slice starts inside rank r's copy of the gathered vector (dst[self] = local memory, the others peer memory
-// mapped over NVLink: cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess).  count == 0: plain `out`.
-struct GatherDst {
-  uint64_t* dst[8];
-  uint32_t count;
-};
-
+// GatherDst (share_tc.h): where the reconstructed secrets go when the all-gather is fused into the kernel
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_recover61_pm(const uint64_t* __restrict__ in, uint64_t N, uint32_t n, uint64_t stride_i,

@@ -1692,9 +1692,21 @@ extern "C" int sclgpu_enable_peer(sclgpu_ctx* ctx, int peer_device) {
 static int share_recover61_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
                                const uint8_t seed[16], uint64_t first_block, uint64_t* d_shares,
                                const uint64_t* d_rec_shares, const uint64_t* alphas, const uint64_t* x,
-                               uint64_t* d_out) {
-  if (!ctx || !seed || ((!d_secrets || !d_shares || !d_rec_shares || !d_out) && N && n))
+                               uint64_t* d_out, uint64_t* const* d_dsts = nullptr, uint32_t n_dsts = 0, uint64_t offset = 0) {
+  if (!ctx || !seed || ((!d_secrets || !d_shares || !d_rec_shares) && N && n))
     return fail(ctx, SCLGPU_EINVAL, "null argument");
+  GatherDst gd;
+  std::memset(&gd, 0, sizeof(gd));
+  if (d_dsts) {  // reconstructed secrets gathered into every destination at `offset` instead of d_out
+    if (n_dsts < 1 || n_dsts > 8) return fail(ctx, SCLGPU_EINVAL, "1..8 gather destinations");
+    for (uint32_t r = 0; r < n_dsts; ++r) {
+      if (!d_dsts[r]) return fail(ctx, SCLGPU_EINVAL, "null gather destination");
+      gd.dst[r] = d_dsts[r] + offset;
+    }
+    gd.count = n_dsts;
+    d_out = gd.dst[0];
+  }
+  if (!d_out && N && n) return fail(ctx, SCLGPU_EINVAL, "null argument");
   if (n >= (1u << 31)) return fail(ctx, SCLGPU_EINVAL, "n too large");
   CK(cudaSetDevice(ctx->device));
   if (N == 0 || n == 0) return SCLGPU_OK;
@@ -1705,9 +1717,11 @@ static int share_recover61_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint6
   const bool fused = t <= kTcMaxT && n <= kTcMaxParties && share_tc_enabled() && !env_flag("SCLGPU_SHARE_GENERIC") &&
                      !env_flag("SCLGPU_NO_FUSED_STEP") && N % 2 == 0 &&
                      ((reinterpret_cast<uintptr_t>(d_rec_shares) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
-  if (!fused) {
+  uintptr_t galign = 0;
+  for (uint32_t r = 0; r < gd.count; ++r) galign |= reinterpret_cast<uintptr_t>(gd.dst[r]);
+  if (!fused || (galign & 15)) {
     RET(share_strided_on<F61>(ctx, st, d_secrets, N, t, n, seed, first_block, d_shares, N, 1));
-    return recover_p_on<F61>(ctx, st, d_rec_shares, N, n, N, 1, d_basis, d_out);
+    return recover_p_on<F61>(ctx, st, d_rec_shares, N, n, N, 1, d_basis, d_out, gd.count ? &gd : nullptr);
   }
   auto it = ctx->rec_basis_cache.find(d_basis);
   if (it == ctx->rec_basis_cache.end()) {
@@ -1732,10 +1746,11 @@ static int share_recover61_dev(sclgpu_ctx* ctx, const uint64_t* d_secrets, uint6
   const AesKey key = aes_expand(seed);
   ctx->launches++;
   cudaError_t e = share_recover61_launch(st, ctx->sm_count, env_int("SCLGPU_SR_WARPS", 4), key, it->second, ctx->d_t0, d_bmat, first_block, d_secrets, N, t, n,
-                                         d_shares, d_rec_shares, d_out);
+                                         d_shares, d_rec_shares, d_out, gd.count ? &gd : nullptr);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "launch");
   return SCLGPU_OK;
 }
+extern "C" int sclgpu_fp61_shamir_share_recover_gather_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* sh, const uint64_t* rs, const uint64_t* a, const uint64_t* x, uint64_t* const* d, uint32_t nd, uint64_t off) { return guarded(c, [&] { return d ? share_recover61_dev(c, s, N, t, n, seed, fb, sh, rs, a, x, nullptr, d, nd, off) : fail(c, SCLGPU_EINVAL, "null argument"); }); }
 extern "C" int sclgpu_fp61_shamir_share_recover_dev(sclgpu_ctx* c, const uint64_t* s, uint64_t N, uint32_t t, uint32_t n, const uint8_t seed[16], uint64_t fb, uint64_t* sh, const uint64_t* rs, const uint64_t* a, const uint64_t* x, uint64_t* o) { return guarded(c, [&] { return share_recover61_dev(c, s, N, t, n, seed, fb, sh, rs, a, x, o); }); }
 
 // shamirRecoverP on Vector<Array<FF, W>> (shamir.h:100-104 with T = Array): the basis of nodes 1..n at 0

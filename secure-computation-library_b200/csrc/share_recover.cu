@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(128 * GROUPS + 32 * RWARPS, 1)
 k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ RecBasis61 basis,
                   const uint32_t* __restrict__ g_t0, const uint4* __restrict__ g_bmat, uint64_t first_block,
                   const uint64_t* __restrict__ secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* out,
-                  const uint64_t* rec_in, uint64_t* __restrict__ rec_out, uint32_t dependent) {
+                  const uint64_t* rec_in, uint64_t* __restrict__ rec_out, uint32_t dependent,
+                  const __grid_constant__ GatherDst gather) {
   // warp roles: [0, RWARPS) reconstruction, then GROUPS x 4 share warps
   constexpr uint32_t kRecWarps = RWARPS, kRecThreads = 32 * kRecWarps;
   static_assert(RWARPS % 4 == 0, "share warp w must sit on tensor-memory lane quarter w % 4");
@@ -270,7 +271,17 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
                            rot61(acc[h][4], 53) + rot61(acc[h][5], 13);  // < 6 * 2^61 < 2^64
         r[h] = F61::from_raw(s);
       }
-      if (j < N) *reinterpret_cast<ulonglong2*>(rec_out + j) = make_ulonglong2(r[0], r[1]);
+      if (j < N) {
+        if (gather.count == 0) {
+          *reinterpret_cast<ulonglong2*>(rec_out + j) = make_ulonglong2(r[0], r[1]);
+        } else {
+          // all-gather fused in: the pair goes to every rank's copy of the gathered vector (posted stores over NVLink
+          // peer memory), hidden under the share groups' work
+#pragma unroll
+          for (uint32_t g = 0; g < 8u; ++g)
+            if (g < gather.count) *reinterpret_cast<ulonglong2*>(gather.dst[g] + j) = make_ulonglong2(r[0], r[1]);
+        }
+      }
     }
   }
 
@@ -294,17 +305,19 @@ cudaError_t share_recover61_prepare() {
 cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int rec_warps, const AesKey& key, const RecBasis61& basis,
                                    const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
                                    const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
-                                   const uint64_t* d_rec_in, uint64_t* d_rec_out) {
+                                   const uint64_t* d_rec_in, uint64_t* d_rec_out, const GatherDst* gather) {
+  GatherDst gd{};
+  if (gather) gd = *gather;
   const uint64_t tiles = (N + 127) / 128;
   const int grid = (int)std::min<uint64_t>((tiles + kSrGroups - 1) / kSrGroups, (uint64_t)sm_count);
   const uint32_t dependent = (d_rec_in == d_shares) ? 1u : 0u;
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
   if (rec_warps == 4) {
     k_share_recover61<kSrGroups, 4><<<grid, 128 * kSrGroups + 128, kSrDynSmem, st>>>(
-        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent);
+        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd);
   } else {
     k_share_recover61<kSrGroups, 8><<<grid, 128 * kSrGroups + 256, kSrDynSmem, st>>>(
-        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent);
+        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd);
   }
   return cudaGetLastError();
 }

@@ -36,13 +36,20 @@ static inline uint32_t tc_bmat_offset(uint32_t r, uint32_t kk) {
 struct RecBasis61 {
   uint32_t l[32][3];
 };
+// Destinations of reconstructed secrets when the result is gathered while it is produced: dst[r] is where THIS rank's
+// slice starts inside rank r's copy of the gathered vector (own memory or peer memory mapped over NVLink:
+// cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess).  count == 0: the plain output pointer.
+struct GatherDst {
+  uint64_t* dst[8];
+  uint32_t count;
+};
 cudaError_t share_recover61_prepare();
 // d_rec_in == d_shares: reconstruct the sharings produced by this launch (tile by tile, as they are stored);
 // otherwise d_rec_in holds another batch of N sharings in the same party-major [n][N] layout.
 cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int rec_warps, const AesKey& key, const RecBasis61& basis,
                                    const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
                                    const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
-                                   const uint64_t* d_rec_in, uint64_t* d_rec_out);
+                                   const uint64_t* d_rec_in, uint64_t* d_rec_out, const GatherDst* gather = nullptr);
 
 cudaError_t share_tc_prepare();
 // variant 1: A in shared memory, 3 groups; variants >= 2: A in tensor memory with

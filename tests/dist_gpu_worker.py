@@ -109,6 +109,21 @@ def main():
     assert np.array_equal(mine.cpu().numpy().view(np.uint64), port.vector_random(61, "secrets", 0, Ng)), \
         "gathered reconstruction differs on rank %d" % rank
     dist.barrier()
+    # the same gather from the single-launch step (k_share_recover61 with gather destinations)
+    zero = torch.zeros(Ng, dtype=torch.int64, device=dev)
+    ctx.memcpy_d2d(buf, zero.data_ptr(), 8 * Ng)
+    torch.cuda.synchronize()
+    dist.barrier()
+    d_gsh2 = torch.empty((n, sg.count), dtype=torch.int64, device=dev)
+    ctx.shamir_share_recover_gather_dev(d_gsec, sg.count, t, n, "shamir bench", sh.share_first_block(61, t, 77, sg), d_gsh2, peers,
+                                        sg.lo, rec_shares=d_gsh)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ctx.memcpy_d2d(mine.data_ptr(), buf, 8 * Ng)
+    torch.cuda.synchronize()
+    assert np.array_equal(mine.cpu().numpy().view(np.uint64), port.vector_random(61, "secrets", 0, Ng)), \
+        "gathered reconstruction (single-launch step) differs on rank %d" % rank
+    dist.barrier()
     for r in range(world):
         if r != rank:
             ctx.ipc_close(peers[r])

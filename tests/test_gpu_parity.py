@@ -1106,6 +1106,33 @@ def test_recover_p_gather_destinations(ctx, orc, N, n):
         assert not h[:off].any() and not h[off + N:].any()
 
 
+def test_fused_launch_with_gather_destinations(ctx, orc):
+    """sclgpu_fp61_shamir_share_recover_gather_dev: share planes as usual, the reconstructed secrets of ANOTHER batch
+    stored into every destination at the offset (single GPU: several local buffers; peers: tests/dist_gpu_worker.py)."""
+    import torch
+    N, t, n = 40000, 15, 32
+    secrets = orc.vector_random(61, "secrets", 0, N)
+    prev = orc.shamir_share(61, secrets, t, n, "previous batch", 0)
+    d_prev = torch.from_numpy(np.ascontiguousarray(prev.T).view(np.int64)).cuda()
+    d_sec = torch.from_numpy(secrets.view(np.int64)).cuda()
+    d_sh = torch.zeros((n, N), dtype=torch.int64, device="cuda")
+    off = 10
+    bufs = [torch.zeros(N + 32, dtype=torch.int64, device="cuda") for _ in range(4)]
+    ctx.shamir_share_recover_gather_dev(d_sec, N, t, n, "shamir bench", 5, d_sh, [b_.data_ptr() for b_ in bufs], off, rec_shares=d_prev)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, orc.shamir_share(61, secrets, t, n, "shamir bench", 5))
+    for b_ in bufs:
+        h = b_.cpu().numpy().view(np.uint64)
+        assert np.array_equal(h[off:off + N], secrets) and not h[:off].any() and not h[off + N:].any()
+    # same batch (dependent mode), odd offset: 8-byte aligned destinations fall back to the two-kernel path
+    for b_ in bufs:
+        b_.zero_()
+    ctx.shamir_share_recover_gather_dev(d_sec, N, t, n, "shamir bench", 5, d_sh, [b_.data_ptr() for b_ in bufs], 7)
+    torch.cuda.synchronize()
+    for b_ in bufs:
+        assert np.array_equal(b_.cpu().numpy().view(np.uint64)[7:7 + N], secrets)
+
+
 def test_multi_context_vs_oracle(pkg, orc):
     """sclgpu_mctx over every visible GPU (one is enough: the slicing and the PRG offsets are the same code): share,
     recoverP, recoverD and Vector::random equal the one-PRG batch of the oracle."""

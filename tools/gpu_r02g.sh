@@ -2,7 +2,7 @@
 # 2-GPU session: multi-GPU tests + bench under torchrun
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "multi_gpu_nccl or gather_destinations or multi_context or async_host or fused_share" > gpurun_out/r02g_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "multi_gpu_nccl or gather or multi_context or fused" > gpurun_out/r02g_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r02g_pytest.log
 tail -15 gpurun_out/r02g_pytest.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02g_bench2.json 2> gpurun_out/r02g_bench2.err
