@@ -83,7 +83,7 @@ k_recover_c_cta(const typename F::E* __restrict__ in, uint64_t N, uint64_t strid
   E* R = X + np;
   E* Qt = R + np;
   int* bad = reinterpret_cast<int*>(Qt + np);          // per row: disagrees with the decoded polynomial
-  int* ctl = bad + np;                                   // [0] pivot row, [1] flag, [2] degree, [3] count
+  int* ctl = bad + np;                                   // [1] flag, [2] degree, [3] count, [4..5] pivot rows
   const uint32_t tid = threadIdx.x;
   const bool row = tid < np;
   const E minus1 = F::neg(F::one());
@@ -116,11 +116,12 @@ k_recover_c_cta(const typename F::E* __restrict__ in, uint64_t N, uint64_t strid
       }
       int my_col = -1;
       for (uint32_t c = 0; c < np; ++c) {
-        if (tid == 0) ctl[0] = 0x7fffffff;
+        int* slot = ctl + 4 + (c & 1u);  // alternating pivot slots: resetting the next one never touches the one being read
+        if (tid == 0) *slot = 0x7fffffff;
         __syncthreads();
-        if (row && my_col < 0 && !F::is_zero(M[(size_t)tid * cols + c])) atomicMin(&ctl[0], (int)tid);
+        if (row && my_col < 0 && !F::is_zero(M[(size_t)tid * cols + c])) atomicMin(slot, (int)tid);
         __syncthreads();
-        const int piv = ctl[0];
+        const int piv = *slot;
         if (piv == 0x7fffffff) continue;  // free unknown
         if ((int)tid == piv) my_col = (int)c;
         const E p = M[(size_t)piv * cols + c];
@@ -233,11 +234,12 @@ k_recover_c_cta(const typename F::E* __restrict__ in, uint64_t N, uint64_t strid
       }
       bool singular = false;
       for (uint32_t c = 0; c < np; ++c) {
-        if (tid == 0) ctl[0] = 0x7fffffff;
+        int* slot = ctl + 4 + (c & 1u);
+        if (tid == 0) *slot = 0x7fffffff;
         __syncthreads();
-        if (row && tid >= c && !F::is_zero(M[(size_t)tid * cols + c])) atomicMin(&ctl[0], (int)tid);
+        if (row && tid >= c && !F::is_zero(M[(size_t)tid * cols + c])) atomicMin(slot, (int)tid);
         __syncthreads();
-        const int piv = ctl[0];
+        const int piv = *slot;
         if (piv == 0x7fffffff) {
           singular = true;
           break;

@@ -42,5 +42,39 @@ for field, W, t, n, N in [(61, 2, 15, 32, 300), (61, 4, 2, 5, 77), (61, 3, 3, 7,
     assert np.array_equal(sh, port.shamir_share_array(field, sec, t, n, "pedersen", 3))
     assert np.array_equal(ctx.recover_p_array(field, sh), sec)
 assert np.array_equal(ctx.hyper_invertible(61, 4, 5), port.hyper_invertible(61, 4, 5))
+# round 2: the single-launch step (both modes, with gather destinations), reconstruction with the gather fused in,
+# Berlekamp-Welch with more than 32 points (CTA per sharing), chunked mat-vec, caller-node Vandermonde / evaluation
+import torch
+N, t, n = 1500, 15, 32
+sec = port.vector_random(61, "secrets", 0, N)
+want = port.shamir_share(61, sec, t, n, "shamir bench", 9)
+d_sec = torch.from_numpy(sec.view(np.int64)).cuda()
+d_sh = torch.zeros((n, N), dtype=torch.int64, device="cuda"); d_sh2 = torch.zeros((n, N), dtype=torch.int64, device="cuda")
+d_out = torch.zeros(N, dtype=torch.int64, device="cuda")
+ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", 9, d_sh, d_out)
+torch.cuda.synchronize()
+assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, want) and np.array_equal(d_out.cpu().numpy().view(np.uint64), sec)
+d_out.zero_()
+ctx.shamir_share_recover_dev(d_sec, N, t, n, "shamir bench", 9, d_sh2, d_out, rec_shares=d_sh)
+bufs = [torch.zeros(N + 8, dtype=torch.int64, device="cuda") for _ in range(3)]
+ctx.shamir_share_recover_gather_dev(d_sec, N, t, n, "shamir bench", 9, d_sh2, [b_.data_ptr() for b_ in bufs], 4, rec_shares=d_sh)
+ctx.recover_p_gather_dev(d_sh, N, n, [b_.data_ptr() for b_ in bufs[:2]], 2)
+torch.cuda.synchronize()
+assert np.array_equal(d_out.cpu().numpy().view(np.uint64), sec)
+assert np.array_equal(bufs[2].cpu().numpy().view(np.uint64)[4:4 + N], sec) and np.array_equal(bufs[0].cpu().numpy().view(np.uint64)[2:2 + N], sec)
+for field, nn in ((61, 40), (127, 34)):
+    tt = (nn - 1) // 3
+    sec = port.vector_random(field, "secrets", 0, 12)
+    sh = port.shamir_share(field, sec, tt, nn, "rc", 0).copy()
+    sh.reshape(12, nn, -1)[::2, 5, 0] ^= np.uint64(3)
+    sh.reshape(12, nn, -1)[1, :tt + 1, 0] ^= np.uint64(7)
+    got, want = ctx.recover_c(field, sh), port.recover_c(field, sh)
+    assert all(np.array_equal(g, w) for g, w in zip(got[:3], want[:3]))
+A = port.vector_random(61, "mat A", 0, 1024 * 4096).reshape(1024, 4096); x = port.vector_random(61, "vec x", 0, 4096)
+assert np.array_equal(ctx.matvec(61, A[:64], x), port.matvec(61, A[:64], x))
+assert np.array_equal(ctx.matvec(61, A, x)[:8], port.matvec(61, A[:8], x))
+xs = port.vector_random(61, "xs", 0, 9)
+cf = port.vector_random(61, "cf", 0, 50 * 6).reshape(50, 6)
+assert ctx.poly_evaluate(61, cf, xs).shape == (50, 9) and ctx.vandermonde_xs(61, 9, 4, xs).shape == (9, 4)
 ctx.close()
 print("SANITIZE_DRIVER_OK")
