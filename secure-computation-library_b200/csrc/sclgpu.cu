@@ -23,6 +23,7 @@
 #include "../../include/sclgpu.h"
 #include "kernels.cuh"
 #include "recover_c_big.cuh"
+#include "recover_c_syndrome.cuh"
 #include "matmul_tc.h"
 #include "share_tc.h"
 #include "host_stage.h"
@@ -1993,6 +1994,36 @@ static int recover_c_on(sclgpu_ctx* ctx, cudaStream_t st, const typename F::E* d
     if (n_failed) *n_failed = bad_big;
     if (bad_big) return fail(ctx, SCLGPU_ECORRECT, "could not correct shares");
     return SCLGPU_OK;
+  }
+  // Sharings with errors: syndrome decoding, one thread each (k_recover_c_syndrome); what it cannot settle -- more than
+  // t errors -- goes on, compacted again, to the elimination kernel below.
+  StreamBuf dpending2(ctx, st);
+  DevBuf dsyn;
+  if (d_pending != nullptr && t >= 1 && t <= kSynMaxT && !env_flag("SCLGPU_RECOVER_C_NOSYN")) {
+    const uint32_t m = t + 1;
+    std::vector<E> cst((size_t)3 * np + (size_t)m * m);
+    for (uint32_t i = 0; i < np; ++i) {
+      E prod = F::one();
+      for (uint32_t j = 0; j < np; ++j)
+        if (j != i) prod = F::mul(prod, F::sub(al[i], al[j]));
+      cst[i] = al[i];
+      cst[np + i] = F::inv(prod);
+      cst[2 * np + i] = prod;
+    }
+    std::copy(coef.begin(), coef.end(), cst.begin() + 3 * np);
+    CK(dsyn.alloc(cst.size() * sizeof(E)));
+    CK(cudaMemcpyAsync(dsyn.p, cst.data(), cst.size() * sizeof(E), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // cst is a local
+    CK(dpending2.alloc(N * sizeof(uint32_t) + sizeof(unsigned long long)));
+    unsigned long long* d_n2 = dpending2.as<unsigned long long>();
+    uint32_t* d_p2 = reinterpret_cast<uint32_t*>(d_n2 + 1);
+    CK(cudaMemsetAsync(d_n2, 0, sizeof(unsigned long long), st));
+    const size_t ssm = cst.size() * sizeof(E);
+    k_recover_c_syndrome<F><<<grid_for(ctx, N, 128, 8), 128, ssm, st>>>(d_shares, si, sj, t, dsyn.as<E>(), d_f, d_e, d_status,
+                                                                       d_pending, d_n_pending, d_p2, d_n2);
+    CKL();
+    d_pending = d_p2;
+    d_n_pending = d_n2;
   }
   const int warps_per_cta = 8;
   const size_t smem = (size_t)warps_per_cta * ((size_t)np * (np + 1) + 3 * np) * sizeof(E);

@@ -31,3 +31,20 @@ for every in (2, 64, 0):
     ok = bool(torch.equal(fo[:, 0], sec)) and int(st.sum().item()) == 0
     print(f"corrupted share in every {every or 'no'} sharing: {ms:.3f} ms  {N / ms / 1e3:.1f} M sharings/s  ok={ok}")
     if every: sh[3, ::every] ^= 5
+
+# several corrupted shares per sharing (up to t), and larger t
+for n2, k_err in ((16, 5), (31, 10), (31, 3)):
+    t2 = (n2 - 1) // 3
+    N2 = 1 << 19
+    sec2 = torch.empty(N2, dtype=torch.int64, device="cuda")
+    sh2 = torch.empty((n2, N2), dtype=torch.int64, device="cuda")
+    ctx.random_dev(61, "secrets", 0, N2, sec2)
+    ctx.shamir_share_dev(61, sec2, N2, t2, n2, "rc", 0, sh2, B.PARTY_MAJOR)
+    for i in range(k_err):
+        sh2[(3 * i + 1) % (3 * t2 + 1)] ^= (7 + i)
+    fo2 = torch.empty((N2, 3 * t2 + 1), dtype=torch.int64, device="cuda")
+    eo2 = torch.empty((N2, t2 + 1), dtype=torch.int64, device="cuda")
+    st2 = torch.empty(N2, dtype=torch.uint8, device="cuda")
+    ms = timeit(lambda: ctx.recover_c_dev(61, sh2, N2, n2, fo2, eo2, st2, B.PARTY_MAJOR))
+    ok = bool(torch.equal(fo2[:, 0], sec2)) and int(st2.sum().item()) == 0
+    print(f"n={n2} t={t2}: {k_err} corrupted shares in EVERY sharing: {ms:.3f} ms  {N2 / ms / 1e3:.1f} M sharings/s  ok={ok}")
