@@ -475,6 +475,9 @@ typedef struct sclgpu_mctx sclgpu_mctx;
 int sclgpu_multi_init(const int* devices, int n_devices, sclgpu_mctx** mctx);
 void sclgpu_multi_destroy(sclgpu_mctx* mctx);
 int sclgpu_multi_device_count(const sclgpu_mctx* mctx);
+/* the slicing rule (pure function, needs no device): units [*lo, *hi) of [0, n_units) go to slice `index` of `parts`;
+ * boundaries are multiples of `align` (2 for Fp61 Vector::random and the plane kernels' 128-bit accesses) */
+int sclgpu_multi_slice(uint64_t n_units, int parts, int index, uint64_t align, uint64_t* lo, uint64_t* hi);
 sclgpu_ctx* sclgpu_multi_context(sclgpu_mctx* mctx, int index); /* the per-device context (borrowed) */
 const char* sclgpu_multi_last_error(const sclgpu_mctx* mctx);
 /* same contracts as the single-device host entry points of the same name */

@@ -125,6 +125,7 @@ def load() -> C.CDLL:
     _sig(lib, "sclgpu_multi_init", _int, _vp, _int, C.POINTER(_vp))
     _sig(lib, "sclgpu_multi_destroy", None, _vp)
     _sig(lib, "sclgpu_multi_device_count", _int, _vp)
+    _sig(lib, "sclgpu_multi_slice", _int, _u64, _int, _int, _u64, C.POINTER(_u64), C.POINTER(_u64))
     _sig(lib, "sclgpu_multi_context", _vp, _vp, _int)
     _sig(lib, "sclgpu_multi_last_error", C.c_char_p, _vp)
     _sig(lib, "sclgpu_multi_fp61_random", _int, _vp, _vp, _u64, _u64, _vp)

@@ -91,6 +91,13 @@ int mfail(sclgpu_mctx* m, int code, const char* msg) {
 
 }  // namespace
 
+// the slicing rule itself (no device needed): slice `index` of `parts` over [0, n_units), boundaries on multiples of `align`
+extern "C" int sclgpu_multi_slice(uint64_t n_units, int parts, int index, uint64_t align, uint64_t* lo, uint64_t* hi) {
+  if (parts < 1 || index < 0 || index >= parts || align < 1 || !lo || !hi) return SCLGPU_EINVAL;
+  slice_of(n_units, parts, index, align, *lo, *hi);
+  return SCLGPU_OK;
+}
+
 extern "C" int sclgpu_multi_init(const int* devices, int n_devices, sclgpu_mctx** out) {
   if (!out) return SCLGPU_EINVAL;
   *out = nullptr;

@@ -266,6 +266,9 @@ extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
   for (auto& kv : ctx->basis_cache) cudaFree(kv.second);
   for (auto& kv : ctx->tc_bmat_cache) cudaFree(kv.second);
   for (auto& kv : ctx->rd_bmat_cache) cudaFree(kv.second);
+  // the chunk buffers held secrets and shares of the caller's batches: wipe them before the memory goes back to the driver
+  for (auto& pb : ctx->pool)
+    if (pb.first) cudaMemset(pb.first, 0, pb.second);
   for (auto& pb : ctx->pool) cudaFree(pb.first);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);

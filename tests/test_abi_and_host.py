@@ -137,3 +137,38 @@ def test_gloo_world2_sharded_share_recover():
     r = subprocess.run(cmd, env=env, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "DIST_OK world=2" in r.stdout, r.stdout[-3000:]
+
+
+def test_multi_device_slicing_rule(pkg):
+    """sclgpu_multi_slice (multi.cu; a pure function, no device): the slices of the multi-device handle tile [0, N)
+    contiguously, start on multiples of `align`, differ in size by at most one aligned group, and agree with the
+    per-process sharding rule (sharding.shard_range) -- so one process over G GPUs and G processes over one GPU each
+    cut a batch, and its PRG stream, at the same places."""
+    import ctypes as C
+
+    lib, sh = pkg.binding.load(), pkg.sharding
+    lo, hi = C.c_uint64(), C.c_uint64()
+    for n_units in (0, 1, 2, 7, 64, 1000, 100003, (1 << 26) + 5):
+        for parts in (1, 2, 3, 4, 8):
+            for align in (1, 2):
+                prev, sizes = 0, []
+                for g in range(parts):
+                    assert lib.sclgpu_multi_slice(n_units, parts, g, align, C.byref(lo), C.byref(hi)) == 0
+                    assert lo.value == prev and hi.value >= lo.value and (lo.value % align == 0 or lo.value == n_units)
+                    s = sh.shard_range(n_units, parts, g, align)
+                    assert (s.lo, s.hi) == (lo.value, hi.value)
+                    sizes.append(hi.value - lo.value)
+                    prev = hi.value
+                assert prev == n_units and max(sizes) - min(sizes) <= 2 * align
+    assert lib.sclgpu_multi_slice(10, 0, 0, 1, C.byref(lo), C.byref(hi)) == pkg.binding.EINVAL
+    assert lib.sclgpu_multi_slice(10, 2, 2, 1, C.byref(lo), C.byref(hi)) == pkg.binding.EINVAL
+
+
+def test_async_and_multi_fail_loudly_without_gpu(pkg):
+    """No device: the multi-device handle refuses to come up as a whole, and there is no context to be asynchronous on."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.CudaError):
+        pkg.MultiContext([0, 1])
