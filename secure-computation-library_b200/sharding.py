@@ -99,11 +99,15 @@ def gather_shards(local, shard: Shard, n_units: int, group=None, align: int = 1)
         return local
     counts = [shard_range(n_units, shard.world, r, align).count for r in range(shard.world)]
     pad = max(counts)
-    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    buf[: local.shape[0]] = local
+    # gloo (several ranks sharing one GPU, or the CPU tests) moves host tensors; NCCL device tensors
+    via_host = local.is_cuda and dist.get_backend(group) == "gloo"
+    src = local.cpu() if via_host else local
+    buf = torch.zeros((pad,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    buf[: src.shape[0]] = src
     out = [torch.empty_like(buf) for _ in range(shard.world)]
     dist.all_gather(out, buf, group=group)
-    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+    res = torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+    return res.to(local.device) if via_host else res
 
 
 def sum_over_ranks(value: int, device=None, group=None) -> int:
@@ -113,6 +117,8 @@ def sum_over_ranks(value: int, device=None, group=None) -> int:
 
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return int(value)
+    if dist.get_backend(group) == "gloo":
+        device = None
     t = torch.tensor([int(value)], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t.item())

@@ -26,11 +26,19 @@ def main():
     sh = pkg.sharding
     B = pkg.binding
     rank, world, local_rank = sh.dist_env()
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-    ctx = pkg.Context(local_rank)
+    # one GPU per rank under NCCL; with fewer GPUs than ranks (a one-GPU box) the ranks share devices and the
+    # collectives go through gloo -- the per-rank PRG offsets, the peer-memory gather (cudaIpc between processes) and
+    # the multi-device handle are exercised all the same
+    ndev = torch.cuda.device_count()
+    my_dev = local_rank % ndev
+    torch.cuda.set_device(my_dev)
+    if ndev >= world:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", my_dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = pkg.Context(my_dev)
     ctx.use_torch_stream()
-    dev = torch.device("cuda", local_rank)
+    dev = torch.device("cuda", my_dev)
 
     # ---- batch-sharded share / reconstruct
     field, t, n, N = 61, 15, 32, 100003
@@ -133,7 +141,7 @@ def main():
     # ---- one process, one handle over all the GPUs (sclgpu_mctx): rank 0 drives, the others wait
     dist.barrier()
     if rank == 0:
-        m = pkg.MultiContext(list(range(world)))
+        m = pkg.MultiContext([r % ndev for r in range(world)])
         Nm = 50001
         secrets = port.vector_random(61, "secrets", 0, Nm)
         assert np.array_equal(m.random("secrets", 0, Nm), secrets)
@@ -152,7 +160,7 @@ def main():
         m.close()
     dist.barrier()
     if rank == 0:
-        print(f"DIST_GPU_OK world={world}")
+        print(f"DIST_GPU_OK world={world} gpus={min(ndev, world)} backend={dist.get_backend()}")
     ctx.close()
     dist.destroy_process_group()
 

@@ -1187,9 +1187,11 @@ def test_async_host_calls(ctx, orc):
 
 # ------------------------------------------------------------------ several GPUs, NCCL
 def test_multi_gpu_nccl():
-    """tests/dist_gpu_worker.py under torchrun, one process per visible GPU (needs >= 2): batch-sharded
-    share / reconstruct with per-rank PRG offsets, error counts summed over ranks, and C5's row-sharded
-    mat-vec with its all-gather, all against the oracle."""
+    """tests/dist_gpu_worker.py under torchrun: batch-sharded share / reconstruct with per-rank PRG offsets, error counts
+    summed over ranks, C5's row-sharded mat-vec with its all-gather, both peer-memory gathers, the multi-device handle --
+    all against the oracle.  One process per visible GPU over NCCL when there are at least two; on a one-GPU box two
+    ranks share the GPU (collectives over gloo, peer memory through cudaIpc between the two processes), so the N > 1
+    path is exercised on every box."""
     import os
     import subprocess
     import sys
@@ -1197,10 +1199,9 @@ def test_multi_gpu_nccl():
     import torch
 
     g = torch.cuda.device_count()
-    if g < 2:
-        pytest.skip("one GPU visible")
+    world = min(g, 8) if g >= 2 else 2
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(g, 8)}",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(repo, "tests", "dist_gpu_worker.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
