@@ -299,25 +299,37 @@ cudaError_t share_recover61_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_share_recover61<kSrGroups, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_share_recover61<kSrGroups, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_share_recover61<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_share_recover61<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
   return e;
 }
 
+template <int G, int RW>
+static void sr_launch(cudaStream_t st, int sm_count, const AesKey& key, const RecBasis61& basis, const uint32_t* d_t0,
+                      const uint4* bm, uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
+                      uint64_t* d_shares, const uint64_t* d_rec_in, uint64_t* d_rec_out, uint32_t dependent, const GatherDst& gd) {
+  const uint64_t tiles = (N + 127) / 128;
+  const int grid = (int)std::min<uint64_t>((tiles + G - 1) / G, (uint64_t)sm_count);
+  k_share_recover61<G, RW><<<grid, 128 * G + 32 * RW, kSrDynSmem, st>>>(key, basis, d_t0, bm, first_block, d_secrets, N, t, n,
+                                                                        d_shares, d_rec_in, d_rec_out, dependent, gd);
+}
+
+// rec_warps: 4 (default) or 8; + 100 selects the four-share-group form (measurement only)
 cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int rec_warps, const AesKey& key, const RecBasis61& basis,
                                    const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
                                    const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
                                    const uint64_t* d_rec_in, uint64_t* d_rec_out, const GatherDst* gather) {
   GatherDst gd{};
   if (gather) gd = *gather;
-  const uint64_t tiles = (N + 127) / 128;
-  const int grid = (int)std::min<uint64_t>((tiles + kSrGroups - 1) / kSrGroups, (uint64_t)sm_count);
   const uint32_t dependent = (d_rec_in == d_shares) ? 1u : 0u;
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
-  if (rec_warps == 4) {
-    k_share_recover61<kSrGroups, 4><<<grid, 128 * kSrGroups + 128, kSrDynSmem, st>>>(
-        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd);
-  } else {
-    k_share_recover61<kSrGroups, 8><<<grid, 128 * kSrGroups + 256, kSrDynSmem, st>>>(
-        key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd);
+  switch (rec_warps) {
+    case 8: sr_launch<kSrGroups, 8>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
+    case 104: sr_launch<4, 4>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
+    case 108: sr_launch<4, 8>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
+    default: sr_launch<kSrGroups, 4>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
   }
   return cudaGetLastError();
 }

@@ -808,7 +808,7 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
         for (uint32_t ii = 0; ii < kLdRows; ++ii) {
           const uint32_t rr = h * kLdRows + ii, r = p * kPassRows + rr;
           E y;
-          if constexpr (EB == 8) y = tc_combine(v + 8 * ii);
+          if constexpr (EB == 8) y = (ACOLS == 64) ? tc_combine24(v + 8 * ii) : tc_combine(v + 8 * ii);  // 24-bit limbs with two K tiles
           else y = tc_combine127(v + 16 * ii);
           if (r < n_checks) bad = bad || !F::eq(y, chk[rr]);
           else if (r == n_checks) result = y;

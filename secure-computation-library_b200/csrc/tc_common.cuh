@@ -108,6 +108,17 @@ __device__ __forceinline__ uint64_t tc_combine(const uint32_t* v) {
   return (uint64_t)r0 | ((uint64_t)r1 << 32);
 }
 
+// The same recombination for accumulators of up to 24 bits (K = 256 bytes per row: 256 * 255^2 < 2^24, the
+// reconstruction kernels with more than 16 Fp61 shares per row).  There p45 * 2^32 alone can reach 2^64, so its bits
+// from 29 up are folded first (2^61 = 1): R < 2^32 + 2^48 + 2^61 + 2^61 + 2^19 < 2^63 for ANY limb values below 2^24.
+__device__ __forceinline__ uint64_t tc_combine24(const uint32_t* v) {
+  const uint32_t p01 = v[0] + (v[1] << 8), p23 = v[2] + (v[3] << 8);  // < 2^32 (v < 2^24 - 2^17)
+  const uint32_t p45 = v[4] + (v[5] << 8), p67 = v[6] + (v[7] << 8);
+  const uint64_t R = (uint64_t)p01 + ((uint64_t)p23 << 16) + ((uint64_t)(p45 & 0x1FFFFFFFu) << 32) + (uint64_t)(p45 >> 29) +
+                     ((uint64_t)(p67 & 0x1FFFu) << 48) + (uint64_t)(p67 >> 13);
+  return F61::from_raw(R);
+}
+
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(

@@ -739,6 +739,30 @@ def test_recover_p_packets_non_canonical_words(ctx, orc, field, t, n, N):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("field,t", [(61, 7), (61, 15), (61, 20), (61, 31), (127, 7), (127, 15)])
+def test_reconstruction_extreme_limbs(ctx, port, field, t):
+    """Largest byte-limb sums through the tensor-core reconstruction kernels: every share p - 1 (the sharing of the
+    constant polynomial p - 1: all bytes 0xff but the top one), and sharings of random secrets with a zero polynomial
+    tail scaled to p - 1.  With more than 16 Fp61 shares per row the accumulators reach 24 bits (two K tiles); the
+    recombination must still be exact."""
+    N, n = 257, 2 * t + 1
+    pm1 = (1 << field) - 2
+    sh = port.from_ints([pm1] * (N * n), field).reshape((N, n) + (() if field == 61 else (2,)))
+    out, err, nd = ctx.recover_d(field, sh, t)
+    w_out, w_err, w_nd = port.recover_d(field, sh, t)
+    assert nd == w_nd == 0 and np.array_equal(out, w_out) and np.array_equal(err, w_err)
+    assert np.array_equal(ctx.recover_p(field, sh), port.recover_p(field, sh))
+    assert np.array_equal(ctx.recover_p(field, sh[:, : min(n, 32 if field == 61 else 16)]),
+                          port.recover_p(field, sh[:, : min(n, 32 if field == 61 else 16)]))
+    # one share of every sharing replaced by 0 / by 1: flagged (or not) exactly as the oracle says
+    sh2 = sh.copy()
+    sh2.reshape(N, n, -1)[::2, t + 1] = 0
+    sh2.reshape(N, n, -1)[1::2, 0, 0] = 1
+    out, err, nd = ctx.recover_d(field, sh2, t)
+    w_out, w_err, w_nd = port.recover_d(field, sh2, t)
+    assert nd == w_nd and np.array_equal(out, w_out) and np.array_equal(err, w_err)
+
+
 @pytest.mark.parametrize("field", [61, 127])
 def test_recover_d_degenerate_thresholds(ctx, pkg, port, field):
     """t = 0: the reference's own size check (n_given >= d + t) lets d + 1 > n_given through and then reads one share
