@@ -51,10 +51,13 @@ __device__ __forceinline__ uint64_t rot61(uint64_t acc, int s) {  // acc * 2^s m
 
 // GROUPS share groups of 4 warps + RWARPS reconstruction warps.  Fp61, t <= 15, n <= 32, party-major planes:
 // share (j, i) at out[i * N + j].  rec_in: planes [n][N] to reconstruct (== out for the dependent mode).
-template <int GROUPS, int RWARPS>
+// TCREC: the reconstruction as a byte-limb product on the tensor core (k_recover_d_tc's formulation: the 8n share bytes
+// of a secret as one A row in tensor memory, the limbs of lambda_i * 2^(8a) as B, g_rdimg) instead of IMAD chains.
+template <int GROUPS, int RWARPS, bool TCREC>
 __global__ void __launch_bounds__(128 * GROUPS + 32 * RWARPS, 1)
 k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ RecBasis61 basis,
-                  const uint32_t* __restrict__ g_t0, const uint4* __restrict__ g_bmat, uint64_t first_block,
+                  const uint32_t* __restrict__ g_t0, const uint4* __restrict__ g_bmat, const uint4* __restrict__ g_rdimg,
+                  uint64_t first_block,
                   const uint64_t* __restrict__ secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* out,
                   const uint64_t* rec_in, uint64_t* __restrict__ rec_out, uint32_t dependent,
                   const __grid_constant__ GatherDst gather) {
@@ -63,7 +66,9 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
   static_assert(RWARPS % 4 == 0, "share warp w must sit on tensor-memory lane quarter w % 4");
   constexpr uint32_t kThreads = kRecThreads + 128 * GROUPS;
   constexpr uint32_t PCOLS = 64, kColsPerGroup = 32u + PCOLS, kPassParties = 8, kLdParties = 4;
-  static_assert(GROUPS * kColsPerGroup <= 512, "tensor memory has 512 columns");
+  constexpr uint32_t kRecACols = 64, kRecDCols = 16;  // TCREC: 256 share bytes per lane, one 16-column accumulator
+  static_assert(GROUPS * kColsPerGroup + (TCREC ? kRecACols + kRecDCols : 0u) <= 512, "tensor memory has 512 columns");
+  static_assert(!TCREC || RWARPS == 4, "the tensor-core reconstruction is one group of four warps");
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const uint32_t dyn = smem_u32(dyn_smem);
   const uint32_t tbase = aes_table_base(dyn_smem);
@@ -71,14 +76,22 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
   // control block: GROUPS mbarriers | GROUPS tile counters | TMEM base address
   const uint32_t ctl = b_base + kTcBmatBytes;
   const uint32_t done0 = ctl + 64u;            // u32 per group: warps of that group that have stored a tile
-  const uint32_t tmem_slot = ctl + 96u;
-  if (ctl + 128u > dyn + kSrDynSmem) __trap();
+  const uint32_t tmem_slot = ctl + 96u, mbar_rec = ctl + 48u;
+  // TCREC: the reconstruction's B image (two K tiles of 16 rows x 128 bytes) in the free shared memory below the tables
+  const uint32_t brec = (dyn + 1023u) & ~1023u;
+  if (ctl + 128u > dyn + kSrDynSmem || brec + 4096u > tbase) __trap();
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   aes_fill_tables(tbase, g_t0);
   for (uint32_t e = tid; e < kTcBmatBytes / 16; e += kThreads) {
     const uint4 w = __ldg(g_bmat + e);
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+  }
+  if constexpr (TCREC) {
+    for (uint32_t e = tid; e < 256u; e += kThreads) {  // 2 x 2 KiB: rows 0..15 of each K tile of the image
+      const uint4 w = __ldg(g_rdimg + (e >> 7) * (kTcRdKTileBytes / 16u) + (e & 127u));
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(brec + e * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
@@ -89,6 +102,7 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ctl + 8u * i) : "memory");
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 4u * i), "r"(0u) : "memory");
     }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_rec) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -139,7 +153,23 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
       if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(done0 + 4u * g), "r"(1u) : "memory");
       ++published;
     };
-    for (uint64_t tile = (uint64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += tile_step) {
+    // Tiles of this group.  IMAD-reconstruction forms: strided over the grid (the reconstruction warps follow the same
+    // order).  Tensor-core form: a CONTIGUOUS range, so that a thread's consecutive tiles are consecutive 256-counter
+    // groups of the PRG and the group state can be carried over (prg_group_cached: 5 lookups per tile instead of 27).
+    uint64_t tile_begin, tile_end, tile_inc;
+    if constexpr (TCREC) {
+      const uint64_t gi = (uint64_t)blockIdx.x * GROUPS + g, n_groups = (uint64_t)gridDim.x * GROUPS;
+      tile_begin = gi * tiles / n_groups;
+      tile_end = (gi + 1u) * tiles / n_groups;
+      tile_inc = 1;
+    } else {
+      tile_begin = (uint64_t)blockIdx.x * GROUPS + g;
+      tile_end = tiles;
+      tile_inc = tile_step;
+    }
+    PrgGroupCache gcache;
+    gcache.tag = ~0ull;
+    for (uint64_t tile = tile_begin; tile < tile_end; tile += tile_inc) {
       const uint64_t j = tile * 128u + gt;
       const bool valid = j < N;
       const uint64_t jj = valid ? j : N - 1;  // tail lanes recompute the last secret (never stored)
@@ -152,13 +182,15 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
       } else {
         PrgGroup grp;
         uint64_t gid = ctr0 >> 8;
-        prg_group(key, lanebase, ctr0, grp);
+        if constexpr (TCREC) prg_group_cached(key, lanebase, ctr0, grp, gcache);
+        else prg_group(key, lanebase, ctr0, grp);
 #pragma unroll 1
         for (uint32_t b = 0; b < nblk; ++b) {
           const uint64_t ctr = ctr0 + b;
           if ((ctr >> 8) != gid) {  // crossed a 256-block group: at most once per secret
             gid = ctr >> 8;
-            prg_group(key, lanebase, ctr, grp);
+            if constexpr (TCREC) prg_group_cached(key, lanebase, ctr, grp, gcache);
+            else prg_group(key, lanebase, ctr, grp);
           }
           uint32_t o0, o1, o2, o3;
           prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
@@ -203,6 +235,75 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
       ++produced;
     }
     if (dependent && published < produced) publish();
+  } else if constexpr (TCREC) {
+    // ================================================================ reconstruction group on the tensor core
+    // Thread = secret = tensor-memory lane.  Per 128-secret tile: the n shares of the secret go into the lane's A row
+    // (two shares per tcgen05.st; the loads were requested one tile ahead, under the previous tile's MMAs and epilogue),
+    // one elected thread issues ceil(8n / 32) MMAs (M = 128, N = 16, K = 32) against the limb
+    // image of the Lagrange coefficients, and the 8 limbs of the secret come back with one tcgen05.ld.  Pipelined mode
+    // only (the planes of another batch): the prefetch would run ahead of a tile this launch has yet to store.
+    const uint32_t a_rec = tmem + GROUPS * kColsPerGroup, d_rec = a_rec + kRecACols;
+    const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
+    const uint32_t ksteps = (n * 8u + 31u) / 32u;
+    uint32_t ph = 0;
+    uint64_t sh[32];  // the next tile's shares: requested right after this tile's MMAs are issued
+    auto load_tile = [&](const uint64_t* src) {
+#pragma unroll
+      for (uint32_t u = 0; u < 32u; ++u)
+        if (u < n) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(sh[u]) : "l"(src + (uint64_t)u * N));
+    };
+    // this CTA's tiles: the contiguous ranges of its share groups, i.e. one contiguous range
+    const uint64_t n_groups = (uint64_t)gridDim.x * GROUPS;
+    const uint64_t cta_lo = (uint64_t)blockIdx.x * GROUPS * tiles / n_groups;
+    const uint64_t cta_hi = ((uint64_t)blockIdx.x + 1u) * GROUPS * tiles / n_groups;
+    if (cta_lo < cta_hi) {
+      const uint64_t j0 = cta_lo * 128u + tid;
+      load_tile(rec_in + (j0 < N ? j0 : N - 1));
+    }
+    for (uint64_t tile = cta_lo; tile < cta_hi; ++tile) {
+      const uint64_t j = tile * 128u + tid;
+#pragma unroll
+      for (uint32_t c = 0; c < 16u; ++c)
+        if (2u * c < n)  // CTA-uniform; an odd n leaves a stale word in the last pair: its B rows are zero
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_rec + lane_off + 4u * c),
+                       "r"((uint32_t)sh[2 * c]), "r"((uint32_t)(sh[2 * c] >> 32)), "r"((uint32_t)sh[2 * c + 1]),
+                       "r"((uint32_t)(sh[2 * c + 1] >> 32))
+                       : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"((uint32_t)GROUPS + 1u) : "memory");
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (uint32_t ks = 0; ks < ksteps; ++ks)
+          tc_mma_ts(d_rec, a_rec + ks * 8u, tc_desc(brec + (ks >> 2) * 2048u + (ks & 3u) * 32u), tc_idesc(kRecDCols), ks);
+        tc_commit(mbar_rec);
+      }
+      if (tile + 1u < cta_hi) {  // the next tile's planes: in flight under this tile's MMAs and epilogue
+        const uint64_t jn = (tile + 1u) * 128u + tid;
+        load_tile(rec_in + (jn < N ? jn : N - 1));
+      }
+      mbar_wait(mbar_rec, ph);
+      ph ^= 1u;
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(d_rec + lane_off)
+                   : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      const uint64_t r = tc_combine24(v);
+      if (j < N) {
+        if (gather.count == 0) {
+          rec_out[j] = r;
+        } else {
+#pragma unroll
+          for (uint32_t g = 0; g < 8u; ++g)
+            if (g < gather.count) gather.dst[g][j] = r;
+        }
+      }
+    }
   } else {
     // ================================================================ reconstruction warps (shamirRecoverP)
     // A 128-secret tile is reconstructed by a pair of warps, two secrets per thread through 128-bit loads, eight
@@ -296,41 +397,50 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
 static constexpr int kSrGroups = 5;
 
 cudaError_t share_recover61_prepare() {
-  cudaError_t e = cudaFuncSetAttribute(k_share_recover61<kSrGroups, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_share_recover61<kSrGroups, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_share_recover61<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_share_recover61<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
+  cudaError_t e = cudaSuccess;
+#define SCLGPU_SR_ATTR(G, RW, TC) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_share_recover61<G, RW, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrDynSmem);
+  SCLGPU_SR_ATTR(kSrGroups, 4, false)
+  SCLGPU_SR_ATTR(kSrGroups, 8, false)
+  SCLGPU_SR_ATTR(4, 4, false)
+  SCLGPU_SR_ATTR(4, 8, false)
+  SCLGPU_SR_ATTR(4, 4, true)
+#undef SCLGPU_SR_ATTR
   return e;
 }
 
-template <int G, int RW>
+template <int G, int RW, bool TC>
 static void sr_launch(cudaStream_t st, int sm_count, const AesKey& key, const RecBasis61& basis, const uint32_t* d_t0,
-                      const uint4* bm, uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n,
-                      uint64_t* d_shares, const uint64_t* d_rec_in, uint64_t* d_rec_out, uint32_t dependent, const GatherDst& gd) {
+                      const uint4* bm, const uint4* rdimg, uint64_t first_block, const uint64_t* d_secrets, uint64_t N, uint32_t t,
+                      uint32_t n, uint64_t* d_shares, const uint64_t* d_rec_in, uint64_t* d_rec_out, uint32_t dependent,
+                      const GatherDst& gd) {
   const uint64_t tiles = (N + 127) / 128;
   const int grid = (int)std::min<uint64_t>((tiles + G - 1) / G, (uint64_t)sm_count);
-  k_share_recover61<G, RW><<<grid, 128 * G + 32 * RW, kSrDynSmem, st>>>(key, basis, d_t0, bm, first_block, d_secrets, N, t, n,
-                                                                        d_shares, d_rec_in, d_rec_out, dependent, gd);
+  k_share_recover61<G, RW, TC><<<grid, 128 * G + 32 * RW, kSrDynSmem, st>>>(key, basis, d_t0, bm, rdimg, first_block, d_secrets, N, t, n,
+                                                                            d_shares, d_rec_in, d_rec_out, dependent, gd);
 }
 
-// rec_warps: 4 (default) or 8; + 100 selects the four-share-group form (measurement only)
-cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int rec_warps, const AesKey& key, const RecBasis61& basis,
-                                   const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
+// variant: 4 (default) / 8 reconstruction warps beside five share groups; 104 / 108 the same beside four share groups;
+// 204 four share groups + the tensor-core reconstruction group (needs d_rdimg and the pipelined mode)
+cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int variant, const AesKey& key, const RecBasis61& basis,
+                                   const uint32_t* d_t0, const void* d_bmat, const void* d_rdimg, uint64_t first_block,
                                    const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
                                    const uint64_t* d_rec_in, uint64_t* d_rec_out, const GatherDst* gather) {
   GatherDst gd{};
   if (gather) gd = *gather;
   const uint32_t dependent = (d_rec_in == d_shares) ? 1u : 0u;
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
-  switch (rec_warps) {
-    case 8: sr_launch<kSrGroups, 8>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
-    case 104: sr_launch<4, 4>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
-    case 108: sr_launch<4, 8>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
-    default: sr_launch<kSrGroups, 4>(st, sm_count, key, basis, d_t0, bm, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd); break;
+  const uint4* rd = reinterpret_cast<const uint4*>(d_rdimg);
+  if (variant == 204 && (dependent || rd == nullptr)) variant = 4;
+#define SCLGPU_SR_ARGS st, sm_count, key, basis, d_t0, bm, rd, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd
+  switch (variant) {
+    case 8: sr_launch<kSrGroups, 8, false>(SCLGPU_SR_ARGS); break;
+    case 104: sr_launch<4, 4, false>(SCLGPU_SR_ARGS); break;
+    case 108: sr_launch<4, 8, false>(SCLGPU_SR_ARGS); break;
+    case 204: sr_launch<4, 4, true>(SCLGPU_SR_ARGS); break;
+    default: sr_launch<kSrGroups, 4, false>(SCLGPU_SR_ARGS); break;
   }
+#undef SCLGPU_SR_ARGS
   return cudaGetLastError();
 }
 

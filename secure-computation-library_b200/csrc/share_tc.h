@@ -46,8 +46,8 @@ struct GatherDst {
 cudaError_t share_recover61_prepare();
 // d_rec_in == d_shares: reconstruct the sharings produced by this launch (tile by tile, as they are stored);
 // otherwise d_rec_in holds another batch of N sharings in the same party-major [n][N] layout.
-cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int rec_warps, const AesKey& key, const RecBasis61& basis,
-                                   const uint32_t* d_t0, const void* d_bmat, uint64_t first_block,
+cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int variant, const AesKey& key, const RecBasis61& basis,
+                                   const uint32_t* d_t0, const void* d_bmat, const void* d_rdimg, uint64_t first_block,
                                    const uint64_t* d_secrets, uint64_t N, uint32_t t, uint32_t n, uint64_t* d_shares,
                                    const uint64_t* d_rec_in, uint64_t* d_rec_out, const GatherDst* gather = nullptr);
 
