@@ -7,9 +7,10 @@ A "step" is one pass of the hot path over one batch of synthetic secrets:
 Workload at N=1: BASELINE configs[1] -- Mersenne-61, n=32, t=15, 2^26 secrets.
 
   value   : secrets/s, secrets resident in HBM, shares written to and read back from HBM (party-major planes),
-            CUDA events, max over ranks.  Schedule: ONE persistent launch per step (k_share_recover61): the share
-            groups produce batch k while reconstruction warps of the same CTAs reconstruct batch k-1 from the other
-            plane buffer (the share kernel is bound by the SM's shared-memory/ALU pipes, the reconstruction by HBM).
+            CUDA events, max over ranks.  Schedule: ONE persistent launch per step (k_share_recover61): four share
+            groups produce batch k while a reconstruction group of the same CTAs reconstructs batch k-1 from the other
+            plane buffer, both on the tensor cores (the share side is bound by the SM's shared-memory/ALU pipes, the
+            reconstruction by HBM).
             K shares and K reconstructions run inside the timed region.  `schedules` holds the same step as two
             kernels back to back on one stream, as two kernels on two streams, and as one launch that reconstructs
             the very tiles it stores; each verified.
@@ -529,7 +530,8 @@ def run_b200(args):
     weak = {"ms_per_step": prim_ms, "value": world * NW / (prim_ms * 1e-3)}
     schedules = {
         "one_launch_pipelined": {"ms_per_step": prim_ms, "value": world * NW / (prim_ms * 1e-3), "launches_per_step": 1,
-                                 "kernel": "k_share_recover61<5,4>: share(batch k) + recoverP(batch k-1); this is `value`"},
+                                 "kernel": "k_share_recover61<4,4,tc>: four tcgen05 share groups + a reconstruction group on the tensor core; "
+                                           "share(batch k) + recoverP(batch k-1); this is `value`"},
         "one_launch_same_batch": {"ms_per_step": fused_ms, "value": world * NW / (fused_ms * 1e-3), "launches_per_step": 1,
                                   "kernel": "k_share_recover61<5,4>, reconstruction of the tiles the launch itself stores"},
         "two_streams_pipelined": {"ms_per_step": pipe_ms, "value": world * NW / (pipe_ms * 1e-3), "launches_per_step": 2,
@@ -634,7 +636,7 @@ def run_b200(args):
         share_kernel = {"0": "k_share61<15>", "1": "k_share61_tc", "2": "k_share_tcm<F61,4,1,64>"}.get(
             os.environ.get("SCLGPU_SHARE_TC", "3"), "k_share_tcm<F61,5,1,64>")
         # the step IS one kernel: its CUDA-event time is ms_per_step, its algorithmic bytes the whole 528 B per secret
-        dominant = "k_share_recover61<5,4>"
+        dominant = "k_share_recover61<4,4,tc>"
         dom_gbs = (ALGO_BYTES_SHARE + ALGO_BYTES_RECOVER) * N / (prim_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:

@@ -246,11 +246,13 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
     const uint32_t lane_off = ((warp & 3u) * 32u) << 16;
     const uint32_t ksteps = (n * 8u + 31u) / 32u;
     uint32_t ph = 0;
-    uint64_t sh[32];  // the next tile's shares: requested right after this tile's MMAs are issued
+    // the next tile's shares, as the 32-bit words tcgen05.st takes (a load can land in the registers the store reads)
+    uint32_t w[64];
     auto load_tile = [&](const uint64_t* src) {
 #pragma unroll
       for (uint32_t u = 0; u < 32u; ++u)
-        if (u < n) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(sh[u]) : "l"(src + (uint64_t)u * N));
+        if (u < n)
+          asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(w[2 * u]), "=r"(w[2 * u + 1]) : "l"(src + (uint64_t)u * N));
     };
     // this CTA's tiles: the contiguous ranges of its share groups, i.e. one contiguous range
     const uint64_t n_groups = (uint64_t)gridDim.x * GROUPS;
@@ -266,10 +268,24 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
       for (uint32_t c = 0; c < 16u; ++c)
         if (2u * c < n)  // CTA-uniform; an odd n leaves a stale word in the last pair: its B rows are zero
           asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_rec + lane_off + 4u * c),
-                       "r"((uint32_t)sh[2 * c]), "r"((uint32_t)(sh[2 * c] >> 32)), "r"((uint32_t)sh[2 * c + 1]),
-                       "r"((uint32_t)(sh[2 * c + 1] >> 32))
+                       "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
                        : "memory");
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      // the stores have read their registers: the next tile's planes are requested now, in flight under this tile's
+      // barrier, MMAs and epilogue; the tile after that is pulled into L2 (two 128-byte lines per thread)
+      if (tile + 1u < cta_hi) {
+        const uint64_t jn = (tile + 1u) * 128u + tid;
+        load_tile(rec_in + (jn < N ? jn : N - 1));
+      }
+      if (tile + 2u < cta_hi) {
+#pragma unroll
+        for (uint32_t h = 0; h < 2u; ++h) {
+          const uint32_t line = tid + 128u * h;  // 32 planes x 8 lines of 16 secrets
+          const uint64_t e = (tile + 2u) * 128u + (line & 7u) * 16u;
+          if ((line >> 3) < n && e < N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_in + (uint64_t)(line >> 3) * N + e));
+        }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"((uint32_t)GROUPS + 1u) : "memory");
       if (tid == 0) {
@@ -277,10 +293,6 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
         for (uint32_t ks = 0; ks < ksteps; ++ks)
           tc_mma_ts(d_rec, a_rec + ks * 8u, tc_desc(brec + (ks >> 2) * 2048u + (ks & 3u) * 32u), tc_idesc(kRecDCols), ks);
         tc_commit(mbar_rec);
-      }
-      if (tile + 1u < cta_hi) {  // the next tile's planes: in flight under this tile's MMAs and epilogue
-        const uint64_t jn = (tile + 1u) * 128u + tid;
-        load_tile(rec_in + (jn < N ? jn : N - 1));
       }
       mbar_wait(mbar_rec, ph);
       ph ^= 1u;
