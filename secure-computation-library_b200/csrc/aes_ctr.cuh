@@ -30,6 +30,10 @@ struct AesKey {
 #ifndef SCLGPU_AES_FMA_ADDR
 #define SCLGPU_AES_FMA_ADDR 0
 #endif
+// final round through 8-bit loads of S[x] and FMA-pipe joins (1) or T-table words joined by byte-permutes (0)
+#ifndef SCLGPU_AES_LAST_U8
+#define SCLGPU_AES_LAST_U8 1
+#endif
 
 static constexpr uint32_t kPrgNonceLo = 0x89ABCDEFu;  // PRG_NONCE, prg.h:34-36
 static constexpr uint32_t kPrgNonceHi = 0x01234567u;
@@ -230,11 +234,29 @@ __device__ __forceinline__ void prg_group_cached(const AesKey& key, uint32_t lan
   g.u3 = c.p3 ^ aes_t<0, 0>(t3, lanebase);
 }
 
+// S[byte K of w], zero-extended: byte 1 of the lane's T0 entry (T0[x] = (2s, s, s, 3s))
+template <int K>
+__device__ __forceinline__ uint32_t aes_sbox(uint32_t w, uint32_t lanebase) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1+1];" : "=r"(v) : "r"(aes_addr<K>(w, lanebase)));
+  return v;
+}
+// b0 | b1 << 8 | b2 << 16 | b3 << 24 for bytes b* < 256, as three IMADs (k8, k16: 2^8, 2^16 as run-time values)
+__device__ __forceinline__ uint32_t aes_join4(const AesKey& key, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  uint32_t lo, hi, r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(b1), "r"(key.k8), "r"(b0));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(b3), "r"(key.k8), "r"(b2));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(key.k16), "r"(lo));
+  return r;
+}
+
 // rounds R0..9 and the final round on state (s0..s3) = output of round R0-1
+// low == false: output words 0 and 1 are not wanted (keystream block 0 of an Fp61 sharing: slot 0 of the draw is
+// replaced by the secret, shamir.h:56-57) -- their eight final-round lookups are skipped and o0, o1 are left untouched
 template <int R0>
 __device__ __forceinline__ void aes128_tail(const AesKey& key, uint32_t lanebase, uint32_t s0, uint32_t s1,
                                             uint32_t s2, uint32_t s3, uint32_t& o0, uint32_t& o1,
-                                            uint32_t& o2, uint32_t& o3) {
+                                            uint32_t& o2, uint32_t& o3, bool low = true) {
 #pragma unroll
   for (int r = R0; r < 10; ++r) {
     const uint32_t t0 = aes_tk<0, 0>(key, s0, lanebase) ^ aes_tk<1, 1>(key, s1, lanebase) ^ aes_tk<2, 2>(key, s2, lanebase) ^
@@ -250,12 +272,23 @@ __device__ __forceinline__ void aes128_tail(const AesKey& key, uint32_t lanebase
     s2 = t2;
     s3 = t3;
   }
+#if SCLGPU_AES_LAST_U8
+  // final round (SubBytes + ShiftRows + AddRoundKey): S[x] is byte 1 of the T0 entry, read zero-extended by an 8-bit
+  // load; the four bytes of an output word are joined by integer multiply-adds with RUN-TIME multipliers (FMA pipe),
+  // so the ALU pipe -- co-critical with the shared-memory pipe in the fused kernels -- sees one XOR per word
+  // instead of three byte-permutes and the XOR.
+#define SCLGPU_AES_LAST2(w0, w1, w2, w3)                                                                   \
+  aes_join4(key, aes_sbox<0>(w0, lanebase), aes_sbox<1>(w1, lanebase), aes_sbox<2>(w2, lanebase), aes_sbox<3>(w3, lanebase))
+#else
   // final round: S[x] sits in byte 0 of T2/T3, byte 1 of T0/T3, byte 2 of T0/T1, byte 3 of T1/T2
 #define SCLGPU_AES_LAST2(w0, w1, w2, w3)                                                          \
   __byte_perm(__byte_perm(aes_tk<2, 0>(key, w0, lanebase), aes_tk<3, 1>(key, w1, lanebase), 0x0050),          \
               __byte_perm(aes_tk<0, 2>(key, w2, lanebase), aes_tk<1, 3>(key, w3, lanebase), 0x7200), 0x7610)
-  o0 = SCLGPU_AES_LAST2(s0, s1, s2, s3) ^ key.rk[40];
-  o1 = SCLGPU_AES_LAST2(s1, s2, s3, s0) ^ key.rk[41];
+#endif
+  if (low) {
+    o0 = SCLGPU_AES_LAST2(s0, s1, s2, s3) ^ key.rk[40];
+    o1 = SCLGPU_AES_LAST2(s1, s2, s3, s0) ^ key.rk[41];
+  }
   o2 = SCLGPU_AES_LAST2(s2, s3, s0, s1) ^ key.rk[42];
   o3 = SCLGPU_AES_LAST2(s3, s0, s1, s2) ^ key.rk[43];
 #undef SCLGPU_AES_LAST2
@@ -264,13 +297,13 @@ __device__ __forceinline__ void aes128_tail(const AesKey& key, uint32_t lanebase
 // keystream block whose counter has low 32 bits ctr_lo and lies in group g
 __device__ __forceinline__ void prg_block_grouped(const AesKey& key, uint32_t lanebase, const PrgGroup& g,
                                                   uint32_t ctr_lo, uint32_t& o0, uint32_t& o1, uint32_t& o2,
-                                                  uint32_t& o3) {
+                                                  uint32_t& o3, bool low = true) {
   const uint32_t t0 = aes_t<0, 0>(ctr_lo ^ key.rk[0], lanebase) ^ g.k0;
   const uint32_t s0 = aes_tk<0, 0>(key, t0, lanebase) ^ g.u0;
   const uint32_t s1 = aes_tk<3, 3>(key, t0, lanebase) ^ g.u1;
   const uint32_t s2 = aes_t<2, 2>(t0, lanebase) ^ g.u2;
   const uint32_t s3 = aes_t<1, 1>(t0, lanebase) ^ g.u3;
-  aes128_tail<3>(key, lanebase, s0, s1, s2, s3, o0, o1, o2, o3);
+  aes128_tail<3>(key, lanebase, s0, s1, s2, s3, o0, o1, o2, o3, low);
 }
 
 // keystream block `ctr` of the PRG (prg.cc:82-84): plaintext = LE64(ctr) || LE64(nonce)

@@ -40,13 +40,14 @@
 using namespace sclgpu;
 
 // ------------------------------------------------------------------ context
+static constexpr int kMaxPipes = 4;
 struct sclgpu_ctx {
   int device = 0;
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   cudaStream_t stream = nullptr;      // user stream for _dev entry points
-  cudaStream_t pipe[2] = {nullptr, nullptr};  // host-pointer pipelines
-  cudaEvent_t pipe_ev[2] = {nullptr, nullptr};
+  cudaStream_t pipe[kMaxPipes] = {};  // host-pointer pipelines (share / recoverP use up to kMaxPipes, the others two)
+  cudaEvent_t pipe_ev[kMaxPipes] = {};
   uint32_t* d_t0 = nullptr;           // AES T0 table (256 words)
   int* d_flag = nullptr;              // lagrange "zero denominator" flag
   unsigned long long* d_count = nullptr;  // recover_d error counter
@@ -175,15 +176,38 @@ static bool env_flag(const char* name) {
 }
 
 static int env_int(const char* name, int dflt) {
+  // the cache holds what the ENVIRONMENT says (set or not), never a caller's default: two call sites may ask for the
+  // same variable with different defaults (SCLGPU_SR_WARPS: same-batch and pipelined mode)
   static std::mutex mu;
-  static std::map<std::string, int> seen;
+  static std::map<std::string, std::pair<bool, int>> seen;
   std::lock_guard<std::mutex> lock(mu);
   auto it = seen.find(name);
-  if (it != seen.end()) return it->second;
-  const char* e = getenv(name);
-  const int v = e ? atoi(e) : dflt;
-  seen.emplace(name, v);
-  return v;
+  if (it == seen.end()) {
+    const char* e = getenv(name);
+    it = seen.emplace(name, std::make_pair(e != nullptr, e ? atoi(e) : 0)).first;
+  }
+  return it->second.first ? it->second.second : dflt;
+}
+
+// Depth and chunk size of the share / recoverP host pipelines.  A chunk's chain is small copy -> kernels -> big copy
+// (share: secrets up, shares down; recoverP: shares up, secrets down).  When a share and a reconstruction run at the
+// same time (sclgpu_*_async), the SMALL copy of one pipeline queues on the copy engine behind the BIG copies of the
+// other.  Measured on B200 (2^25 secrets, n = 32, duplex, GB/s each way): 2 x 256 MiB 46.7, 3 x 128 43.9, 4 x 128 43.7,
+// 4 x 64 41.1, 4 x 32 39.1 -- fewer, larger chunks win (a fixed cost of about 0.3 ms per chunk and direction), so the
+// defaults stay at two chunks of 256 MiB in flight; the knobs remain for other hosts (DESIGN.md 8a').
+static int host_pipes() {
+  return std::min(std::max(env_int("SCLGPU_HOST_PIPES", 2), 1), kMaxPipes);
+}
+static uint64_t host_chunk_bytes() {
+  return (uint64_t)std::min(std::max(env_int("SCLGPU_HOST_CHUNK_MB", 256), 1), 1024) << 20;
+}
+static cudaError_t sync_pipes(sclgpu_ctx* ctx) {
+  cudaError_t first = cudaSuccess;
+  for (int i = 0; i < kMaxPipes; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->pipe[i]);
+    if (first == cudaSuccess) first = e;
+  }
+  return first;
 }
 
 // ------------------------------------------------------------ launch helpers
@@ -251,7 +275,7 @@ extern "C" int sclgpu_init(int device, sclgpu_ctx** out) {
             cudaMalloc(&ctx->d_flag, sizeof(int)) == cudaSuccess &&
             cudaMalloc(&ctx->d_count, sizeof(unsigned long long)) == cudaSuccess &&
             cudaMalloc(&ctx->d_partial, kMaxPartials * 16) == cudaSuccess;
-  for (int i = 0; i < 2 && ok; ++i) {
+  for (int i = 0; i < kMaxPipes && ok; ++i) {
     ok = cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming) == cudaSuccess;
   }
@@ -279,7 +303,7 @@ extern "C" void sclgpu_destroy(sclgpu_ctx* ctx) {
   for (auto& pb : ctx->pool)
     if (pb.first) cudaMemset(pb.first, 0, pb.second);
   for (auto& pb : ctx->pool) cudaFree(pb.first);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kMaxPipes; ++i) {
     if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
     if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
   }
@@ -433,8 +457,7 @@ struct PoolScope {
     if (g_pool_ctx) {
       // error paths: nothing enqueued by the call -- kernels, async copies into the caller's buffers, staged copies --
       // outlives it (on the success path the streams are already idle and this costs nothing)
-      cudaStreamSynchronize(g_pool_ctx->pipe[0]);
-      cudaStreamSynchronize(g_pool_ctx->pipe[1]);
+      for (int i = 0; i < kMaxPipes; ++i) cudaStreamSynchronize(g_pool_ctx->pipe[i]);
       g_pool_ctx->stager.drain();
     }
     g_pool_ctx = nullptr;

@@ -24,7 +24,11 @@
 //   * planes staged by cp.async.bulk into a 3 x 16 KiB shared-memory ring + 4 consumer warps: 13.4 ms -- the bulk
 //     writes and the LDS re-reads both go through the shared-memory pipe the AES already saturates (the loader
 //     alone cost +1.0 ms, LDS + arithmetic +1.4 ms);
-//   * the two kernels on two streams: 12.8 ms.
+//   * the two kernels on two streams: 12.8 ms;
+//   * homogeneous groups (round 2): no reconstruction group -- every group shares a tile, then reconstructs one on the
+//     tensor core inside its own 96 tensor-memory columns, which lets a FIFTH group fit: 13.07 ms (planes loaded 16 at a
+//     time), 16.6 ms (all 32 at once: spills), 13.5 ms with four groups, against 12.28 ms for <4,4,tc>: the plane loads
+//     cannot be requested a tile ahead (no registers beside the AES state), so each group waits for them in line.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -181,23 +185,18 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %3};" ::"r"(a_lane), "r"(s0), "r"(s1), "r"(0u) : "memory");
       } else {
         PrgGroup grp;
-        uint64_t gid = ctr0 >> 8;
         if constexpr (TCREC) prg_group_cached(key, lanebase, ctr0, grp, gcache);
         else prg_group(key, lanebase, ctr0, grp);
+        // the block of this secret (if any; nblk <= 8) that opens the next 256-counter group
+        const uint32_t cross = 256u - ((uint32_t)ctr0 & 255u), c_lo = (uint32_t)ctr0;
 #pragma unroll 1
         for (uint32_t b = 0; b < nblk; ++b) {
-          const uint64_t ctr = ctr0 + b;
-          if ((ctr >> 8) != gid) {  // crossed a 256-block group: at most once per secret
-            gid = ctr >> 8;
-            if constexpr (TCREC) prg_group_cached(key, lanebase, ctr, grp, gcache);
-            else prg_group(key, lanebase, ctr, grp);
+          if (b == cross) {  // at most once per secret
+            if constexpr (TCREC) prg_group_cached(key, lanebase, ctr0 + b, grp, gcache);
+            else prg_group(key, lanebase, ctr0 + b, grp);
           }
-          uint32_t o0, o1, o2, o3;
-          prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
-          if (b == 0) {
-            o0 = s0;
-            o1 = s1;
-          }
+          uint32_t o0 = s0, o1 = s1, o2, o3;  // block 0: coefficient 0 is the secret, the keystream words are not computed
+          prg_block_grouped(key, lanebase, grp, c_lo + b, o0, o1, o2, o3, b != 0);
           __syncwarp();
           // keystream block b = K bytes [16b, 16b+16) of the row = TMEM columns 4b..4b+3 of this lane
           asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");

@@ -401,21 +401,14 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
     if (t != 0) {
       PrgGroup grp;
       const uint32_t b0 = (EB == 16) ? 1u : 0u;
-      uint64_t gid = (ctr0 + b0) >> 8;
       prg_group(key, lanebase, ctr0 + b0, grp);
+      // the block of this secret (if any; nblk <= 8) that opens the next 256-counter group
+      const uint32_t cross = b0 + 256u - ((uint32_t)(ctr0 + b0) & 255u), c_lo = (uint32_t)ctr0;
 #pragma unroll 1
       for (uint32_t b = b0; b < nblk; ++b) {
-        const uint64_t ctr = ctr0 + b;
-        if ((ctr >> 8) != gid) {  // crossed a 256-block group: at most once per secret
-          gid = ctr >> 8;
-          prg_group(key, lanebase, ctr, grp);
-        }
-        uint32_t o0, o1, o2, o3;
-        prg_block_grouped(key, lanebase, grp, (uint32_t)ctr, o0, o1, o2, o3);
-        if (EB == 8 && b == 0) {
-          o0 = s0;
-          o1 = s1;
-        }
+        if (b == cross) prg_group(key, lanebase, ctr0 + b, grp);  // at most once per secret
+        uint32_t o0 = s0, o1 = s1, o2, o3;  // Fp61 block 0: coefficient 0 is the secret, the keystream words are not computed
+        prg_block_grouped(key, lanebase, grp, c_lo + b, o0, o1, o2, o3, !(EB == 8 && b == 0));
         __syncwarp();
         // keystream block b = K bytes [16b, 16b+16) of the row = TMEM columns 4b..4b+3 of this lane
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lane + 4u * b), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
