@@ -24,11 +24,14 @@
 
 namespace sclgpu {
 
-static constexpr uint32_t kSynMaxT = 10;           // 3t+1 <= 31: the warp kernel's range
-static constexpr uint32_t kSynMaxPoints = 3 * kSynMaxT + 1;
+static constexpr uint32_t kSynMaxT = 10;     // 3t+1 <= 31: the range of the warp-per-sharing elimination kernel
+static constexpr uint32_t kSynMaxTBig = 55;  // 3t+1 <= 166: the range of the CTA-per-sharing one (recover_c_big.cuh)
 
 // consts: [0, np) nodes a_i | [np, 2np) w_i | [2np, 3np) 1 / w_i | then the (t+1) x (t+1) coefficient matrix
-template <class F>
+// MAXT bounds the per-thread arrays (local memory: they are indexed dynamically).  MAXT = kSynMaxT serves 3t+1 <= 31,
+// MAXT = kSynMaxTBig everything the CTA kernel takes; the host launches the latter with one CTA per SM so that the
+// threads' arrays (7 / 15 KiB each for Fp61 / Fp127 at t = 55 / 39) stay in L2.
+template <class F, uint32_t MAXT>
 __global__ void __launch_bounds__(128)
 k_recover_c_syndrome(const typename F::E* __restrict__ in, uint64_t stride_i, uint64_t stride_j, uint32_t t,
                      const typename F::E* __restrict__ consts, typename F::E* __restrict__ f_out,
@@ -36,6 +39,7 @@ k_recover_c_syndrome(const typename F::E* __restrict__ in, uint64_t stride_i, ui
                      const unsigned long long* __restrict__ n_pending, uint32_t* __restrict__ pending2,
                      unsigned long long* __restrict__ n_pending2) {
   typedef typename F::E E;
+  constexpr uint32_t kSynMaxT = MAXT, kSynMaxPoints = 3 * MAXT + 1;  // shadow the namespace constants: this kernel's bounds
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   E* sm = reinterpret_cast<E*>(dyn_smem);
   const uint32_t m = t + 1u, np = 3u * t + 1u, n_const = 3u * np + m * m;
@@ -53,21 +57,18 @@ k_recover_c_syndrome(const typename F::E* __restrict__ in, uint64_t stride_i, ui
     E r[kSynMaxPoints];
 #pragma unroll 1
     for (uint32_t i = 0; i < np; ++i) r[i] = src[(uint64_t)i * stride_i];
-    // ---- syndromes
+    // ---- syndromes: node by node, the running power in a register (S is the only array touched in the inner loop)
     E S[2 * kSynMaxT];
-    {
-      E v[kSynMaxPoints];
 #pragma unroll 1
-      for (uint32_t i = 0; i < np; ++i) v[i] = F::mul(W[i], r[i]);
+    for (uint32_t k = 0; k < 2u * t; ++k) S[k] = F::zero();
+#pragma unroll 1
+    for (uint32_t i = 0; i < np; ++i) {
+      E pw = F::mul(W[i], r[i]);
+      const E a = A[i];
 #pragma unroll 1
       for (uint32_t k = 0; k < 2u * t; ++k) {
-        E s = F::zero();
-#pragma unroll 1
-        for (uint32_t i = 0; i < np; ++i) {
-          s = F::add(s, v[i]);
-          v[i] = F::mul(v[i], A[i]);
-        }
-        S[k] = s;
+        S[k] = F::add(S[k], pw);
+        pw = F::mul(pw, a);
       }
     }
     // ---- inversion-free Berlekamp-Massey: C(x) <- b C(x) - d x^mm B(x)
@@ -177,8 +178,15 @@ k_recover_c_syndrome(const typename F::E* __restrict__ in, uint64_t stride_i, ui
         for (uint32_t rr = 0; rr < m; ++rr) {
           const E* row = COEF + rr * m;
           typename F::Acc acc = F::acc_zero();
+          uint32_t terms = 0;
 #pragma unroll 1
-          for (uint32_t k = 0; k < m; ++k) F::mac(acc, r[k], row[k]);  // m <= 11 terms: no fold needed
+          for (uint32_t k = 0; k < m; ++k) {
+            F::mac(acc, r[k], row[k]);
+            if (++terms == F::ACC_TERMS - 1) {  // the lazy accumulator holds ACC_TERMS products (m can reach 56 here)
+              F::acc_fold(acc);
+              terms = 0;
+            }
+          }
           fo[rr] = F::acc_reduce(acc);
         }
         // ---- verification against the ORIGINAL shares: disagreements exactly at the positions found

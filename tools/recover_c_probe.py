@@ -48,3 +48,21 @@ for n2, k_err in ((16, 5), (31, 10), (31, 3)):
     ms = timeit(lambda: ctx.recover_c_dev(61, sh2, N2, n2, fo2, eo2, st2, B.PARTY_MAJOR))
     ok = bool(torch.equal(fo2[:, 0], sec2)) and int(st2.sum().item()) == 0
     print(f"n={n2} t={t2}: {k_err} corrupted shares in EVERY sharing: {ms:.3f} ms  {N2 / ms / 1e3:.1f} M sharings/s  ok={ok}")
+
+# more than 32 points: the CTA-per-sharing kernel's range (run once with SCLGPU_RECOVER_C_NOSYN=1 for the elimination alone)
+for n3, k_err, lgN in ((64, 21, 13), (64, 3, 13), (166, 55, 11)):
+    t3 = (n3 - 1) // 3
+    N3 = 1 << lgN
+    sec3 = torch.empty(N3, dtype=torch.int64, device="cuda")
+    sh3 = torch.empty((n3, N3), dtype=torch.int64, device="cuda")
+    ctx.random_dev(61, "secrets", 0, N3, sec3)
+    ctx.shamir_share_dev(61, sec3, N3, t3, n3, "rc", 0, sh3, B.PARTY_MAJOR)
+    for i in range(k_err):
+        sh3[(3 * i + 1) % (3 * t3 + 1)] ^= (7 + i)
+    fo3 = torch.empty((N3, 3 * t3 + 1), dtype=torch.int64, device="cuda")
+    eo3 = torch.empty((N3, t3 + 1), dtype=torch.int64, device="cuda")
+    st3 = torch.empty(N3, dtype=torch.uint8, device="cuda")
+    ms = timeit(lambda: ctx.recover_c_dev(61, sh3, N3, n3, fo3, eo3, st3, B.PARTY_MAJOR), reps=2)
+    ok = bool(torch.equal(fo3[:, 0], sec3)) and int(st3.sum().item()) == 0
+    print(f"n={n3} t={t3}: {k_err} corrupted shares in EVERY one of 2^{lgN} sharings: {ms:.3f} ms  {N3 / ms:.1f} k sharings/s  ok={ok}"
+          f"  nosyn={os.environ.get('SCLGPU_RECOVER_C_NOSYN', '0')}")
