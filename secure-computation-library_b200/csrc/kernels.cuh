@@ -1327,6 +1327,51 @@ k_matvec61_chunks(const uint64_t* __restrict__ A, uint64_t n_chunks, uint32_t ch
   }
 }
 
+// The same sweep with ROUNDS x 4 KiB per chunk (a chunk still lies inside one row: cols a multiple of 512 * ROUNDS), the
+// column offset carried from chunk to chunk instead of a 64-bit modulo per chunk, and the 32 lane sums joined by three
+// warp-wide integer reductions (REDUX) over 21-bit limbs instead of five shuffle + modular-add levels: about a fifth
+// fewer instructions per byte than k_matvec61_chunks.  MINB: resident CTAs per SM the register budget is set for --
+// with 4 (64 registers) the loads of a chunk really are in flight together; at 32 registers ptxas serialises them.
+// Measured at 8192 x 8192, L2 flushed before every call, one call per event pair (tools/matvec_probe.py):
+// k_matvec61_chunks 0.109 ms, this kernel at 32 registers 0.105, at 64 registers 0.0965 (16 loads in flight at 120
+// registers: the same).
+template <int ROUNDS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_matvec61_sweep(const uint64_t* __restrict__ A, uint64_t n_chunks, uint32_t chunks_per_row,
+                 const uint64_t* __restrict__ x, uint64_t* __restrict__ partial) {
+  constexpr uint32_t CH = kMatvecChunk * ROUNDS;  // 16-byte units per chunk
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const ulonglong2* A2 = reinterpret_cast<const ulonglong2*>(A);
+  const ulonglong2* x2 = reinterpret_cast<const ulonglong2*>(x);
+  uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t xoff = (uint32_t)(q % chunks_per_row);
+  const uint32_t step = (uint32_t)(warps % chunks_per_row);
+  for (; q < n_chunks; q += warps) {
+    const ulonglong2* src = A2 + q * CH + lane;
+    const ulonglong2* xs = x2 + (uint64_t)xoff * CH + lane;
+    F61::Acc acc = F61::acc_zero();  // 16 * ROUNDS <= 32 products: inside the bound of the lazy accumulator
+    ulonglong2 a[8 * ROUNDS];  // every load of the chunk is requested before the first product
+#pragma unroll
+    for (int k = 0; k < 8 * ROUNDS; ++k)
+      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a[k].x), "=l"(a[k].y) : "l"(src + 32 * k));
+#pragma unroll
+    for (int k = 0; k < 8 * ROUNDS; ++k) {
+      const ulonglong2 xv = __ldg(xs + 32 * k);
+      F61::mac(acc, a[k].x, xv.x);
+      F61::mac(acc, a[k].y, xv.y);
+    }
+    const uint64_t s = F61::acc_reduce(acc);  // < 2^61
+    const uint32_t t0 = __reduce_add_sync(0xffffffffu, (uint32_t)s & 0x1FFFFFu);          // 32 * 2^21 = 2^26
+    const uint32_t t1 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 21) & 0x1FFFFFu);
+    const uint32_t t2 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 42));              // 32 * 2^19 = 2^24
+    if (lane == 0)  // t2 * 2^42 = (t2 mod 2^19) * 2^42 + (t2 >> 19) * 2^61, and 2^61 = 1: the sum stays below 2^62
+      partial[q] = F61::from_raw((uint64_t)t0 + ((uint64_t)t1 << 21) + ((uint64_t)(t2 & 0x7FFFFu) << 42) + (uint64_t)(t2 >> 19));
+    xoff += step;
+    if (xoff >= chunks_per_row) xoff -= chunks_per_row;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_matvec61_finish(const uint64_t* __restrict__ partial, uint32_t rows, uint32_t chunks_per_row, uint64_t* __restrict__ y) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -39,5 +39,9 @@ for field, rows, inner, cols in [(61, 300, 520, 70), (61, 129, 4100, 33), (61, 2
     A = port.vector_random(field, "mat A", 0, rows * inner).reshape((rows, inner) + shp)
     Bm = port.vector_random(field, "mat B", 7, inner * cols).reshape((inner, cols) + shp)
     assert np.array_equal(ctx.matmul(field, A, Bm), port.matmul(field, A, Bm)), ("matmul", field, rows, inner, cols)
+for rows, cols in [(512, 8192), (1024, 4608), (700, 6144)]:   # long rows: the chunked sweep (8 KiB and 4 KiB chunks) + finish
+    A = port.vector_random(61, "mat A", 0, rows * cols).reshape(rows, cols)
+    x = port.vector_random(61, "vec x", 0, cols)
+    assert np.array_equal(ctx.matvec(61, A, x), port.matvec(61, A, x)), ("matvec", rows, cols)
 ctx.close()
 print("KNOB_CHECK PASSED", {k: v for k, v in os.environ.items() if k.startswith("SCLGPU_")})
