@@ -86,6 +86,12 @@ int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_bl
                       uint64_t n_bytes, uint8_t* out);
 int sclgpu_prg_expand_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
                           uint64_t n_bytes, uint8_t* d_out);
+/* The same keystream (prg.cc:82-84) from the BITSLICED AES-128 kernel (no table lookups: Boyar-Peralta S-box
+ * circuit, 32 blocks per thread) -- the measured comparison arm of the T-table kernels; bit-identical output.
+ * Whole blocks only: n_bytes a multiple of 16 and d_out 16-byte aligned, else SCLGPU_EINVAL.
+ * SCLGPU_PRG_BITSLICED=1 in the environment routes sclgpu_prg_expand[_dev] through it. */
+int sclgpu_prg_expand_bitsliced_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block,
+                                    uint64_t n_bytes, uint8_t* d_out);
 
 /* ---- FF::read / Vector::random / FF::random ---------------------------------
  * from_bytes: FF::read = load LE word then "% p" (ff.h:63-67,

@@ -187,6 +187,10 @@ class Context:
     def prg_expand_dev(self, seed, first_block: int, n_bytes: int, out):
         self._check(self.lib.sclgpu_prg_expand_dev(self._ctx, seed16(seed), first_block, n_bytes, _dp(out)))
 
+    def prg_expand_bitsliced_dev(self, seed, first_block: int, n_bytes: int, out):
+        """The same keystream from the bitsliced AES kernel (whole, aligned blocks): the comparison arm."""
+        self._check(self.lib.sclgpu_prg_expand_bitsliced_dev(self._ctx, seed16(seed), first_block, n_bytes, _dp(out)))
+
     def from_bytes(self, field: int, raw) -> np.ndarray:
         bs = 8 if field == 61 else 16
         src = np.frombuffer(bytes(raw), dtype=np.uint8).copy() if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw, dtype=np.uint8)

@@ -70,7 +70,7 @@ def load() -> C.CDLL:
     _sig(lib, "sclgpu_host_free", _int, _vp, _vp)
     _sig(lib, "sclgpu_memcpy_h2d", _int, _vp, _vp, _vp, C.c_size_t)
     _sig(lib, "sclgpu_memcpy_d2h", _int, _vp, _vp, _vp, C.c_size_t)
-    for suf in ("", "_dev"):
+    for suf in ("", "_dev", "_bitsliced_dev"):
         _sig(lib, "sclgpu_prg_expand" + suf, _int, _vp, _vp, _u64, _u64, _vp)
     for f in ("fp61", "fp127"):
         for suf in ("", "_dev"):

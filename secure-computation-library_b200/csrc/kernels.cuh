@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "aes_ctr.cuh"
+#include "aes_bitsliced.cuh"
 #include "share_tc.h"
 #include "field.cuh"
 

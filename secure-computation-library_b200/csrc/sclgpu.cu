@@ -495,6 +495,7 @@ struct PoolBuf {
 // ------------------------------------------------------------------ guarded wrappers of the entry points above
 // (every extern "C" function goes through guarded(): no C++ exception crosses the ABI)
 extern "C" int sclgpu_prg_expand_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n_bytes, uint8_t* d_out) { return guarded(ctx, [&] { return sclgpu_prg_expand_dev_impl(ctx, seed, first_block, n_bytes, d_out); }); }
+extern "C" int sclgpu_prg_expand_bitsliced_dev(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n_bytes, uint8_t* d_out) { return guarded(ctx, [&] { return sclgpu_prg_expand_bitsliced_dev_impl(ctx, seed, first_block, n_bytes, d_out); }); }
 extern "C" int sclgpu_prg_expand(sclgpu_ctx* ctx, const uint8_t seed[16], uint64_t first_block, uint64_t n_bytes, uint8_t* out) { return guarded(ctx, [&] { return sclgpu_prg_expand_impl(ctx, seed, first_block, n_bytes, out); }); }
 extern "C" int sclgpu_fp61_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, uint64_t* o) { return guarded(ctx, [&] { return sclgpu_fp61_from_bytes_dev_impl(ctx, b, n, o); }); }
 extern "C" int sclgpu_fp127_from_bytes_dev(sclgpu_ctx* ctx, const uint8_t* b, uint64_t n, void* o) { return guarded(ctx, [&] { return sclgpu_fp127_from_bytes_dev_impl(ctx, b, n, o); }); }

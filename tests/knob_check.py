@@ -43,5 +43,8 @@ for rows, cols in [(512, 8192), (1024, 4608), (700, 6144)]:   # long rows: the c
     A = port.vector_random(61, "mat A", 0, rows * cols).reshape(rows, cols)
     x = port.vector_random(61, "vec x", 0, cols)
     assert np.array_equal(ctx.matvec(61, A, x), port.matvec(61, A, x)), ("matvec", rows, cols)
+for seed, first, nbytes in [("prg bench", 0, 1 << 16), ("", 5, 16 * 1000), ("shamir bench", (1 << 32) - 40, 16 * 200), ("k", 31, 48),
+                            ("k", 7, 1001)]:   # util::PRG keystream (with SCLGPU_PRG_BITSLICED: the bitsliced kernel)
+    assert np.array_equal(ctx.prg_expand(seed, first, nbytes), port.prg_next(seed, first, nbytes)), ("prg", seed, first, nbytes)
 ctx.close()
 print("KNOB_CHECK PASSED", {k: v for k, v in os.environ.items() if k.startswith("SCLGPU_")})

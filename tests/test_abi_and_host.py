@@ -172,3 +172,15 @@ def test_async_and_multi_fail_loudly_without_gpu(pkg):
         pytest.skip("GPU present")
     with pytest.raises(pkg.CudaError):
         pkg.MultiContext([0, 1])
+
+
+def test_bitsliced_aes_host_build_vs_oracle():
+    """csrc/aes_bitsliced.cuh compiled for the HOST (g++): the S-box circuit on all 256 inputs and 896 keystream blocks
+    (four seeds, counters across the 2^32 boundary) against the oracle's util::PRG -- the same functions the GPU kernel
+    k_prg_bitsliced runs (tests/cpp/bitsliced_check.cc)."""
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(repo, "tests", "cpp", "_build", "bitsliced_check")
+    r = subprocess.run(["make", "-C", os.path.join(repo, "tests", "cpp"), "_build/bitsliced_check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "BITSLICED_CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -41,6 +41,23 @@ def test_prg_vs_oracle(ctx, orc, nbytes):
     assert np.array_equal(got, orc.prg_next("prg bench", first, nbytes))
 
 
+def test_prg_bitsliced_kernel_vs_oracle(ctx, pkg, port):
+    """sclgpu_prg_expand_bitsliced_dev (k_prg_bitsliced): ranges that start and end inside a 32-counter group, cross the
+    2^32 counter boundary, a single block; whole aligned blocks only."""
+    import torch
+
+    ctx.use_torch_stream()
+    for seed, first, nblk in [("prg bench", 0, 4096), ("", 5, 1000), ("shamir bench", (1 << 32) - 40, 200), ("k", 31, 3), ("k", 64, 1),
+                              ("k", (1 << 63) - 70, 64)]:
+        d = torch.zeros(16 * nblk + 16, dtype=torch.uint8, device="cuda")
+        ctx.prg_expand_bitsliced_dev(seed, first, 16 * nblk, d)
+        got = d.cpu().numpy()
+        assert np.array_equal(got[:16 * nblk], port.prg_next(seed, first, 16 * nblk)), (seed, first, nblk)
+        assert not got[16 * nblk:].any()
+    with pytest.raises(pkg.InvalidArgument):
+        ctx.prg_expand_bitsliced_dev("k", 0, 40, torch.zeros(64, dtype=torch.uint8, device="cuda"))
+
+
 def test_prg_counter_high_word(ctx, port):
     first = (1 << 32) - 3  # crosses the 32-bit boundary of the counter
     assert np.array_equal(ctx.prg_expand("k", first, 160), port.prg_next("k", first, 160))
@@ -946,12 +963,13 @@ def test_share_kernel_paths_vs_oracle(tc):
 
 @pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC",
                                   "SCLGPU_RECOVER_C_FULL", "SCLGPU_RECOVER_C_NOSYN", "SCLGPU_MATVEC_WARP", "SCLGPU_MATVEC_VARIANT=0",
+                                  "SCLGPU_PRG_BITSLICED",
                                   "SCLGPU_NO_KNOB"])
 def test_selectable_kernels_vs_oracle(knob):
     """tests/knob_check.py with one kernel-selection knob set: the first GEMM form, the
     integer-pipe GEMM, the integer-pipe reconstruction kernels, the staged share path, Berlekamp-Welch without the
     error-free fast path / without the syndrome decoder, the one-warp-per-row and the first chunked mat-vec;
-    SCLGPU_NO_KNOB is the same sweep on the defaults."""
+    the bitsliced keystream kernel; SCLGPU_NO_KNOB is the same sweep on the defaults."""
     import os
     import subprocess
     import sys
