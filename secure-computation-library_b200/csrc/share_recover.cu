@@ -189,6 +189,22 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
         else prg_group(key, lanebase, ctr0, grp);
         // the block of this secret (if any; nblk <= 8) that opens the next 256-counter group
         const uint32_t cross = 256u - ((uint32_t)ctr0 & 255u), c_lo = (uint32_t)ctr0;
+        if ((nblk & 1u) == 0u && __all_sync(0xffffffffu, cross >= nblk)) {
+          // TWO blocks per iteration (no group crossing inside this warp's secrets: the usual case): two independent
+          // lookup chains for the scheduler to interleave.  With one block at a time a warp stalls at every round
+          // boundary (XOR tree -> address -> lookup); measured 12.33 -> 11.89 ms for the step on one box.  Four blocks
+          // per iteration: 12.20 ms (the 96-register budget).
+#pragma unroll 1
+          for (uint32_t b = 0; b < nblk; b += 2u) {
+            uint32_t o0 = s0, o1 = s1, o2, o3, q0, q1, q2, q3;  // block 0: coefficient 0 is the secret
+            prg_block_grouped(key, lanebase, grp, c_lo + b, o0, o1, o2, o3, b != 0);
+            prg_block_grouped(key, lanebase, grp, c_lo + b + 1u, q0, q1, q2, q3);
+            __syncwarp();
+            // keystream blocks b, b + 1 = K bytes [16b, 16b + 32) of the row = TMEM columns 4b..4b+7 of this lane
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a_lane + 4u * b),
+                         "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+          }
+        } else
 #pragma unroll 1
         for (uint32_t b = 0; b < nblk; ++b) {
           if (b == cross) {  // at most once per secret
