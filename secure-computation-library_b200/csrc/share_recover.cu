@@ -193,7 +193,7 @@ k_share_recover61(const __grid_constant__ AesKey key, const __grid_constant__ Re
           // TWO blocks per iteration (no group crossing inside this warp's secrets: the usual case): two independent
           // lookup chains for the scheduler to interleave.  With one block at a time a warp stalls at every round
           // boundary (XOR tree -> address -> lookup); measured 12.33 -> 11.89 ms for the step on one box.  Four blocks
-          // per iteration: 12.20 ms (the 96-register budget).
+          // per iteration: 12.20 ms (the 96-register budget); three share groups (128 registers) with four: 12.92 ms.
 #pragma unroll 1
           for (uint32_t b = 0; b < nblk; b += 2u) {
             uint32_t o0 = s0, o1 = s1, o2, o3, q0, q1, q2, q3;  // block 0: coefficient 0 is the secret
