@@ -76,5 +76,10 @@ assert np.array_equal(ctx.matvec(61, A, x)[:8], port.matvec(61, A[:8], x))
 xs = port.vector_random(61, "xs", 0, 9)
 cf = port.vector_random(61, "cf", 0, 50 * 6).reshape(50, 6)
 assert ctx.poly_evaluate(61, cf, xs).shape == (50, 9) and ctx.vandermonde_xs(61, 9, 4, xs).shape == (9, 4)
+# round 2, second session: the bitsliced keystream kernel (ranges inside / across 32-counter groups)
+d_ks = torch.zeros(16 * 300, dtype=torch.uint8, device="cuda")
+ctx.prg_expand_bitsliced_dev("k", 250, 16 * 300, d_ks)
+torch.cuda.synchronize()
+assert np.array_equal(d_ks.cpu().numpy(), port.prg_next("k", 250, 16 * 300))
 ctx.close()
 print("SANITIZE_DRIVER_OK")
