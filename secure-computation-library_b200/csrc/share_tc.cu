@@ -754,10 +754,20 @@ k_recover_d_tc(const uint4* __restrict__ g_bmat, const typename F::E* __restrict
     tc_commit(mbar);
   };
 
+  const uint32_t n_planes = m + n_checks;
   for (uint64_t tile = (uint64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (uint64_t)gridDim.x * GROUPS) {
     const uint64_t j = tile * 128u + gt;
     const bool valid = j < N;
     const E* src = in + (valid ? j : N - 1) * stride_j;
+    if (stride_j == 1) {
+      // party-major planes: the group's NEXT tile is pulled into L2 now (128 * BYTES bytes per plane = BYTES lines of
+      // 128 bytes), so that its loads, a whole tile of MMAs and epilogue later, are L2 hits -- no registers held
+      const uint64_t jn = (tile + (uint64_t)gridDim.x * GROUPS) * 128u;
+      for (uint32_t line = gt; line < n_planes * EB; line += 128u) {
+        const uint64_t e = jn + (uint64_t)(line % EB) * (128u / EB);
+        if (e < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (uint64_t)(line / EB) * stride_i + e));
+      }
+    }
     // the m interpolation shares: all requested before the first is consumed
     E a[kMaxM];
 #pragma unroll
