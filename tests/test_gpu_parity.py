@@ -171,6 +171,31 @@ def test_share_recover_vs_oracle(ctx, orc, field, t, n, N):
     assert np.array_equal(rec, secrets)
 
 
+@pytest.mark.parametrize("first", [0, 1, 7, 8, 250, 255, 256, (1 << 32) - 3, (1 << 40) + 12])
+def test_share_prg_offsets_aligned_and_not(ctx, pkg, port, first):
+    """The fused share kernels draw two keystream blocks per thread and iteration when no secret of a warp crosses a
+    256-counter group (first_block a multiple of the blocks per sharing) and one block at a time otherwise: both loops,
+    with the crossing at every position inside a secret, for the share kernel (both fields, even and odd block counts)
+    and for the single-launch step, against the oracle (shamir.h:52-68 on one PRG, prg.cc:124-146)."""
+    import torch
+
+    for field, t, n, N in [(61, 15, 32, 1500), (61, 7, 16, 700), (61, 4, 9, 300), (127, 7, 16, 700), (127, 4, 11, 260)]:
+        sec = port.vector_random(field, "secrets", 0, N)
+        assert np.array_equal(ctx.shamir_share(field, sec, t, n, "offsets", first), port.shamir_share(field, sec, t, n, "offsets", first)), \
+            (field, t, n, first)
+    ctx.use_torch_stream()
+    N, t, n = 3000, 15, 32
+    sec = port.vector_random(61, "secrets", 0, N)
+    want = port.shamir_share(61, sec, t, n, "offsets", first)
+    d_sec = torch.from_numpy(sec.view(np.int64)).cuda()
+    d_prev = torch.from_numpy(np.ascontiguousarray(want.T).view(np.int64)).cuda()     # the batch to reconstruct: party-major planes
+    d_sh = torch.zeros((n, N), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros(N, dtype=torch.int64, device="cuda")
+    ctx.shamir_share_recover_dev(d_sec, N, t, n, "offsets", first, d_sh, d_out, rec_shares=d_prev)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, want) and np.array_equal(d_out.cpu().numpy().view(np.uint64), sec)
+
+
 def test_share_empty_and_degenerate(ctx, port):
     for field in (61, 127):
         e = port.from_ints([], field).reshape((0,) + (() if field == 61 else (2,)))
