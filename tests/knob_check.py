@@ -9,7 +9,8 @@ import __graft_entry__ as entry
 pkg = entry.load_package()
 o = entry.load_oracle(); port = o.PortOracle()
 ctx = pkg.Context(0)
-for field, t, n, N in [(61, 15, 32, 3000), (61, 2, 5, 777), (127, 7, 16, 1500), (127, 2, 7, 300), (61, 7, 16, 2048)]:
+for field, t, n, N in [(61, 15, 32, 3000), (61, 2, 5, 777), (127, 7, 16, 1500), (127, 2, 7, 300), (61, 7, 16, 2048),
+                       (61, 15, 32, 21001)]:   # the last one: several chunks in the host pipelines when SCLGPU_HOST_CHUNK_MB=1
     sec = port.vector_random(field, "secrets", 0, N)
     sh = ctx.shamir_share(field, sec, t, n, "knobs", 11)
     assert np.array_equal(sh, port.shamir_share(field, sec, t, n, "knobs", 11)), ("share", field, t, n)

@@ -988,21 +988,24 @@ def test_share_kernel_paths_vs_oracle(tc):
 
 @pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC",
                                   "SCLGPU_RECOVER_C_FULL", "SCLGPU_RECOVER_C_NOSYN", "SCLGPU_MATVEC_WARP", "SCLGPU_MATVEC_VARIANT=0",
-                                  "SCLGPU_PRG_BITSLICED",
+                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=4",
+                                  "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=1",
                                   "SCLGPU_NO_KNOB"])
 def test_selectable_kernels_vs_oracle(knob):
     """tests/knob_check.py with one kernel-selection knob set: the first GEMM form, the
     integer-pipe GEMM, the integer-pipe reconstruction kernels, the staged share path, Berlekamp-Welch without the
     error-free fast path / without the syndrome decoder, the one-warp-per-row and the first chunked mat-vec;
-    the bitsliced keystream kernel; SCLGPU_NO_KNOB is the same sweep on the defaults."""
+    the bitsliced keystream kernel, the host pipelines with four / one chunk(s) of 1 MiB in flight; SCLGPU_NO_KNOB is
+    the same sweep on the defaults."""
     import os
     import subprocess
     import sys
 
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
-    name, _, value = knob.partition("=")
-    env[name] = value or "1"
+    for item in knob.split(","):
+        name, _, value = item.partition("=")
+        env[name] = value or "1"
     r = subprocess.run([sys.executable, os.path.join(repo, "tests", "knob_check.py")], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and "KNOB_CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
