@@ -1458,6 +1458,62 @@ k_transpose(const E* __restrict__ in, uint64_t rows, uint64_t cols, E* __restric
   }
 }
 
+// The same transposition when one side is NARROW (a batch of sharings: [n][N] planes <-> SCL's [N][n], n <= 32).  The
+// 32 x 32 tiles above keep 32 - n lanes idle on the narrow side (Fp61: 4.8 TB/s at n = 32, 2.9 at 16, 1.3 at 5).  Here
+// a WARP owns 32 consecutive positions of the long side; the other side of its data is ONE contiguous run of 32 * n
+// elements, so it is moved flat -- lane l takes elements l, l + 32, ... of the run -- with the (position, row) index
+// carried from step to step instead of divided out.  A private slab of shared memory per warp, __syncwarp only.
+// TO_LONG_ROWS: in = [long][n] (runs), out = [n][long] (planes); otherwise the reverse.
+static constexpr uint32_t kNarrowWarps = 4;    // per CTA: 4 slabs of 32 x 33 elements = 33 KiB for Fp61, 66 KiB for Fp127
+
+template <class E, bool TO_LONG_ROWS>
+__global__ void __launch_bounds__(32 * kNarrowWarps)
+k_transpose_narrow(const E* __restrict__ in, uint64_t n_long, uint32_t n, E* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  E* slab = reinterpret_cast<E*>(dyn_smem) + (size_t)wid * 32u * 33u;  // [row i < n][position s < 32], row stride 33
+  const uint64_t warps = (uint64_t)gridDim.x * kNarrowWarps;
+  const uint64_t groups = (n_long + 31u) / 32u;
+  const uint32_t step_i = 32u % n, step_s = 32u / n;
+  for (uint64_t g = (uint64_t)blockIdx.x * kNarrowWarps + wid; g < groups; g += warps) {
+    const uint64_t s0 = g * 32u;
+    const uint32_t cnt = (uint32_t)(n_long - s0 < 32u ? n_long - s0 : 32u);  // positions of this group
+    const uint32_t run = cnt * n;
+    if (TO_LONG_ROWS) {
+      const E* src = in + s0 * n;
+      uint32_t s = lane / n, i = lane % n;
+      for (uint32_t e = lane; e < run; e += 32u) {  // flat, coalesced
+        slab[i * 33u + s] = src[e];
+        i += step_i;
+        s += step_s;
+        if (i >= n) {
+          i -= n;
+          ++s;
+        }
+      }
+      __syncwarp();
+      if (lane < cnt)
+        for (uint32_t r = 0; r < n; ++r) out[(uint64_t)r * n_long + s0 + lane] = slab[r * 33u + lane];
+    } else {
+      if (lane < cnt)
+        for (uint32_t r = 0; r < n; ++r) slab[r * 33u + lane] = in[(uint64_t)r * n_long + s0 + lane];
+      __syncwarp();
+      E* dst = out + s0 * n;
+      uint32_t s = lane / n, i = lane % n;
+      for (uint32_t e = lane; e < run; e += 32u) {
+        dst[e] = slab[i * 33u + s];
+        i += step_i;
+        s += step_s;
+        if (i >= n) {
+          i -= n;
+          ++s;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // [rows][cols][W] -> [cols][rows][W]: the same transposition on W-wide elements
 // (Vector<Array<FF, W>> shares, secret-major <-> party-major).  32 x 32 tiles of
 // up to CW components at a time, contiguous runs of 32*cw elements on both sides.

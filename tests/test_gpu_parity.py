@@ -988,7 +988,7 @@ def test_share_kernel_paths_vs_oracle(tc):
 
 @pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC",
                                   "SCLGPU_RECOVER_C_FULL", "SCLGPU_RECOVER_C_NOSYN", "SCLGPU_MATVEC_WARP", "SCLGPU_MATVEC_VARIANT=0",
-                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=4",
+                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_TRANSPOSE_TILES", "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=4",
                                   "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=1",
                                   "SCLGPU_NO_KNOB"])
 def test_selectable_kernels_vs_oracle(knob):
@@ -1154,7 +1154,9 @@ def test_vandermonde_xs_poly_evaluate_transpose(ctx, pkg, orc, port, field):
         torch.cuda.synchronize()
         assert np.array_equal(d_sm.cpu().numpy().view(np.uint64).reshape(want.shape), want)
         assert np.array_equal(np.swapaxes(d_pm.cpu().numpy().view(np.uint64), 0, 1).reshape(want.shape), want)
-    for rows, cols in ((1, 1), (3, 5), (64, 33), (1000, 17)):
+    # the last eight: one side narrow and the other long -- k_transpose_narrow, both directions, ragged ends
+    for rows, cols in ((1, 1), (3, 5), (64, 33), (1000, 17), (5000, 5), (7, 4097), (32, 1025), (3001, 32), (2049, 1), (1, 5000),
+                       (8, 2000), (16, 3000)):
         A = port.vector_random(field, "tr", 0, rows * cols).reshape((rows, cols) + ((2,) if w == 2 else ()))
         assert np.array_equal(ctx.transpose(field, A), orc.transpose(field, A))
 
