@@ -533,7 +533,7 @@ def run_b200(args):
                                  "kernel": "k_share_recover61<4,4,tc>: four tcgen05 share groups + a reconstruction group on the tensor core; "
                                            "share(batch k) + recoverP(batch k-1); this is `value`"},
         "one_launch_same_batch": {"ms_per_step": fused_ms, "value": world * NW / (fused_ms * 1e-3), "launches_per_step": 1,
-                                  "kernel": "k_share_recover61<5,4>, reconstruction of the tiles the launch itself stores"},
+                                  "kernel": "k_share_recover61<4,4>: four share groups + four IMAD reconstruction warps, reconstruction of the tiles the launch itself stores"},
         "two_streams_pipelined": {"ms_per_step": pipe_ms, "value": world * NW / (pipe_ms * 1e-3), "launches_per_step": 2,
                                   "note": "k_share_tcm || k_recover61_pm: co-residency is up to the block scheduler"},
         "one_stream_back_to_back": {"ms_per_step": seq_ms, "value": world * NW / (seq_ms * 1e-3), "launches_per_step": 2,

@@ -458,7 +458,7 @@ cudaError_t share_recover61_launch(cudaStream_t st, int sm_count, int variant, c
   const uint32_t dependent = (d_rec_in == d_shares) ? 1u : 0u;
   const uint4* bm = reinterpret_cast<const uint4*>(d_bmat);
   const uint4* rd = reinterpret_cast<const uint4*>(d_rdimg);
-  if (variant == 204 && (dependent || rd == nullptr)) variant = 4;
+  if (variant == 204 && (dependent || rd == nullptr)) variant = 104;  // the tensor-core form needs another batch
 #define SCLGPU_SR_ARGS st, sm_count, key, basis, d_t0, bm, rd, first_block, d_secrets, N, t, n, d_shares, d_rec_in, d_rec_out, dependent, gd
   switch (variant) {
     case 8: sr_launch<kSrGroups, 8, false>(SCLGPU_SR_ARGS); break;
