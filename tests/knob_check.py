@@ -47,5 +47,22 @@ for rows, cols in [(512, 8192), (1024, 4608), (700, 6144)]:   # long rows: the c
 for seed, first, nbytes in [("prg bench", 0, 1 << 16), ("", 5, 16 * 1000), ("shamir bench", (1 << 32) - 40, 16 * 200), ("k", 31, 48),
                             ("k", 7, 1001)]:   # util::PRG keystream (with SCLGPU_PRG_BITSLICED: the bitsliced kernel)
     assert np.array_equal(ctx.prg_expand(seed, first, nbytes), port.prg_next(seed, first, nbytes)), ("prg", seed, first, nbytes)
+# the single-launch step (k_share_recover61; form selected by SCLGPU_SR_WARPS): same-batch and pipelined mode
+import torch
+ctx.use_torch_stream()
+for N, t, n, first in [(5000, 15, 32, 16), (777, 7, 16, 3), (130, 2, 5, 0)]:
+    sec = port.vector_random(61, "secrets", 0, N)
+    want = port.shamir_share(61, sec, t, n, "step", first)
+    d_sec = torch.from_numpy(sec.view(np.int64)).cuda()
+    d_sh = torch.zeros((n, N), dtype=torch.int64, device="cuda")
+    d_sh2 = torch.zeros((n, N), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros(N, dtype=torch.int64, device="cuda")
+    ctx.shamir_share_recover_dev(d_sec, N, t, n, "step", first, d_sh, d_out)                       # reconstructs its own tiles
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, want) and np.array_equal(d_out.cpu().numpy().view(np.uint64), sec), ("step", N, t, n)
+    d_out.zero_()
+    ctx.shamir_share_recover_dev(d_sec, N, t, n, "step", first, d_sh2, d_out, rec_shares=d_sh)     # reconstructs another batch
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sh2.cpu().numpy().view(np.uint64).T, want) and np.array_equal(d_out.cpu().numpy().view(np.uint64), sec), ("step2", N, t, n)
 ctx.close()
 print("KNOB_CHECK PASSED", {k: v for k, v in os.environ.items() if k.startswith("SCLGPU_")})

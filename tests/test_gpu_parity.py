@@ -988,14 +988,15 @@ def test_share_kernel_paths_vs_oracle(tc):
 
 @pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC",
                                   "SCLGPU_RECOVER_C_FULL", "SCLGPU_RECOVER_C_NOSYN", "SCLGPU_MATVEC_WARP", "SCLGPU_MATVEC_VARIANT=0",
-                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_TRANSPOSE_TILES", "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=4",
+                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_TRANSPOSE_TILES", "SCLGPU_SR_WARPS=4", "SCLGPU_SR_WARPS=8", "SCLGPU_SR_WARPS=108",
+                                  "SCLGPU_NO_FUSED_STEP", "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=4",
                                   "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=1",
                                   "SCLGPU_NO_KNOB"])
 def test_selectable_kernels_vs_oracle(knob):
     """tests/knob_check.py with one kernel-selection knob set: the first GEMM form, the
     integer-pipe GEMM, the integer-pipe reconstruction kernels, the staged share path, Berlekamp-Welch without the
     error-free fast path / without the syndrome decoder, the one-warp-per-row and the first chunked mat-vec;
-    the bitsliced keystream kernel, the host pipelines with four / one chunk(s) of 1 MiB in flight; SCLGPU_NO_KNOB is
+    the bitsliced keystream kernel, the other forms of the single-launch step and the two-kernel step, the host pipelines with four / one chunk(s) of 1 MiB in flight; SCLGPU_NO_KNOB is
     the same sweep on the defaults."""
     import os
     import subprocess
