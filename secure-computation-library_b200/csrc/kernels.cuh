@@ -1202,6 +1202,58 @@ k_vec_mismatch(const typename F::E* __restrict__ a, const typename F::E* __restr
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
 
+// ==================================================== shamirRecoverP, Fp61, SCL's own layout
+// shamir.h:100-104 on a batch in SCL's [N][n] layout (row j = what shamirSecretShare returned for secret j), read
+// where it lies, n <= 32.  A warp takes 32 consecutive secrets = ONE contiguous run of 32 * n elements, copies it flat
+// (coalesced) into its slab of shared memory -- row stride n | 1, so that the rows can then be read by one lane each
+// without bank conflicts -- and lane l forms the inner product of row l with the Lagrange basis (broadcast reads, lazy
+// 128-bit accumulation: n <= 32 products).  The store is one coalesced line per warp.
+// Measured (B200, 2^25 secrets, n = 32): the strided generic kernel 3.87 ms (every lane reads 16 bytes from its own
+// line), lane-pair products joined by integer REDUX over 16 lanes 2.84 ms, this form 2.14 ms; the plane kernel on
+// party-major input 1.43 ms.
+static constexpr uint32_t kRecSmWarps = 8;
+
+__global__ void __launch_bounds__(32 * kRecSmWarps)
+k_recover61_sm(const uint64_t* __restrict__ in, uint64_t N, uint32_t n, const uint64_t* __restrict__ basis,
+               uint64_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  uint64_t* lam = reinterpret_cast<uint64_t*>(dyn_smem);  // n coefficients, then the slabs
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const uint32_t stride = n | 1u;
+  uint64_t* slab = lam + 32 + (size_t)wid * 32u * 33u;
+  if (threadIdx.x < n) lam[threadIdx.x] = basis[threadIdx.x];
+  __syncthreads();
+  const uint64_t warps = (uint64_t)gridDim.x * kRecSmWarps;
+  const uint64_t n_runs = (N + 31u) / 32u;
+  const uint32_t step_i = 32u % n, step_s = 32u / n;
+  for (uint64_t q = (uint64_t)blockIdx.x * kRecSmWarps + wid; q < n_runs; q += warps) {
+    const uint64_t s0 = q * 32u;
+    const uint32_t cnt = (uint32_t)(N - s0 < 32u ? N - s0 : 32u);
+    const uint32_t run = cnt * n;
+    const uint64_t* src = in + s0 * n;
+    uint32_t s = lane / n, i = lane % n;
+    for (uint32_t e = lane; e < run; e += 32u) {  // flat, coalesced: element e = share i of secret s0 + s
+      uint64_t v;
+      asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(src + e));
+      slab[s * stride + i] = v;
+      i += step_i;
+      s += step_s;
+      if (i >= n) {
+        i -= n;
+        ++s;
+      }
+    }
+    __syncwarp();
+    if (lane < cnt) {
+      const uint64_t* row = slab + lane * stride;
+      F61::Acc acc = F61::acc_zero();
+      for (uint32_t k = 0; k < n; ++k) F61::mac(acc, row[k], lam[k]);  // n <= 32 = the bound of the lazy accumulator
+      out[s0 + lane] = F61::acc_reduce(acc);
+    }
+    __syncwarp();
+  }
+}
+
 // ==================================================== Matrix::multiply(Vector)
 // matrix.h:498-513: y[r] = innerProd(row r, x).  One CTA per row; A is streamed
 // once with coalesced loads (8 bytes of HBM traffic per modmul), x comes from L2.

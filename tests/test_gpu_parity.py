@@ -196,6 +196,28 @@ def test_share_prg_offsets_aligned_and_not(ctx, pkg, port, first):
     assert np.array_equal(d_sh.cpu().numpy().view(np.uint64).T, want) and np.array_equal(d_out.cpu().numpy().view(np.uint64), sec)
 
 
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 8, 16, 31, 32])
+def test_recover_p_secret_major_device_kernel(ctx, pkg, port, n):
+    """sclgpu_fp61_recover_p_dev on SCL's own [N][n] layout (k_recover61_sm: the rows read where they lie, a warp per 32
+    secrets): ragged batch sizes, default and custom nodes / evaluation point, arbitrary canonical words as shares --
+    against the oracle's shamirRecoverP (shamir.h:82-104)."""
+    import torch
+
+    ctx.use_torch_stream()
+    for N in (1, 31, 33, 1000, 4097):
+        sh = port.vector_random(61, "any shares", 7, N * n).reshape(N, n)
+        d_sh = torch.from_numpy(sh.view(np.int64)).cuda()
+        d_out = torch.zeros(N + 2, dtype=torch.int64, device="cuda")
+        ctx.recover_p_dev(61, d_sh, N, n, d_out, pkg.binding.SECRET_MAJOR)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got[:N], port.recover_p(61, sh)) and not got[N:].any(), (n, N)
+        alphas = port.from_ints([5 * i + 2 for i in range(n)], 61)
+        ctx.recover_p_dev(61, d_sh, N, n, d_out, pkg.binding.SECRET_MAJOR, alphas=alphas, x=11)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint64)[:N], port.recover_p(61, sh, alphas=alphas, x=11)), (n, N, "nodes")
+
+
 def test_share_empty_and_degenerate(ctx, port):
     for field in (61, 127):
         e = port.from_ints([], field).reshape((0,) + (() if field == 61 else (2,)))
