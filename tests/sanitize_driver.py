@@ -8,6 +8,7 @@ import __graft_entry__ as entry
 pkg = entry.load_package()
 o = entry.load_oracle(); port = o.PortOracle()
 ctx = pkg.Context(0)
+B = pkg.binding
 for field, t, n, N in [(61, 15, 32, 700), (61, 2, 5, 130), (127, 7, 16, 300), (61, 16, 40, 64)]:
     sec = port.vector_random(field, "secrets", 0, N)
     sh = ctx.shamir_share(field, sec, t, n, "shamir bench", 5)
@@ -81,5 +82,15 @@ d_ks = torch.zeros(16 * 300, dtype=torch.uint8, device="cuda")
 ctx.prg_expand_bitsliced_dev("k", 250, 16 * 300, d_ks)
 torch.cuda.synchronize()
 assert np.array_equal(d_ks.cpu().numpy(), port.prg_next("k", 250, 16 * 300))
+# narrow transpositions (k_transpose_narrow, both directions, ragged ends) and shamirRecoverP on SCL's layout on the device
+for rows, cols in ((3001, 5), (7, 2049), (32, 1025), (1100, 32)):
+    A = port.vector_random(61, "tr", 0, rows * cols).reshape(rows, cols)
+    assert np.array_equal(ctx.transpose(61, A), np.ascontiguousarray(A.T))
+for n_, N_ in ((32, 1001), (5, 333), (16, 64)):
+    sh_ = port.vector_random(61, "any shares", 7, N_ * n_).reshape(N_, n_)
+    d_o = torch.zeros(N_, dtype=torch.int64, device="cuda")
+    ctx.recover_p_dev(61, torch.from_numpy(sh_.view(np.int64)).cuda(), N_, n_, d_o, B.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o.cpu().numpy().view(np.uint64), port.recover_p(61, sh_))
 ctx.close()
 print("SANITIZE_DRIVER_OK")
