@@ -267,7 +267,18 @@ k_share_tcm(const __grid_constant__ AesKey key, const uint32_t* __restrict__ g_t
       tc_mma_ts(acc0 + b * PCOLS, a_tm + ks * 8u, tc_desc(b_base + p * (PCOLS * 128u) + ks * 32u), tc_idesc(PCOLS), ks);
     tc_commit(b ? mbar1 : mbar0);
   };
+  // SCL's own layout as the output (stride_i == 1: the shares of a secret are adjacent): 16-byte stores of two shares
+  // -- a warp's store then touches 32 rows, and half as many of them as 8-byte stores would
+  const bool pair_stores = EB == 8 && stride_i == 1 && (stride_j & 1u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   auto emit = [&](const uint32_t (&v)[32], E* dst, uint32_t first_party) {
+    if constexpr (EB == 8) {
+      if (pair_stores && first_party + kLdParties <= n) {
+#pragma unroll
+        for (uint32_t ii = 0; ii < kLdParties; ii += 2)
+          *reinterpret_cast<ulonglong2*>(dst + ii) = make_ulonglong2(tc_combine(v + 8 * ii), tc_combine(v + 8 * ii + 8));
+        return;
+      }
+    }
     if (first_party + kLdParties <= n) {  // all parties of this load exist (always, when n is a multiple of 4 / 2)
 #pragma unroll
       for (uint32_t ii = 0; ii < kLdParties; ++ii) {

@@ -50,6 +50,14 @@ for seed, first, nbytes in [("prg bench", 0, 1 << 16), ("", 5, 16 * 1000), ("sha
 # the single-launch step (k_share_recover61; form selected by SCLGPU_SR_WARPS): same-batch and pipelined mode
 import torch
 ctx.use_torch_stream()
+for field, N, t, n, first in [(61, 4100, 15, 32, 8), (61, 999, 7, 16, 5), (61, 300, 2, 5, 0), (127, 700, 7, 16, 3)]:   # shares in SCL's layout on the device
+    sec = port.vector_random(field, "secrets", 0, N)
+    want = port.shamir_share(field, sec, t, n, "sm", first)
+    w = 1 if field == 61 else 2
+    d_sm = torch.zeros((N, n, w), dtype=torch.int64, device="cuda")
+    ctx.shamir_share_dev(field, torch.from_numpy(sec.view(np.int64)).cuda(), N, t, n, "sm", first, d_sm, pkg.binding.SECRET_MAJOR)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sm.cpu().numpy().view(np.uint64).reshape(want.shape), want), ("share_dev secret-major", field, t, n)
 for N, t, n, first in [(5000, 15, 32, 16), (777, 7, 16, 3), (130, 2, 5, 0)]:
     sec = port.vector_random(61, "secrets", 0, N)
     want = port.shamir_share(61, sec, t, n, "step", first)

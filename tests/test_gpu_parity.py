@@ -1010,7 +1010,7 @@ def test_share_kernel_paths_vs_oracle(tc):
 
 @pytest.mark.parametrize("knob", ["SCLGPU_MATMUL_V1", "SCLGPU_MATMUL_GENERIC", "SCLGPU_RECOVER_GENERIC", "SCLGPU_SHARE_GENERIC",
                                   "SCLGPU_RECOVER_C_FULL", "SCLGPU_RECOVER_C_NOSYN", "SCLGPU_MATVEC_WARP", "SCLGPU_MATVEC_VARIANT=0",
-                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_TRANSPOSE_TILES", "SCLGPU_SR_WARPS=4", "SCLGPU_SR_WARPS=8", "SCLGPU_SR_WARPS=108",
+                                  "SCLGPU_PRG_BITSLICED", "SCLGPU_TRANSPOSE_TILES", "SCLGPU_SHARE_SM_TRANSPOSE", "SCLGPU_SR_WARPS=4", "SCLGPU_SR_WARPS=8", "SCLGPU_SR_WARPS=108",
                                   "SCLGPU_NO_FUSED_STEP", "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=4",
                                   "SCLGPU_HOST_CHUNK_MB=1,SCLGPU_HOST_PIPES=1",
                                   "SCLGPU_NO_KNOB"])
